@@ -1,0 +1,312 @@
+"""mpi4torch_b200 - B200-native, autodiff-transparent collectives for PyTorch.
+
+API parity with helmholtz-analytics/mpi4torch (reference ``src/__init__.py``):
+``COMM_WORLD``, ``MPI_Communicator`` with ``Allreduce / Bcast_ / Reduce_ /
+Gather / Allgather / Scatter / Alltoall / Isend / Irecv / Wait / Send / Recv``,
+``WaitHandle``, ``JoinDummies``, ``JoinDummiesHandle``, the twelve ``MPI_*``
+reduction constants, ``comm_from_mpi4py`` and
+``deactivate_cuda_aware_mpi_support`` - every op a differentiable graph node
+whose backward is the adjoint communication.  Added on top: ``Reduce_scatter``
+(the true adjoint of ``Allgather``), fused scale/accumulate epilogues
+(``AllreduceFused``), ``Barrier`` and the fused Allreduce->GEMM layer in
+:mod:`mpi4torch_b200.ops`.
+
+There is no MPI underneath.  Ranks are OS processes started by
+``python -m mpi4torch_b200.launch`` (or ``torchrun``); CPU tensors travel over a
+POSIX shared-memory backend, CUDA tensors over hand-written sm_100a kernels
+that read and write peer GPUs' HBM through NVLink 5 / NVSwitch (NVLS multicast
+when the fabric offers it).
+"""
+from __future__ import annotations
+
+import atexit
+import os
+from typing import List, Optional
+
+import torch
+
+from . import _build
+
+_C = _build.load()
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "MPI_MAX",
+    "MPI_MIN",
+    "MPI_SUM",
+    "MPI_PROD",
+    "MPI_LAND",
+    "MPI_BAND",
+    "MPI_LOR",
+    "MPI_BOR",
+    "MPI_LXOR",
+    "MPI_BXOR",
+    "MPI_MINLOC",
+    "MPI_MAXLOC",
+    "WaitHandle",
+    "JoinDummies",
+    "JoinDummiesHandle",
+    "MPI_Communicator",
+    "COMM_WORLD",
+    "comm_from_mpi4py",
+    "deactivate_cuda_aware_mpi_support",
+    "activate_nvlink_transport",
+    "cuda_backend_ready",
+    "has_nvls",
+    "heap_mode",
+]
+
+# The reference's integer op constants (reference csrc/extension.cpp:1424-1435).
+MPI_MAX: int = _C.MPI_MAX
+MPI_MIN: int = _C.MPI_MIN
+MPI_SUM: int = _C.MPI_SUM
+MPI_PROD: int = _C.MPI_PROD
+MPI_LAND: int = _C.MPI_LAND
+MPI_BAND: int = _C.MPI_BAND
+MPI_LOR: int = _C.MPI_LOR
+MPI_BOR: int = _C.MPI_BOR
+MPI_LXOR: int = _C.MPI_LXOR
+MPI_BXOR: int = _C.MPI_BXOR
+MPI_MINLOC: int = _C.MPI_MINLOC
+MPI_MAXLOC: int = _C.MPI_MAXLOC
+
+
+def _bootstrap() -> None:
+    """Attach to the job and (collectively) bring up the CUDA backend.
+
+    Replaces ``MPI_Init_thread`` at import (reference csrc/extension.cpp:1323-1394).
+    """
+    want_cuda = os.environ.get("M4T_CUDA", "1") != "0" and torch.cuda.is_available()
+    device = 0
+    if want_cuda:
+        ndev = torch.cuda.device_count()
+        local_rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if ndev == 0 or (world > 1 and int(os.environ.get("LOCAL_WORLD_SIZE", world)) > ndev):
+            want_cuda = False  # more ranks than GPUs: CPU backend + host staging only
+        else:
+            device = local_rank % ndev
+            torch.cuda.set_device(device)
+    _C.init_world(want_cuda, device)
+
+
+_bootstrapped = False
+
+
+def _ensure_world() -> None:
+    global _bootstrapped
+    if not _bootstrapped:
+        _bootstrap()
+        atexit.register(_C.finalize)
+        _bootstrapped = True
+
+
+def deactivate_cuda_aware_mpi_support() -> None:
+    """Force CUDA tensors through host staging + the CPU shared-memory backend.
+
+    Same role as the reference toggle (reference csrc/extension.cpp:54-59): it is
+    the fallback when the NVLink path must be bypassed, and the "host-staged"
+    comparator in the benchmarks.
+    """
+    _ensure_world()
+    _C.deactivate_cuda_aware_mpi_support()
+
+
+def activate_nvlink_transport() -> None:
+    """Undo :func:`deactivate_cuda_aware_mpi_support`."""
+    _ensure_world()
+    _C.activate_nvlink_transport()
+
+
+def cuda_backend_ready() -> bool:
+    _ensure_world()
+    return _C.cuda_backend_ready()
+
+
+def has_nvls() -> bool:
+    """True when the symmetric heap is bound to an NVSwitch multicast object."""
+    _ensure_world()
+    return _C.has_nvls()
+
+
+def heap_mode() -> str:
+    """'vmm+multicast', 'vmm', 'cudaIpc' or 'none'."""
+    _ensure_world()
+    return _C.heap_mode()
+
+
+@torch.jit.script
+class WaitHandle:
+    """Handle returned by the non-blocking calls (reference ``src/__init__.py:27-40``).
+
+    Internally a list of three tensors: a float64 descriptor (usable as a
+    differentiable dummy), the communication buffer, and the original tensor.
+    """
+
+    def __init__(self, raw_handle: List[torch.Tensor]):
+        self._handle = raw_handle
+
+    @property
+    def dummy(self):
+        """Dummy tensor for :func:`JoinDummies` / :func:`JoinDummiesHandle`."""
+        return self._handle[0]
+
+
+@torch.jit.script
+def JoinDummies(loopthrough: torch.Tensor, dummies: List[torch.Tensor]) -> torch.Tensor:
+    """Pass ``loopthrough`` through and make the DAG depend on ``dummies``.
+
+    Forward is a no-op; in backward the dummies receive zero gradients, which
+    is how program order and cross-rank communication dependencies are encoded
+    (reference ``src/__init__.py:42-67``, ``doc/basic_usage.rst:317-348``).
+    """
+    return torch.ops.mpi4torch_b200.JoinDummies(loopthrough, dummies)
+
+
+@torch.jit.script
+def JoinDummiesHandle(handle: WaitHandle, dummies: List[torch.Tensor]) -> WaitHandle:
+    """:func:`JoinDummies` for a :class:`WaitHandle` (reference ``src/__init__.py:69-87``)."""
+    raw_handle = handle._handle
+    return WaitHandle([torch.ops.mpi4torch_b200.JoinDummies(raw_handle[0], dummies), raw_handle[1], raw_handle[2]])
+
+
+@torch.jit.script
+class MPI_Communicator:
+    """Communicator (reference ``src/__init__.py:89-240``).
+
+    Obtain it from :data:`COMM_WORLD`.  Methods with a trailing underscore are
+    in-place operations: always use their return value.
+    """
+
+    def __init__(self, comm: torch.classes.mpi4torch_b200.Communicator):
+        self._comm = comm
+
+    @property
+    def rank(self) -> int:
+        """Rank of this process in ``[0, size)``."""
+        return self._comm.GetRank()
+
+    @property
+    def size(self) -> int:
+        """Number of processes in the communicator."""
+        return self._comm.GetSize()
+
+    def Allreduce(self, tensor: torch.Tensor, op: int) -> torch.Tensor:
+        """Element-wise reduction over all ranks, result on all ranks.
+
+        All twelve ``MPI_*`` ops are accepted forward (``MPI_MINLOC`` /
+        ``MPI_MAXLOC`` raise: there is no pair dtype); only ``MPI_SUM`` has a
+        backward, which is again an ``Allreduce(MPI_SUM)``.
+        """
+        return self._comm.Allreduce(tensor, op)
+
+    def AllreduceFused(self, tensor: torch.Tensor, op: int, scale: float,
+                       accumulate: Optional[torch.Tensor]) -> torch.Tensor:
+        """``accumulate + scale * Allreduce(tensor, op)`` in ONE kernel.
+
+        The scale (e.g. ``1/size``) and the accumulate run in the collective's
+        epilogue, forward and backward (the backward is the same fused kernel
+        applied to the upstream gradient).
+        """
+        return self._comm.AllreduceFused(tensor, op, scale, accumulate)
+
+    def Bcast_(self, tensor: torch.Tensor, root: int) -> torch.Tensor:
+        """Broadcast ``root``'s tensor in place; backward is ``Reduce_(MPI_SUM)``."""
+        return self._comm.Bcast_(tensor, root)
+
+    def Reduce_(self, tensor: torch.Tensor, op: int, root: int) -> torch.Tensor:
+        """Reduce to ``root`` in place (non-root results are zero-filled);
+        backward (``MPI_SUM`` only) is ``Bcast_``."""
+        return self._comm.Reduce_(tensor, op, root)
+
+    def Gather(self, tensor: torch.Tensor, gatheraxis: int, root: int) -> torch.Tensor:
+        """Concatenate along ``gatheraxis`` in rank order on ``root`` (axis length
+        may differ per rank; off-root the result has extent 0 along the axis)."""
+        return self._comm.Gather(tensor, gatheraxis, root)
+
+    def Allgather(self, tensor: torch.Tensor, gatheraxis: int) -> torch.Tensor:
+        """:meth:`Gather` to all ranks; backward is a reduce-scatter."""
+        return self._comm.Allgather(tensor, gatheraxis)
+
+    def Scatter(self, tensor: torch.Tensor, scatteraxis: int, numelem: int, root: int) -> torch.Tensor:
+        """Split ``root``'s tensor along ``scatteraxis``; this rank receives
+        ``numelem`` rows.  Off-root ``tensor`` only provides dtype and device."""
+        return self._comm.Scatter(tensor, scatteraxis, numelem, root)
+
+    def Alltoall(self, tensor: torch.Tensor, gatheraxis: int, scatteraxis: int, numelem: int) -> torch.Tensor:
+        """Every rank scatters along ``scatteraxis`` and gathers along
+        ``gatheraxis`` (equal axes re-partition one global axis).  One kernel."""
+        return self._comm.Alltoall(tensor, gatheraxis, scatteraxis, numelem)
+
+    def Reduce_scatter(self, tensor: torch.Tensor, op: int, scatteraxis: int, numelem: int) -> torch.Tensor:
+        """Reduce identically shaped tensors and keep ``numelem`` rows of
+        ``scatteraxis`` on this rank (the adjoint of :meth:`Allgather`)."""
+        return self._comm.Reduce_scatter(tensor, op, scatteraxis, numelem)
+
+    def Isend(self, tensor: torch.Tensor, dest: int, tag: int) -> WaitHandle:
+        """Start a non-blocking send."""
+        return WaitHandle(self._comm.Isend(tensor, dest, tag))
+
+    def Irecv(self, tensor: torch.Tensor, source: int, tag: int) -> WaitHandle:
+        """Start a non-blocking receive into ``tensor``; use :meth:`Wait`'s result."""
+        return WaitHandle(self._comm.Irecv(tensor, source, tag))
+
+    def Wait(self, waithandle: WaitHandle) -> torch.Tensor:
+        """Complete a non-blocking operation (each handle exactly once)."""
+        return self._comm.Wait(waithandle._handle)
+
+    def Send(self, tensor: torch.Tensor, dest: int, tag: int) -> torch.Tensor:
+        """Blocking send = ``Wait(Isend(...))`` (reference ``src/__init__.py:234-236``)."""
+        handle = self._comm.Isend(tensor, dest, tag)
+        return self._comm.Wait(handle)
+
+    def Recv(self, tensor: torch.Tensor, source: int, tag: int) -> torch.Tensor:
+        """Blocking receive = ``Wait(Irecv(...))`` (reference ``src/__init__.py:238-240``)."""
+        handle = self._comm.Irecv(tensor, source, tag)
+        return self._comm.Wait(handle)
+
+    def Barrier(self) -> None:
+        """Host barrier over all ranks (control plane only)."""
+        self._comm.Barrier()
+
+    def describe(self) -> str:
+        return self._comm.Describe()
+
+
+def _make_comm_world() -> MPI_Communicator:
+    _ensure_world()
+    return MPI_Communicator(torch.ops.mpi4torch_b200.COMM_WORLD())
+
+
+def __getattr__(name: str):
+    # COMM_WORLD is created on first access (a collective start-up: every rank
+    # touches it, normally at the top of the user script, exactly like the
+    # reference's module-level singleton, src/__init__.py:242-245).  Keeping it
+    # lazy lets tools such as the launcher import the package without joining
+    # a job.
+    if name == "COMM_WORLD":
+        world = _make_comm_world()
+        globals()["COMM_WORLD"] = world
+        return world
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def comm_from_mpi4py(comm) -> MPI_Communicator:
+    """Interop shim for code written against ``mpi4torch.comm_from_mpi4py``.
+
+    There is no MPI underneath this library, so only a communicator that is
+    congruent with the launcher's world (same size and rank) can be converted
+    (reference ``src/__init__.py:247-261`` converts any mpi4py communicator).
+    """
+    try:
+        size, rank = comm.Get_size(), comm.Get_rank()
+    except AttributeError as exc:  # pragma: no cover
+        raise RuntimeError("mpi4py is not available!") from exc
+    world = __getattr__("COMM_WORLD") if "COMM_WORLD" not in globals() else globals()["COMM_WORLD"]
+    if size != world.size or rank != world.rank:
+        raise RuntimeError(
+            "mpi4torch_b200 only supports the world communicator: the mpi4py communicator has "
+            f"rank {rank}/{size} but this process is rank {world.rank}/{world.size}"
+        )
+    return world

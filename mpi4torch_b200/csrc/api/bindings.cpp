@@ -1,0 +1,134 @@
+// Registration: TORCH_LIBRARY custom class + ops (reference csrc/extension.cpp:
+// 1270-1304 uses the legacy torch::RegisterOperators API) and the pybind module
+// that bootstraps the world at import (reference :1396-1436).
+#include <execinfo.h>
+#include <signal.h>
+#include <torch/extension.h>
+#include <torch/library.h>
+#include <unistd.h>
+
+#include "../runtime/cuda_backend.h"
+#include "communicator.h"
+
+namespace m4t {
+
+namespace {
+
+// M4T_DEBUG_SEGV=1: print a native backtrace on SIGSEGV/SIGABRT (no gdb in the image).
+void segv_handler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "[m4t] fatal signal, native backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
+void maybe_install_segv_handler() {
+  if (env_i64("M4T_DEBUG_SEGV", 0)) {
+    signal(SIGSEGV, segv_handler);
+    signal(SIGABRT, segv_handler);
+  }
+}
+
+void init_world(bool want_cuda, int64_t device) {
+  maybe_install_segv_handler();
+  World& w = World::instance();
+  if (want_cuda && !w.cuda_ready()) {
+    w.init_cuda(static_cast<int>(device));
+  }
+}
+
+void deactivate_cuda_aware_mpi_support() {
+  // Reference :54-59 forces host staging for CUDA tensors; same effect here.
+  World::instance().set_host_staging(true);
+}
+
+void activate_nvlink_transport() { World::instance().set_host_staging(false); }
+
+}  // namespace
+
+TORCH_LIBRARY(mpi4torch_b200, m) {
+  m.class_<Communicator>("Communicator")
+      .def("GetRank", &Communicator::GetRank)
+      .def("GetSize", &Communicator::GetSize)
+      .def("Allreduce", &Communicator::Allreduce)
+      .def("AllreduceFused", &Communicator::AllreduceFused)
+      .def("Bcast_", &Communicator::Bcast_)
+      .def("Reduce_", &Communicator::Reduce_)
+      .def("Gather", &Communicator::Gather)
+      .def("Allgather", &Communicator::Allgather)
+      .def("Scatter", &Communicator::Scatter)
+      .def("Alltoall", &Communicator::Alltoall)
+      .def("Reduce_scatter", &Communicator::Reduce_scatter)
+      .def("Isend", &Communicator::Isend)
+      .def("Irecv", &Communicator::Irecv)
+      .def("Wait", &Communicator::Wait)
+      .def("Barrier", &Communicator::Barrier)
+      .def("Describe", &Communicator::Describe)
+      // Only the world communicator exists, so pickling round-trips it by name
+      // (the reference's unpickle test is inverted and always throws, :1292-1294).
+      .def_pickle([](const c10::intrusive_ptr<Communicator>&) -> std::string { return "MPI_COMM_WORLD"; },
+                  [](std::string state) -> c10::intrusive_ptr<Communicator> {
+                    TORCH_CHECK(state == "MPI_COMM_WORLD", "mpi4torch_b200: unknown pickled communicator '", state, "'");
+                    return comm_world();
+                  });
+  m.def("COMM_WORLD", &comm_world);
+  m.def("JoinDummies(Tensor loopthrough, Tensor[] dummies) -> Tensor",
+        [](const Tensor& loopthrough, std::vector<Tensor> dummies) { return JoinDummies(loopthrough, dummies); });
+}
+
+}  // namespace m4t
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  using namespace m4t;
+  m.doc() = "mpi4torch_b200 native core: shared-memory control plane, CPU backend, NVLink/NVSwitch CUDA backend";
+  m.def("init_world", &init_world, py::arg("want_cuda"), py::arg("device") = 0,
+        "Attach to the job (collective) and optionally bring up the CUDA backend on `device`.");
+  m.def("finalize", [] { World::finalize(); });
+  m.def("world_initialised", [] { return World::initialised(); });
+  m.def("deactivate_cuda_aware_mpi_support", &deactivate_cuda_aware_mpi_support);
+  m.def("activate_nvlink_transport", &activate_nvlink_transport);
+  m.def("cuda_backend_ready", [] { return World::instance().cuda_ready(); });
+  m.def("has_nvls", [] { return World::instance().cuda_ready() && World::instance().cuda()->has_nvls(); });
+  m.def("heap_mode", [] {
+    World& w = World::instance();
+    if (!w.cuda_ready()) return std::string("none");
+    switch (w.cuda()->heap().mode()) {
+      case HeapMode::VMM_MULTICAST: return std::string("vmm+multicast");
+      case HeapMode::VMM: return std::string("vmm");
+      default: return std::string("cudaIpc");
+    }
+  });
+  m.def("set_tuning", [](const std::string& key, int64_t value) {
+    World& w = World::instance();
+    TORCH_CHECK(w.cuda_ready(), "CUDA backend not initialised");
+    CudaTuning& t = w.cuda()->tuning();
+    if (key == "oneshot_max_bytes") t.oneshot_max_bytes = value;
+    else if (key == "chunk_bytes") t.chunk_bytes = value;
+    else if (key == "ar_blocks") t.ar_blocks = static_cast<int>(value);
+    else if (key == "oneshot_blocks") t.oneshot_blocks = static_cast<int>(value);
+    else if (key == "slab_blocks") t.slab_blocks = static_cast<int>(value);
+    else if (key == "p2p_blocks") t.p2p_blocks = static_cast<int>(value);
+    else if (key == "force_algo") t.force_algo = static_cast<int>(value);
+    else TORCH_CHECK(false, "unknown tuning key ", key);
+  });
+  m.def("check_device_error", [] {
+    World& w = World::instance();
+    if (w.cuda_ready()) w.cuda()->check_device_error();
+  });
+  // the reference's 12 integer op constants (csrc/extension.cpp:1424-1435)
+  m.attr("MPI_MAX") = py::int_(static_cast<int>(ReduceOp::MAX));
+  m.attr("MPI_MIN") = py::int_(static_cast<int>(ReduceOp::MIN));
+  m.attr("MPI_SUM") = py::int_(static_cast<int>(ReduceOp::SUM));
+  m.attr("MPI_PROD") = py::int_(static_cast<int>(ReduceOp::PROD));
+  m.attr("MPI_LAND") = py::int_(static_cast<int>(ReduceOp::LAND));
+  m.attr("MPI_BAND") = py::int_(static_cast<int>(ReduceOp::BAND));
+  m.attr("MPI_LOR") = py::int_(static_cast<int>(ReduceOp::LOR));
+  m.attr("MPI_BOR") = py::int_(static_cast<int>(ReduceOp::BOR));
+  m.attr("MPI_LXOR") = py::int_(static_cast<int>(ReduceOp::LXOR));
+  m.attr("MPI_BXOR") = py::int_(static_cast<int>(ReduceOp::BXOR));
+  m.attr("MPI_MINLOC") = py::int_(static_cast<int>(ReduceOp::MINLOC));
+  m.attr("MPI_MAXLOC") = py::int_(static_cast<int>(ReduceOp::MAXLOC));
+}

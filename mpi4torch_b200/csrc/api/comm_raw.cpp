@@ -1,0 +1,385 @@
+// Raw (non-differentiable) data paths of the communicator: tensor -> backend
+// routing, metadata exchange, plan construction.  The autograd layer
+// (autograd_ops.cpp) wraps these.
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <numeric>
+
+#include "../runtime/cuda_backend.h"
+#include "communicator.h"
+
+namespace m4t {
+
+namespace {
+
+DType to_dtype(at::ScalarType t) {
+  switch (t) {
+    case at::kByte: return DType::U8;
+    case at::kChar: return DType::I8;
+    case at::kShort: return DType::I16;
+    case at::kInt: return DType::I32;
+    case at::kLong: return DType::I64;
+    case at::kFloat: return DType::F32;
+    case at::kDouble: return DType::F64;
+    case at::kBFloat16: return DType::BF16;
+    case at::kHalf: return DType::F16;
+    case at::kBool: return DType::BOOL;
+    default: break;
+  }
+  throw std::invalid_argument(std::string("mpi4torch_b200: Failure to match torch::ScalarType ") +
+                              c10::toString(t) + " to a transport dtype!");
+}
+
+ReduceOp to_op(int64_t op) {
+  if (op < 0 || op >= static_cast<int64_t>(ReduceOp::kCount))
+    throw std::invalid_argument("mpi4torch_b200: Collective operation not supported!");
+  return static_cast<ReduceOp>(op);
+}
+
+// Decides which transport serves a tensor (reference MPIDeviceHelper,
+// csrc/extension.cpp:61-104): CPU tensors -> shared-memory backend; CUDA
+// tensors -> NVLink backend, or host staging when that is switched off.
+struct Route {
+  Backend* be = nullptr;
+  void* stream = nullptr;
+  bool staged = false;
+  c10::Device device;
+  c10::optional<c10::cuda::CUDAGuard> guard;
+
+  Route(World& w, const Tensor& t) : device(t.device()) {
+    if (t.is_cpu()) {
+      be = &w.cpu();
+    } else if (t.is_cuda()) {
+      if (!w.host_staging() && w.cuda_ready()) {
+        CudaBackend* cb = w.cuda();
+        TORCH_CHECK(t.device().index() == cb->device(), "mpi4torch_b200: tensor lives on cuda:",
+                    static_cast<int>(t.device().index()), " but this rank's communicator is bound to cuda:", cb->device());
+        guard.emplace(t.device());
+        stream = c10::cuda::getCurrentCUDAStream(t.device().index()).stream();
+        be = cb;
+      } else {
+        staged = true;
+        be = &w.cpu();
+      }
+    } else {
+      TORCH_CHECK(false, "mpi4torch_b200: unsupported device ", t.device());
+    }
+  }
+  Tensor to_comm(const Tensor& t) const {
+    Tensor c = t.contiguous();
+    return staged ? c.cpu() : c;
+  }
+  Tensor from_comm(const Tensor& t) const { return staged ? t.to(device) : t; }
+};
+
+int64_t wrap_axis(int64_t axis, int64_t ndim, const char* what) {
+  TORCH_CHECK(ndim > 0, "mpi4torch_b200: ", what, " needs a tensor with at least one dimension");
+  TORCH_CHECK(axis >= -ndim && axis < ndim, "mpi4torch_b200: ", what, " axis ", axis, " out of range for a ", ndim,
+              "-d tensor");
+  return axis < 0 ? axis + ndim : axis;
+}
+
+uint32_t ptr_hash(const void* p) { return static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 0xffffffffu); }
+
+}  // namespace
+
+Communicator::Communicator() : world_(&World::instance()) {
+  rank_ = world_->rank();
+  size_ = world_->size();
+}
+
+c10::intrusive_ptr<Communicator> comm_world() { return c10::make_intrusive<Communicator>(); }
+
+void Communicator::Barrier() {
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  world_->control().barrier();
+}
+
+std::string Communicator::Describe() const {
+  std::ostringstream o;
+  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << world_->job_id() << " | cpu: posix-shm";
+  if (world_->cuda_ready()) o << " | " << world_->cuda()->describe();
+  if (world_->host_staging()) o << " | host staging forced";
+  return o.str();
+}
+
+Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scale, bool has_scale,
+                                   const c10::optional<Tensor>& accumulate) {
+  const ReduceOp op = to_op(op_);
+  const DType dt = to_dtype(input.scalar_type());
+  check_op_dtype(op, dt);
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  Tensor in = r.to_comm(input);
+  Tensor acc;
+  Epilogue epi;
+  epi.scale = scale;
+  epi.has_scale = has_scale;
+  if (accumulate.has_value() && accumulate->defined()) {
+    TORCH_CHECK(accumulate->sizes() == input.sizes() && accumulate->scalar_type() == input.scalar_type() &&
+                    accumulate->device() == input.device(),
+                "mpi4torch_b200: accumulate tensor must match the input's shape, dtype and device");
+    acc = r.to_comm(*accumulate);
+    epi.accumulate = acc.data_ptr();
+  }
+  Tensor out = at::empty_like(in, at::MemoryFormat::Contiguous);
+  r.be->allreduce(in.data_ptr(), out.data_ptr(), in.numel(), dt, op, epi, r.stream);
+  return r.from_comm(out);
+}
+
+void Communicator::raw_bcast_(Tensor& work, int64_t root) {
+  TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Bcast_ root ", root, " out of range");
+  const DType dt = to_dtype(work.scalar_type());
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, work);
+  if (r.staged) {
+    Tensor h = work.cpu();
+    r.be->bcast(h.data_ptr(), h.numel(), dt, static_cast<int>(root), nullptr);
+    work.copy_(h);
+  } else {
+    r.be->bcast(work.data_ptr(), work.numel(), dt, static_cast<int>(root), r.stream);
+  }
+}
+
+void Communicator::raw_reduce_(Tensor& work, int64_t op_, int64_t root) {
+  TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Reduce_ root ", root, " out of range");
+  const ReduceOp op = to_op(op_);
+  const DType dt = to_dtype(work.scalar_type());
+  check_op_dtype(op, dt);
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, work);
+  if (r.staged) {
+    Tensor h = work.cpu();
+    r.be->reduce(h.data_ptr(), h.numel(), dt, op, static_cast<int>(root), nullptr);
+    work.copy_(h);
+  } else {
+    r.be->reduce(work.data_ptr(), work.numel(), dt, op, static_cast<int>(root), r.stream);
+  }
+}
+
+Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root, bool all) {
+  TORCH_CHECK(all || (root >= 0 && root < size_), "mpi4torch_b200: Gather root ", root, " out of range");
+  const DType dt = to_dtype(input.scalar_type());
+  const int64_t axis = wrap_axis(axis_, input.dim(), all ? "Allgather" : "Gather");
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  Tensor in = r.to_comm(input);
+  const auto shape = in.sizes().vec();
+  const Axis3 a3 = split_axis(shape, axis);
+  // one metadata round: [axis length, before, after]
+  int64_t mine[3] = {a3.axis, a3.before, a3.after};
+  std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
+  world_->control().allgather_i64(mine, 3, allmeta.data());
+  std::vector<int64_t> lens(static_cast<size_t>(size_));
+  for (int64_t p = 0; p < size_; ++p) {
+    lens[p] = allmeta[p * 3];
+    TORCH_CHECK(allmeta[p * 3 + 1] == a3.before && allmeta[p * 3 + 2] == a3.after,
+                "mpi4torch_b200: ", all ? "Allgather" : "Gather", ": rank ", p,
+                " has different non-gather dimensions than rank ", rank_);
+  }
+  const int rroot = all ? 0 : static_cast<int>(root);
+  PullPlan plan = plan_gather(static_cast<int>(rank_), static_cast<int>(size_), rroot, a3.before, a3.after, lens, all);
+  auto out_shape = shape;
+  const bool i_receive = all || rank_ == root;
+  // off-root the result has extent 0 along the gather axis (reference :538-554)
+  out_shape[axis] = i_receive ? std::accumulate(lens.begin(), lens.end(), int64_t{0}) : 0;
+  Tensor out = at::empty(out_shape, in.options());
+  r.be->pull(plan, in.data_ptr(), out.data_ptr(), dt, r.stream);
+  return r.from_comm(out);
+}
+
+Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t numelem, int64_t root) {
+  TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Scatter root ", root, " out of range");
+  TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Scatter numelem must be non-negative");
+  const DType dt = to_dtype(input.scalar_type());
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  Tensor in = r.to_comm(input);
+  // one metadata round: [numelem, ndim, sizes...]; only root's shape matters
+  // (off-root tensors are placeholders, reference :786-796).
+  const int64_t nd = in.dim();
+  TORCH_CHECK(nd + 2 <= kMetaWords, "mpi4torch_b200: tensor rank too large");
+  std::vector<int64_t> mine(kMetaWords, 0);
+  mine[0] = numelem;
+  mine[1] = nd;
+  for (int64_t i = 0; i < nd; ++i) mine[2 + i] = in.size(i);
+  std::vector<int64_t> allmeta(static_cast<size_t>(size_) * kMetaWords);
+  world_->control().allgather_i64(mine.data(), kMetaWords, allmeta.data());
+  const int64_t* rootmeta = allmeta.data() + root * kMetaWords;
+  const int64_t rnd = rootmeta[1];
+  std::vector<int64_t> rshape(rootmeta + 2, rootmeta + 2 + rnd);
+  const int64_t axis = wrap_axis(axis_, rnd, "Scatter");
+  std::vector<int64_t> counts(static_cast<size_t>(size_));
+  int64_t total = 0;
+  for (int64_t p = 0; p < size_; ++p) {
+    counts[p] = allmeta[p * kMetaWords];
+    total += counts[p];
+  }
+  // every rank sees the same numbers, so every rank raises (the reference only
+  // raises on root, :835-837, leaving the others hanging)
+  if (total != rshape[axis])
+    throw std::invalid_argument("mpi4torch_b200: Scatter: sum of numelem (" + std::to_string(total) +
+                                ") does not match the root tensor's axis length (" + std::to_string(rshape[axis]) + ")");
+  const Axis3 a3 = split_axis(rshape, axis);
+  PullPlan plan = plan_scatter(static_cast<int>(rank_), static_cast<int>(size_), static_cast<int>(root), a3.before,
+                               a3.after, counts);
+  auto out_shape = rshape;
+  out_shape[axis] = numelem;
+  Tensor out = at::empty(out_shape, in.options());
+  r.be->pull(plan, in.data_ptr(), out.data_ptr(), dt, r.stream);
+  return r.from_comm(out);
+}
+
+Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int64_t scatteraxis_, int64_t numelem) {
+  TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Alltoall numelem must be non-negative");
+  const DType dt = to_dtype(input.scalar_type());
+  const int64_t nd = input.dim();
+  const int64_t gaxis = wrap_axis(gatheraxis_, nd, "Alltoall");
+  const int64_t saxis = wrap_axis(scatteraxis_, nd, "Alltoall");
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  Tensor in = r.to_comm(input);
+  const auto shape = in.sizes().vec();
+  int64_t mine[2] = {numelem, shape[gaxis]};
+  std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 2);
+  world_->control().allgather_i64(mine, 2, allmeta.data());
+  std::vector<int64_t> counts(static_cast<size_t>(size_)), glen(static_cast<size_t>(size_));
+  for (int64_t p = 0; p < size_; ++p) {
+    counts[p] = allmeta[p * 2];
+    glen[p] = allmeta[p * 2 + 1];
+  }
+  PullPlan plan;
+  auto out_shape = shape;
+  if (gaxis == saxis) {
+    const Axis3 a3 = split_axis(shape, gaxis);
+    plan = plan_repartition(static_cast<int>(rank_), static_cast<int>(size_), a3.before, a3.after, glen, counts);
+    out_shape[gaxis] = numelem;
+  } else {
+    const int64_t total = std::accumulate(counts.begin(), counts.end(), int64_t{0});
+    if (total != shape[saxis])
+      throw std::invalid_argument("mpi4torch_b200: Alltoall: sum of numelem (" + std::to_string(total) +
+                                  ") does not match the scatter axis length (" + std::to_string(shape[saxis]) + ")");
+    plan = plan_alltoall(static_cast<int>(rank_), static_cast<int>(size_), shape, gaxis, saxis, glen, counts);
+    out_shape[gaxis] = std::accumulate(glen.begin(), glen.end(), int64_t{0});
+    out_shape[saxis] = numelem;
+  }
+  Tensor out = at::empty(out_shape, in.options());
+  r.be->pull(plan, in.data_ptr(), out.data_ptr(), dt, r.stream);
+  return r.from_comm(out);
+}
+
+Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_t axis_, int64_t numelem) {
+  TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Reduce_scatter numelem must be non-negative");
+  const ReduceOp op = to_op(op_);
+  const DType dt = to_dtype(input.scalar_type());
+  check_op_dtype(op, dt);
+  const int64_t axis = wrap_axis(axis_, input.dim(), "Reduce_scatter");
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  Tensor in = r.to_comm(input);
+  const auto shape = in.sizes().vec();
+  const Axis3 a3 = split_axis(shape, axis);
+  int64_t mine[3] = {numelem, a3.before * a3.after, a3.axis};
+  std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
+  world_->control().allgather_i64(mine, 3, allmeta.data());
+  std::vector<int64_t> counts(static_cast<size_t>(size_));
+  int64_t total = 0;
+  for (int64_t p = 0; p < size_; ++p) {
+    counts[p] = allmeta[p * 3];
+    total += counts[p];
+    TORCH_CHECK(allmeta[p * 3 + 1] == mine[1] && allmeta[p * 3 + 2] == mine[2],
+                "mpi4torch_b200: Reduce_scatter needs identically shaped tensors on all ranks");
+  }
+  if (total != a3.axis)
+    throw std::invalid_argument("mpi4torch_b200: Reduce_scatter: sum of numelem (" + std::to_string(total) +
+                                ") does not match the scatter axis length (" + std::to_string(a3.axis) + ")");
+  ReducePlan plan = plan_reduce_scatter(static_cast<int>(rank_), static_cast<int>(size_), a3.before, a3.after, counts);
+  auto out_shape = shape;
+  out_shape[axis] = numelem;
+  Tensor out = at::empty(out_shape, in.options());
+  r.be->reduce_pull(plan, in.data_ptr(), out.data_ptr(), dt, op, Epilogue{}, r.stream);
+  return r.from_comm(out);
+}
+
+// ---------------------------------------------------------------------------
+// Non-blocking point-to-point.  The raw handle keeps the reference's layout
+// (csrc/extension.cpp:1094-1107): [descriptor f64[7], comm buffer, original].
+// descriptor = [request id, kind (0 send / 1 recv), peer, tag,
+//               low 32 bits of the buffer address, device type, device index]
+// ---------------------------------------------------------------------------
+namespace {
+Tensor make_descriptor(int64_t req, int kind, int64_t peer, int64_t tag, const Tensor& buf, const Tensor& orig) {
+  Tensor d = at::empty({7}, at::TensorOptions().dtype(at::kDouble).device(at::kCPU));
+  double* p = d.data_ptr<double>();
+  p[0] = static_cast<double>(req);
+  p[1] = static_cast<double>(kind);
+  p[2] = static_cast<double>(peer);
+  p[3] = static_cast<double>(tag);
+  p[4] = static_cast<double>(ptr_hash(buf.data_ptr()));
+  p[5] = static_cast<double>(static_cast<int>(orig.device().type()));
+  p[6] = static_cast<double>(orig.device().index());
+  return d;
+}
+}  // namespace
+
+std::vector<Tensor> Communicator::raw_isend(const Tensor& input, int64_t dest, int64_t tag) {
+  TORCH_CHECK(dest >= 0 && dest < size_, "mpi4torch_b200: Isend destination ", dest, " out of range");
+  to_dtype(input.scalar_type());
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  Tensor buf = r.to_comm(input);
+  if (buf.is_same(input)) buf = input.detach();  // own TensorImpl: the handle is an autograd output
+  const int64_t req = r.be->isend(buf.data_ptr(), static_cast<int64_t>(buf.nbytes()), static_cast<int>(dest), tag, r.stream);
+  return {make_descriptor(req, 0, dest, tag, buf, input), buf, input.detach()};
+}
+
+std::vector<Tensor> Communicator::raw_irecv(const Tensor& input, int64_t source, int64_t tag) {
+  TORCH_CHECK(source >= 0 && source < size_, "mpi4torch_b200: Irecv source ", source, " out of range");
+  to_dtype(input.scalar_type());
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, input);
+  // A non-contiguous (or host-staged) receive lands in a fresh buffer; callers
+  // must use Wait's return value (same contract as the reference, :1256-1259).
+  Tensor buf;
+  if (r.staged) {
+    buf = at::empty(input.sizes(), input.options().device(at::kCPU));
+  } else {
+    buf = input.is_contiguous() ? input.detach() : at::empty(input.sizes(), input.options());
+  }
+  const int64_t req = r.be->irecv(buf.data_ptr(), static_cast<int64_t>(buf.nbytes()), static_cast<int>(source), tag, r.stream);
+  return {make_descriptor(req, 1, source, tag, buf, input), buf, input.detach()};
+}
+
+Tensor Communicator::raw_wait(const std::vector<Tensor>& handle) {
+  TORCH_CHECK(handle.size() == 3, "mpi4torch_b200: a raw wait handle consists of exactly 3 tensors");
+  const Tensor& desc = handle[0];
+  TORCH_CHECK(desc.device().is_cpu() && desc.scalar_type() == at::kDouble && desc.numel() == 7,
+              "mpi4torch_b200: malformed wait handle descriptor");
+  const double* p = desc.data_ptr<double>();
+  const int64_t req = static_cast<int64_t>(p[0]);
+  const int kind = static_cast<int>(p[1]);
+  const Tensor& buf = handle[1];
+  // the in-flight transfer targets this exact buffer (reference :1231-1237)
+  if (static_cast<uint32_t>(p[4]) != ptr_hash(buf.data_ptr()))
+    throw std::runtime_error("mpi4torch_b200: Wait: the communication buffer of this handle was replaced "
+                             "(handle bifurcation / gradient accumulation on a wait handle is not supported)");
+  const c10::Device orig(static_cast<c10::DeviceType>(static_cast<int>(p[5])), static_cast<c10::DeviceIndex>(p[6]));
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Backend* be;
+  void* stream = nullptr;
+  c10::optional<c10::cuda::CUDAGuard> guard;
+  if (buf.is_cuda()) {
+    TORCH_CHECK(world_->cuda_ready(), "mpi4torch_b200: CUDA wait handle without a CUDA backend");
+    guard.emplace(buf.device());
+    stream = c10::cuda::getCurrentCUDAStream(buf.device().index()).stream();
+    be = world_->cuda();
+  } else {
+    be = &world_->cpu();
+  }
+  be->wait(req, stream);
+  if (kind == 0) return handle[2];
+  return buf.device() == orig ? buf : buf.to(orig);
+}
+
+}  // namespace m4t

@@ -1,0 +1,71 @@
+// Torch-facing communicator: the custom class exported to Python/TorchScript
+// (reference MPI_Comm_Wrapper, csrc/extension.cpp:140-187) and the
+// differentiable op entry points (reference L2, :254-1265).
+#pragma once
+#include <torch/custom_class.h>
+#include <torch/torch.h>
+
+#include <vector>
+
+#include "../runtime/world.h"
+
+namespace m4t {
+
+using torch::Tensor;
+
+struct Communicator : torch::CustomClassHolder {
+  Communicator();
+
+  // rank/size are cached at construction (the reference re-queries MPI on every
+  // access, csrc/extension.cpp:175-187).
+  int64_t GetRank() const { return rank_; }
+  int64_t GetSize() const { return size_; }
+
+  // ---- differentiable collectives ------------------------------------------
+  Tensor Allreduce(const Tensor& input, int64_t op);
+  // out = accumulate + scale * Allreduce(input): the scale / accumulate run in
+  // the collective's epilogue, forward and backward.
+  Tensor AllreduceFused(const Tensor& input, int64_t op, double scale, const c10::optional<Tensor>& accumulate);
+  Tensor Bcast_(const Tensor& input, int64_t root);
+  Tensor Reduce_(const Tensor& input, int64_t op, int64_t root);
+  Tensor Gather(const Tensor& input, int64_t gatheraxis, int64_t root);
+  Tensor Allgather(const Tensor& input, int64_t gatheraxis);
+  Tensor Scatter(const Tensor& input, int64_t scatteraxis, int64_t numelem, int64_t root);
+  Tensor Alltoall(const Tensor& input, int64_t gatheraxis, int64_t scatteraxis, int64_t numelem);
+  Tensor Reduce_scatter(const Tensor& input, int64_t op, int64_t scatteraxis, int64_t numelem);
+
+  // ---- differentiable non-blocking point-to-point ---------------------------
+  std::vector<Tensor> Isend(const Tensor& input, int64_t dest, int64_t tag);
+  std::vector<Tensor> Irecv(const Tensor& input, int64_t source, int64_t tag);
+  Tensor Wait(const std::vector<Tensor>& handle);
+
+  // ---- utilities --------------------------------------------------------------
+  void Barrier();
+  std::string Describe() const;
+
+  // ---- raw (non-differentiable) data paths, used by the autograd functions ---
+  Tensor raw_allreduce(const Tensor& input, int64_t op, double scale, bool has_scale,
+                       const c10::optional<Tensor>& accumulate);
+  void raw_bcast_(Tensor& work, int64_t root);
+  void raw_reduce_(Tensor& work, int64_t op, int64_t root);
+  Tensor raw_gather(const Tensor& input, int64_t axis, int64_t root, bool all);
+  Tensor raw_scatter(const Tensor& input, int64_t axis, int64_t numelem, int64_t root);
+  Tensor raw_alltoall(const Tensor& input, int64_t gatheraxis, int64_t scatteraxis, int64_t numelem);
+  Tensor raw_reduce_scatter(const Tensor& input, int64_t op, int64_t axis, int64_t numelem);
+  std::vector<Tensor> raw_isend(const Tensor& input, int64_t dest, int64_t tag);
+  std::vector<Tensor> raw_irecv(const Tensor& input, int64_t source, int64_t tag);
+  Tensor raw_wait(const std::vector<Tensor>& handle);
+
+  World& world() const { return *world_; }
+
+ private:
+  World* world_;
+  int64_t rank_, size_;
+};
+
+// Differentiable dependency join (reference csrc/extension.cpp:1024-1046).
+Tensor JoinDummies(const Tensor& loopthrough, const std::vector<Tensor>& dummies);
+
+c10::intrusive_ptr<Communicator> comm_world();
+
+}  // namespace m4t

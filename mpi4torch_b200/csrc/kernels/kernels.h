@@ -1,0 +1,85 @@
+// Host-callable launchers of the sm_100a kernels.  Torch-free; the CUDA backend
+// (runtime/cuda_backend.cpp) fills a DeviceComm once and passes it by value.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../runtime/common.h"
+#include "../runtime/plan.h"
+#include "device_sync.cuh"
+
+namespace m4t {
+
+// Symmetric-heap layout (identical on every rank):
+//   [0, kPadBytes)                       barrier flag pads + p2p flags
+//   [p2p_off, p2p_off + p2p_bytes)       p2p FIFO slots
+//   [stage_off, stage_off + 2*half)      staging halves (op parity)
+constexpr int64_t kBarrierPadBytes = static_cast<int64_t>(kMaxChannels) * kMaxGpuPeers * 4;  // 32 KiB
+
+struct DeviceComm {
+  SyncCtx sync;
+  char* heap[kMaxGpuPeers];  // unicast mappings of every rank's heap (heap[rank] is local)
+  char* mc_heap;             // multicast mapping of the heap, or nullptr
+  int64_t stage_off;         // byte offset of staging half 0
+  int64_t half_bytes;        // bytes per staging half
+  int sm_count;
+};
+
+enum class ArAlgo : int { AUTO = 0, ONESHOT = 1, TWOSHOT = 2, NVLS = 3, LOCAL = 4 };
+
+// True if the (dtype, op) pair has an in-switch multimem.ld_reduce form we emit.
+bool nvls_supported(DType dt, ReduceOp op);
+
+// Bytes of staging (per half) an allreduce of n elements needs with `algo`.
+int64_t allreduce_stage_bytes(int64_t n, DType dt, ArAlgo algo, int size);
+
+// out = epilogue(reduce over ranks of in).  One launch.
+void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n, DType dt, ReduceOp op,
+                      const Epilogue& epi, ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream);
+
+// World-size-1 / local form: out = epilogue(normalise(in)); also the copy kernel.
+void launch_local_epilogue(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                           int sm_count, cudaStream_t stream);
+
+// Broadcast root's private buffer in place (NVLS push when mc_heap, else peer pull).
+void launch_bcast(const DeviceComm& dc, void* buf, int64_t n, DType dt, int root, int blocks,
+                  cudaStream_t stream);
+// Reduce to root in place, zero-fill non-roots.
+void launch_reduce(const DeviceComm& dc, void* buf, int64_t n, DType dt, ReduceOp op, int root, int blocks,
+                   cudaStream_t stream);
+
+// Copies `bytes` of a private buffer into this rank's staging half (current parity).
+void launch_stage_in(const DeviceComm& dc, const void* in, int64_t bytes, int sm_count, cudaStream_t stream);
+// Barrier + strided box pulls from peers' staging (Gather/Allgather/Scatter/Alltoall).
+void launch_slab_pull(const DeviceComm& dc, const PullPlan& plan, const void* in, void* out, DType dt,
+                      int blocks, cudaStream_t stream);
+// Barrier + reduce-scatter box (Allgather adjoint) with fused epilogue.
+void launch_slab_reduce(const DeviceComm& dc, const ReducePlan& plan, const void* in, void* out, DType dt,
+                        ReduceOp op, const Epilogue& epi, bool use_nvls, int blocks, cudaStream_t stream);
+// Local strided box copy (world size 1).
+void launch_slab_local(const PullPlan& plan, const void* in, void* out, DType dt, int sm_count,
+                       cudaStream_t stream);
+
+// ---- point-to-point FIFO (one directed pair) --------------------------------
+// As seen from the launching side: `slots` is the sender's ring (local pointer
+// on the sender, peer mapping on the receiver); head flags live in the
+// RECEIVER's pad (sender writes them remotely), tail flags in the SENDER's pad.
+struct P2pChannel {
+  char* slots;
+  uint32_t* head_flags;  // [nslots], value = chunk index + 1 once the slot holds that chunk
+  uint32_t* tail_flags;  // [nslots], value = chunk index + 1 once that chunk has been consumed
+  int64_t slot_bytes;
+  int nslots;
+};
+// Chunks a message of `bytes` occupies in the ring (>= 1: empty messages carry a flag).
+int64_t p2p_num_chunks(int64_t bytes, int64_t slot_bytes);
+// Sender: copies `bytes` from `src` into the ring, chunk by chunk, publishing head flags.
+void launch_p2p_send(const SyncCtx& sync, const P2pChannel& ch, const void* src, int64_t bytes,
+                     unsigned long long first_chunk, int blocks, cudaStream_t stream);
+// Receiver: pulls chunks out of the sender's ring into `dst`, acknowledging tail flags.
+void launch_p2p_recv(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64_t bytes,
+                     unsigned long long first_chunk, int blocks, cudaStream_t stream);
+
+// Fills `n` bytes with zero (used for non-root results / backward recv buffers).
+void launch_zero(void* p, int64_t bytes, int sm_count, cudaStream_t stream);
+
+}  // namespace m4t

@@ -1,0 +1,446 @@
+#include "cuda_backend.h"
+
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+
+namespace m4t {
+
+#define M4T_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t m4t_e_ = (expr);                                                         \
+    M4T_CHECK(m4t_e_ == cudaSuccess, #expr << " failed: " << cudaGetErrorString(m4t_e_)); \
+  } while (0)
+
+namespace {
+int64_t round_up64(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+constexpr int64_t kP2pHeadOff = 32 * 1024;  // after the 32 KiB barrier pad
+constexpr int64_t kP2pTailOff = 48 * 1024;
+constexpr int64_t kP2pRingOff = 1 << 20;
+constexpr int kMaxSlots = 64;
+}  // namespace
+
+CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) {
+  const int P = ctl.size();
+  M4T_CHECK(P <= kMaxGpuPeers, "the NVLink backend supports up to " << kMaxGpuPeers << " ranks (got " << P << ")");
+  M4T_CUDA(cudaSetDevice(device_));
+  tune_.oneshot_max_bytes = env_i64("M4T_ONESHOT_MAX_KB", 256) * 1024;
+  tune_.chunk_bytes = env_i64("M4T_CHUNK_KB", 8192) * 1024;
+  tune_.ar_blocks = static_cast<int>(env_i64("M4T_AR_BLOCKS", 128));
+  tune_.oneshot_blocks = static_cast<int>(env_i64("M4T_ONESHOT_BLOCKS", 32));
+  tune_.slab_blocks = static_cast<int>(env_i64("M4T_SLAB_BLOCKS", 128));
+  tune_.p2p_blocks = static_cast<int>(env_i64("M4T_P2P_BLOCKS", 16));
+  tune_.force_algo = static_cast<int>(env_i64("M4T_ALLREDUCE_ALGO", 0));
+
+  nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", 8))));
+  slot_bytes_ = round_up64(std::max<int64_t>(4096, env_i64("M4T_P2P_SLOT_KB", 1024) * 1024), 128);
+  p2p_head_off_ = kP2pHeadOff;
+  p2p_tail_off_ = kP2pTailOff;
+  p2p_off_ = kP2pRingOff;
+  const int64_t p2p_bytes = static_cast<int64_t>(P) * nslots_ * slot_bytes_;
+  const int64_t stage_off = round_up64(p2p_off_ + p2p_bytes, 2 << 20);
+  const int64_t half = P > 1 ? round_up64(env_i64("M4T_STAGE_MB", 2176) << 20, 2 << 20) : 0;
+  heap_ = std::make_unique<SymmHeap>(ctl_, device_, static_cast<size_t>(stage_off + 2 * half));
+
+  M4T_CUDA(cudaMalloc(&d_counters_, 2 * sizeof(unsigned long long)));
+  M4T_CUDA(cudaMemset(d_counters_, 0, 2 * sizeof(unsigned long long)));
+  M4T_CUDA(cudaMalloc(&d_done_, sizeof(unsigned int)));
+  M4T_CUDA(cudaMemset(d_done_, 0, sizeof(unsigned int)));
+  M4T_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_err_), sizeof(int), cudaHostAllocMapped));
+  *h_err_ = 0;
+  M4T_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_), h_err_, 0));
+  M4T_CUDA(cudaEventCreateWithFlags(&chain_event_, cudaEventDisableTiming));
+
+  cudaDeviceProp prop;
+  M4T_CUDA(cudaGetDeviceProperties(&prop, device_));
+  std::memset(&dc_, 0, sizeof(dc_));
+  for (int p = 0; p < P; ++p) {
+    dc_.heap[p] = heap_->peer(p);
+    dc_.sync.pads[p] = reinterpret_cast<uint32_t*>(heap_->peer(p));
+  }
+  dc_.mc_heap = heap_->multicast();
+  dc_.sync.counters = d_counters_;
+  dc_.sync.done_ctr = d_done_;
+  dc_.sync.err_flag = d_err_;
+  dc_.sync.timeout_ns = static_cast<unsigned long long>(env_i64("M4T_DEVICE_TIMEOUT_S", 20)) * 1000000000ull;
+  dc_.sync.rank = ctl.rank();
+  dc_.sync.size = P;
+  dc_.stage_off = stage_off;
+  dc_.half_bytes = half;
+  dc_.sm_count = prop.multiProcessorCount;
+
+  send_streams_.assign(static_cast<size_t>(P), nullptr);
+  recv_streams_.assign(static_cast<size_t>(P), nullptr);
+  send_chunks_.assign(static_cast<size_t>(P), 0ull);
+  recv_chunks_.assign(static_cast<size_t>(P), 0ull);
+  send_seq_.assign(static_cast<size_t>(P), 0ull);
+  posted_.resize(static_cast<size_t>(P));
+  unexpected_.resize(static_cast<size_t>(P));
+  M4T_CUDA(cudaDeviceSynchronize());
+  ctl_.barrier();
+}
+
+CudaBackend::~CudaBackend() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  for (auto s : send_streams_)
+    if (s) cudaStreamDestroy(s);
+  for (auto s : recv_streams_)
+    if (s) cudaStreamDestroy(s);
+  for (auto e : event_pool_) cudaEventDestroy(e);
+  if (chain_event_) cudaEventDestroy(chain_event_);
+  if (d_counters_) cudaFree(d_counters_);
+  if (d_done_) cudaFree(d_done_);
+  if (h_err_) cudaFreeHost(h_err_);
+  heap_.reset();
+}
+
+std::string CudaBackend::describe() const {
+  std::ostringstream o;
+  o << "cuda-nvlink rank " << rank() << "/" << size() << " dev " << device_ << " heap " << heap_->describe()
+    << " staging " << (dc_.half_bytes >> 20) << " MiB x2 nvls=" << (has_nvls() ? 1 : 0);
+  return o.str();
+}
+
+void CudaBackend::check_device_error() {
+  if (h_err_ && *reinterpret_cast<volatile int*>(h_err_) != 0) {
+    const int code = *h_err_;
+    *h_err_ = 0;
+    ctl_.signal_abort();
+    M4T_CHECK(false, "device-side wait timed out (code " << code << ") on rank " << rank()
+                         << ": a peer never reached the matching collective / transfer "
+                            "(mismatched collective order across ranks?)");
+  }
+}
+
+void CudaBackend::chain(cudaStream_t s) {
+  if (have_last_ && last_stream_ != s) {
+    M4T_CUDA(cudaEventRecord(chain_event_, last_stream_));
+    M4T_CUDA(cudaStreamWaitEvent(s, chain_event_, 0));
+  }
+  last_stream_ = s;
+  have_last_ = true;
+}
+
+cudaEvent_t CudaBackend::new_event() {
+  if (!event_pool_.empty()) {
+    cudaEvent_t e = event_pool_.back();
+    event_pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  M4T_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return e;
+}
+
+void CudaBackend::free_event(cudaEvent_t e) {
+  if (e) event_pool_.push_back(e);
+}
+
+ArAlgo CudaBackend::pick_algo(int64_t bytes, DType dt, ReduceOp op) const {
+  if (size() == 1) return ArAlgo::LOCAL;
+  const bool nvls_ok = has_nvls() && nvls_supported(dt, op);
+  if (tune_.force_algo == 1) return ArAlgo::ONESHOT;
+  if (tune_.force_algo == 2) return ArAlgo::TWOSHOT;
+  if (tune_.force_algo == 3 && nvls_ok) return ArAlgo::NVLS;
+  const int64_t oneshot_cap = dc_.half_bytes / size() - 128;
+  if (bytes <= tune_.oneshot_max_bytes && bytes <= oneshot_cap) return ArAlgo::ONESHOT;
+  return nvls_ok ? ArAlgo::NVLS : ArAlgo::TWOSHOT;
+}
+
+void CudaBackend::allreduce_algo(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                                 ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream) {
+  check_device_error();
+  check_op_dtype(op, dt);
+  if (n == 0) return;
+  M4T_CUDA(cudaSetDevice(device_));
+  if (size() == 1 || algo == ArAlgo::LOCAL) {
+    launch_local_epilogue(in, out, n, dt, op, epi, dc_.sm_count, stream);
+    return;
+  }
+  chain(stream);
+  const int64_t es = dtype_size(dt);
+  if (algo == ArAlgo::NVLS) M4T_CHECK(has_nvls() && nvls_supported(dt, op), "NVLS unavailable for " << dtype_name(dt) << "/" << op_name(op));
+  if (algo == ArAlgo::ONESHOT) {
+    M4T_CHECK(allreduce_stage_bytes(n, dt, algo, size()) <= dc_.half_bytes, "one-shot allreduce too large for staging");
+    launch_allreduce(dc_, in, out, n, dt, op, epi, algo, blocks, chunk_bytes, stream);
+    return;
+  }
+  // split so that [in copy | reduced out] fits one staging half
+  const int64_t max_bytes = (dc_.half_bytes / 2 - 256) / 128 * 128;
+  const int64_t max_elems = std::max<int64_t>(16, max_bytes / es);
+  for (int64_t off = 0; off < n; off += max_elems) {
+    const int64_t cnt = std::min(max_elems, n - off);
+    Epilogue e = epi;
+    if (e.accumulate) e.accumulate = static_cast<const char*>(e.accumulate) + off * es;
+    launch_allreduce(dc_, static_cast<const char*>(in) + off * es, static_cast<char*>(out) + off * es, cnt, dt, op, e,
+                     algo, blocks, chunk_bytes, stream);
+  }
+}
+
+void CudaBackend::allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                            void* stream) {
+  const ArAlgo algo = pick_algo(n * dtype_size(dt), dt, op);
+  const int blocks = algo == ArAlgo::ONESHOT ? tune_.oneshot_blocks : tune_.ar_blocks;
+  allreduce_algo(in, out, n, dt, op, epi, algo, blocks, tune_.chunk_bytes, static_cast<cudaStream_t>(stream));
+}
+
+void CudaBackend::bcast(void* buf, int64_t n, DType dt, int root, void* stream) {
+  check_device_error();
+  M4T_CHECK(root >= 0 && root < size(), "Bcast_: root " << root << " out of range");
+  if (size() == 1 || n == 0) return;
+  M4T_CUDA(cudaSetDevice(device_));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  chain(s);
+  const int64_t es = dtype_size(dt);
+  const int64_t max_elems = std::max<int64_t>(16, ((dc_.half_bytes - 256) / 128 * 128) / es);
+  for (int64_t off = 0; off < n; off += max_elems)
+    launch_bcast(dc_, static_cast<char*>(buf) + off * es, std::min(max_elems, n - off), dt, root, tune_.ar_blocks, s);
+}
+
+void CudaBackend::reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) {
+  check_device_error();
+  check_op_dtype(op, dt);
+  M4T_CHECK(root >= 0 && root < size(), "Reduce_: root " << root << " out of range");
+  if (n == 0) return;
+  M4T_CUDA(cudaSetDevice(device_));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (size() == 1) {
+    launch_local_epilogue(buf, buf, n, dt, op, Epilogue{}, dc_.sm_count, s);
+    return;
+  }
+  chain(s);
+  const int64_t es = dtype_size(dt);
+  const int64_t max_elems = std::max<int64_t>(16, ((dc_.half_bytes - 256) / 128 * 128) / es);
+  for (int64_t off = 0; off < n; off += max_elems)
+    launch_reduce(dc_, static_cast<char*>(buf) + off * es, std::min(max_elems, n - off), dt, op, root, tune_.ar_blocks, s);
+}
+
+namespace {
+int grid_for(int64_t max_elems, int64_t es, int cap) {
+  const int64_t vecs = (max_elems * es + 15) / 16;
+  const int64_t want = (vecs + 512 * 4 - 1) / (512 * 4);
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(cap, want)));
+}
+}  // namespace
+
+void CudaBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) {
+  check_device_error();
+  M4T_CUDA(cudaSetDevice(device_));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (size() == 1) {
+    launch_slab_local(plan, in, out, dt, dc_.sm_count, s);
+    return;
+  }
+  const int64_t es = dtype_size(dt);
+  M4T_CHECK(plan.max_stage_elems * es <= dc_.half_bytes,
+            "collective stages " << plan.max_stage_elems * es << " B per rank but the staging half is "
+                                 << dc_.half_bytes << " B; raise M4T_STAGE_MB");
+  chain(s);
+  if (plan.stage_elems > 0) launch_stage_in(dc_, in, plan.stage_elems * es, dc_.sm_count, s);
+  launch_slab_pull(dc_, plan, in, out, dt, grid_for(plan.max_out_elems, es, tune_.slab_blocks), s);
+}
+
+void CudaBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op,
+                              const Epilogue& epi, void* stream) {
+  check_device_error();
+  check_op_dtype(op, dt);
+  M4T_CUDA(cudaSetDevice(device_));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t es = dtype_size(dt);
+  if (size() > 1) {
+    M4T_CHECK(plan.stage_elems * es <= dc_.half_bytes,
+              "Reduce_scatter stages " << plan.stage_elems * es << " B but the staging half is " << dc_.half_bytes
+                                       << " B; raise M4T_STAGE_MB");
+    chain(s);
+    if (plan.stage_elems > 0) launch_stage_in(dc_, in, plan.stage_elems * es, dc_.sm_count, s);
+  }
+  launch_slab_reduce(dc_, plan, in, out, dt, op, epi, has_nvls(), grid_for(plan.max_out_elems, es, tune_.slab_blocks), s);
+}
+
+// ---------------------------------------------------------------------------
+// point-to-point
+// ---------------------------------------------------------------------------
+cudaStream_t CudaBackend::send_stream(int peer) {
+  if (!send_streams_[peer]) M4T_CUDA(cudaStreamCreateWithFlags(&send_streams_[peer], cudaStreamNonBlocking));
+  return send_streams_[peer];
+}
+cudaStream_t CudaBackend::recv_stream(int peer) {
+  if (!recv_streams_[peer]) M4T_CUDA(cudaStreamCreateWithFlags(&recv_streams_[peer], cudaStreamNonBlocking));
+  return recv_streams_[peer];
+}
+
+P2pChannel CudaBackend::send_channel(int dest) const {
+  P2pChannel ch;
+  const int r = rank();
+  ch.slots = heap_->peer(r) + p2p_off_ + static_cast<int64_t>(dest) * nslots_ * slot_bytes_;
+  // head flags live in the receiver's pad, indexed by the source rank (me)
+  ch.head_flags = reinterpret_cast<uint32_t*>(heap_->peer(dest) + p2p_head_off_) + static_cast<int64_t>(r) * kMaxSlots;
+  // tail flags live in my pad, indexed by the destination
+  ch.tail_flags = reinterpret_cast<uint32_t*>(heap_->peer(r) + p2p_tail_off_) + static_cast<int64_t>(dest) * kMaxSlots;
+  ch.slot_bytes = slot_bytes_;
+  ch.nslots = nslots_;
+  return ch;
+}
+
+P2pChannel CudaBackend::recv_channel(int source) const {
+  P2pChannel ch;
+  const int r = rank();
+  ch.slots = heap_->peer(source) + p2p_off_ + static_cast<int64_t>(r) * nslots_ * slot_bytes_;
+  ch.head_flags = reinterpret_cast<uint32_t*>(heap_->peer(r) + p2p_head_off_) + static_cast<int64_t>(source) * kMaxSlots;
+  ch.tail_flags = reinterpret_cast<uint32_t*>(heap_->peer(source) + p2p_tail_off_) + static_cast<int64_t>(r) * kMaxSlots;
+  ch.slot_bytes = slot_bytes_;
+  ch.nslots = nslots_;
+  return ch;
+}
+
+int64_t CudaBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) {
+  check_device_error();
+  M4T_CHECK(dest >= 0 && dest < size(), "Isend: destination rank " << dest << " out of range");
+  M4T_CUDA(cudaSetDevice(device_));
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  cudaStream_t ss = send_stream(dest);
+  // the payload is produced on the user's stream
+  cudaEvent_t ready = new_event();
+  M4T_CUDA(cudaEventRecord(ready, user));
+  M4T_CUDA(cudaStreamWaitEvent(ss, ready, 0));
+  free_event(ready);
+  const unsigned long long first = send_chunks_[dest];
+  launch_p2p_send(dc_.sync, send_channel(dest), buf, bytes, first, tune_.p2p_blocks, ss);
+  send_chunks_[dest] += static_cast<unsigned long long>(p2p_num_chunks(bytes, slot_bytes_));
+  Request rq;
+  rq.is_recv = false;
+  rq.matched = true;
+  rq.peer = dest;
+  rq.tag = tag;
+  rq.bytes = bytes;
+  rq.done = new_event();
+  M4T_CUDA(cudaEventRecord(rq.done, ss));
+  // publish the descriptor so the receiver can match (src, tag) on the host
+  PairRing& ring = ctl_.block()->rings[rank()][dest];
+  MsgDesc d{};
+  d.seq = ++send_seq_[dest];
+  d.tag = tag;
+  d.bytes = static_cast<uint64_t>(bytes);
+  d.kind = 2;
+  std::memcpy(d.inline_data, &first, sizeof(first));
+  const uint64_t head = ring.head.load(std::memory_order_relaxed);
+  ctl_.wait_until([&] { return head - ring.tail.load(std::memory_order_acquire) < kMailboxDepth; },
+                  "space in the send ring");
+  ring.entries[head % kMailboxDepth] = d;
+  ring.head.store(head + 1, std::memory_order_release);
+  const int64_t id = next_request_++;
+  requests_[id] = rq;
+  return id;
+}
+
+void CudaBackend::launch_recv(const MsgDesc& d, int source, void* dst, cudaEvent_t ready, cudaEvent_t done) {
+  cudaStream_t rs = recv_stream(source);
+  if (ready) M4T_CUDA(cudaStreamWaitEvent(rs, ready, 0));
+  unsigned long long first = 0;
+  std::memcpy(&first, d.inline_data, sizeof(first));
+  M4T_CHECK(first == recv_chunks_[source], "p2p FIFO out of sync with rank " << source << " (expected chunk "
+                                               << recv_chunks_[source] << ", message starts at " << first << ")");
+  launch_p2p_recv(dc_.sync, recv_channel(source), dst, static_cast<int64_t>(d.bytes), first, tune_.p2p_blocks, rs);
+  recv_chunks_[source] += static_cast<unsigned long long>(p2p_num_chunks(static_cast<int64_t>(d.bytes), slot_bytes_));
+  M4T_CUDA(cudaEventRecord(done, rs));
+}
+
+bool CudaBackend::progress_source(int source, bool blocking) {
+  PairRing& ring = ctl_.block()->rings[source][rank()];
+  const uint64_t tail = ring.tail.load(std::memory_order_relaxed);
+  if (ring.head.load(std::memory_order_acquire) <= tail) {
+    if (!blocking) return false;
+    ctl_.wait_until([&] { return ring.head.load(std::memory_order_acquire) > tail; }, "a matching message");
+  }
+  MsgDesc d = ring.entries[tail % kMailboxDepth];
+  ring.tail.store(tail + 1, std::memory_order_release);
+  M4T_CHECK(d.kind == 2, "host-memory message from rank " << source << " received by the CUDA backend");
+  // the device FIFO is strictly ordered: this message must be drained now
+  for (auto it = posted_[source].begin(); it != posted_[source].end(); ++it) {
+    Request& rq = requests_.at(*it);
+    if (rq.tag != d.tag) continue;
+    M4T_CHECK(static_cast<int64_t>(d.bytes) <= rq.bytes,
+              "message truncated: " << d.bytes << " bytes sent by rank " << source << " (tag " << d.tag
+                                    << ") into a " << rq.bytes << "-byte receive buffer");
+    rq.done = new_event();
+    launch_recv(d, source, rq.buf, rq.ready, rq.done);
+    rq.matched = true;
+    posted_[source].erase(it);
+    return true;
+  }
+  Unexpected u;
+  u.tag = d.tag;
+  u.bytes = static_cast<int64_t>(d.bytes);
+  u.temp = nullptr;
+  if (u.bytes > 0) M4T_CUDA(cudaMalloc(&u.temp, static_cast<size_t>(u.bytes)));
+  u.done = new_event();
+  launch_recv(d, source, u.temp, nullptr, u.done);
+  unexpected_[source].push_back(u);
+  return true;
+}
+
+void CudaBackend::complete_from_unexpected(Request& rq, Unexpected& u) {
+  M4T_CHECK(u.bytes <= rq.bytes, "message truncated: " << u.bytes << " bytes (tag " << u.tag << ") into a "
+                                                       << rq.bytes << "-byte receive buffer");
+  cudaStream_t rs = recv_stream(rq.peer);
+  if (rq.ready) M4T_CUDA(cudaStreamWaitEvent(rs, rq.ready, 0));
+  M4T_CUDA(cudaStreamWaitEvent(rs, u.done, 0));
+  if (u.bytes > 0) M4T_CUDA(cudaMemcpyAsync(rq.buf, u.temp, static_cast<size_t>(u.bytes), cudaMemcpyDeviceToDevice, rs));
+  rq.done = new_event();
+  M4T_CUDA(cudaEventRecord(rq.done, rs));
+  if (u.temp) M4T_CUDA(cudaFreeAsync(u.temp, rs));
+  free_event(u.done);
+  rq.matched = true;
+}
+
+int64_t CudaBackend::irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) {
+  check_device_error();
+  M4T_CHECK(source >= 0 && source < size(), "Irecv: source rank " << source << " out of range");
+  M4T_CUDA(cudaSetDevice(device_));
+  Request rq;
+  rq.is_recv = true;
+  rq.buf = buf;
+  rq.bytes = bytes;
+  rq.peer = source;
+  rq.tag = tag;
+  rq.ready = new_event();
+  M4T_CUDA(cudaEventRecord(rq.ready, static_cast<cudaStream_t>(stream)));
+  const int64_t id = next_request_++;
+  // an earlier unexpected message with this tag?
+  auto& ux = unexpected_[source];
+  for (auto it = ux.begin(); it != ux.end(); ++it) {
+    if (it->tag == tag) {
+      complete_from_unexpected(rq, *it);
+      ux.erase(it);
+      requests_[id] = rq;
+      return id;
+    }
+  }
+  requests_[id] = rq;
+  posted_[source].push_back(id);
+  // opportunistic early match so the pull overlaps whatever the caller does next
+  while (!requests_.at(id).matched && progress_source(source, false)) {
+  }
+  return id;
+}
+
+void CudaBackend::wait(int64_t request, void* stream) {
+  auto it = requests_.find(request);
+  M4T_CHECK(it != requests_.end(), "Wait: unknown or already completed request " << request
+                                       << " (a WaitHandle may only be waited on once)");
+  M4T_CUDA(cudaSetDevice(device_));
+  if (it->second.is_recv) {
+    const int src = it->second.peer;
+    while (!requests_.at(request).matched) progress_source(src, true);
+    it = requests_.find(request);
+  }
+  Request rq = it->second;
+  requests_.erase(it);
+  M4T_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), rq.done, 0));
+  free_event(rq.done);
+  free_event(rq.ready);
+  check_device_error();
+}
+
+}  // namespace m4t

@@ -1,0 +1,123 @@
+// CUDA backend: the symmetric heap + kernel launch policy for one rank.
+// All collectives are stream-ordered on the caller's stream (no host blocking);
+// consecutive collectives issued on different streams are chained with events so
+// the device-side flag protocol always sees one total order per rank.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <list>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "../kernels/kernels.h"
+#include "backend.h"
+#include "control.h"
+#include "symm_heap.h"
+
+namespace m4t {
+
+struct CudaTuning {
+  int64_t oneshot_max_bytes;   // M4T_ONESHOT_MAX_KB
+  int64_t chunk_bytes;         // M4T_CHUNK_KB   (two-shot / NVLS pipeline step)
+  int ar_blocks;               // M4T_AR_BLOCKS  (two-shot / NVLS grid)
+  int oneshot_blocks;          // M4T_ONESHOT_BLOCKS
+  int slab_blocks;             // M4T_SLAB_BLOCKS
+  int p2p_blocks;              // M4T_P2P_BLOCKS
+  int force_algo;              // M4T_ALLREDUCE_ALGO: 0 auto, 1 oneshot, 2 twoshot, 3 nvls
+};
+
+class CudaBackend final : public Backend {
+ public:
+  CudaBackend(Control& ctl, int device);
+  ~CudaBackend() override;
+
+  const char* name() const override { return "cuda-nvlink"; }
+  int rank() const override { return ctl_.rank(); }
+  int size() const override { return ctl_.size(); }
+  int device() const { return device_; }
+  const SymmHeap& heap() const { return *heap_; }
+  const DeviceComm& device_comm() const { return dc_; }
+  CudaTuning& tuning() { return tune_; }
+  bool has_nvls() const { return dc_.mc_heap != nullptr; }
+  std::string describe() const;
+
+  void allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                 void* stream) override;
+  void bcast(void* buf, int64_t n, DType dt, int root, void* stream) override;
+  void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override;
+  void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override;
+  void reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op,
+                   const Epilogue& epi, void* stream) override;
+  int64_t isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) override;
+  int64_t irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) override;
+  void wait(int64_t request, void* stream) override;
+
+  // Explicit algorithm choice (benchmarks / tests).
+  void allreduce_algo(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                      ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream);
+  ArAlgo pick_algo(int64_t bytes, DType dt, ReduceOp op) const;
+
+  // Throws if a device-side wait timed out since the last check.
+  void check_device_error();
+  // Symmetric scratch for fused kernels (e.g. Allreduce->GEMM): bytes inside the current staging half.
+  int64_t half_bytes() const { return dc_.half_bytes; }
+
+ private:
+  struct Request {
+    bool is_recv = false;
+    bool matched = false;
+    void* buf = nullptr;
+    int64_t bytes = 0;
+    int peer = 0;
+    int64_t tag = 0;
+    cudaEvent_t ready = nullptr;  // recv: buffer may be overwritten after this event
+    cudaEvent_t done = nullptr;   // transfer complete
+  };
+  struct Unexpected {
+    int64_t tag;
+    int64_t bytes;
+    void* temp;
+    cudaEvent_t done;
+  };
+
+  void chain(cudaStream_t s);  // serialise collectives across streams
+  cudaEvent_t new_event();
+  void free_event(cudaEvent_t e);
+  cudaStream_t send_stream(int peer);
+  cudaStream_t recv_stream(int peer);
+  P2pChannel send_channel(int dest) const;
+  P2pChannel recv_channel(int source) const;
+  void launch_recv(const MsgDesc& d, int source, void* dst, cudaEvent_t ready, cudaEvent_t done);
+  // Pops one descriptor from source's ring (blocking or not) and matches it; returns false if none available.
+  bool progress_source(int source, bool blocking);
+  void complete_from_unexpected(Request& rq, Unexpected& u);
+
+  Control& ctl_;
+  int device_;
+  std::unique_ptr<SymmHeap> heap_;
+  DeviceComm dc_{};
+  CudaTuning tune_{};
+  unsigned long long* d_counters_ = nullptr;
+  unsigned int* d_done_ = nullptr;
+  int* h_err_ = nullptr;  // pinned + mapped
+  int* d_err_ = nullptr;
+
+  cudaStream_t last_stream_ = nullptr;
+  bool have_last_ = false;
+  cudaEvent_t chain_event_ = nullptr;
+
+  int64_t p2p_off_ = 0, p2p_head_off_ = 0, p2p_tail_off_ = 0;
+  int64_t slot_bytes_ = 0;
+  int nslots_ = 0;
+  std::vector<cudaStream_t> send_streams_, recv_streams_;
+  std::vector<unsigned long long> send_chunks_, recv_chunks_;
+  std::vector<uint64_t> send_seq_;
+  std::unordered_map<int64_t, Request> requests_;
+  std::vector<std::list<int64_t>> posted_;          // per source: unmatched irecv ids in post order
+  std::vector<std::list<Unexpected>> unexpected_;   // per source
+  int64_t next_request_ = 1;
+  std::vector<cudaEvent_t> event_pool_;
+};
+
+}  // namespace m4t

@@ -1,0 +1,153 @@
+"""SPMD launcher: ``python -m mpi4torch_b200.launch -np N script.py [args...]``.
+
+Replaces ``mpirun -np N python script.py`` (reference ``README.md:53-56``,
+``.github/workflows/test.yml:64-84``): starts N ranks on this node, one OS
+process each, wires them with environment variables only
+(``RANK / WORLD_SIZE / LOCAL_RANK / LOCAL_WORLD_SIZE / M4T_JOB_ID`` plus
+``MASTER_ADDR / MASTER_PORT`` so ``torch.distributed`` baselines can rendezvous
+too), supervises them, and tears the whole job down as soon as one rank fails.
+The library itself never spawns processes.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import signal
+import socket
+import subprocess
+import sys
+import time
+import uuid
+from typing import List, Optional, Sequence
+
+
+def _free_port() -> int:
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cleanup_shm(job_id: str) -> None:
+    for path in glob.glob(f"/dev/shm/m4t_{job_id}_*"):
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
+def launch(
+    nprocs: int,
+    cmd: Sequence[str],
+    *,
+    timeout: Optional[float] = None,
+    env: Optional[dict] = None,
+    tag_output: bool = False,
+    cwd: Optional[str] = None,
+) -> int:
+    """Run ``cmd`` as ``nprocs`` ranks; returns the job's exit code (0 = all ranks ok)."""
+    if nprocs < 1:
+        raise ValueError("nprocs must be >= 1")
+    job_id = "j" + uuid.uuid4().hex[:12]
+    base = dict(os.environ if env is None else env)
+    base.update(
+        {
+            "WORLD_SIZE": str(nprocs),
+            "LOCAL_WORLD_SIZE": str(nprocs),
+            "M4T_JOB_ID": job_id,
+            "MASTER_ADDR": "127.0.0.1",
+            "MASTER_PORT": str(_free_port()),
+        }
+    )
+    procs: List[subprocess.Popen] = []
+    try:
+        for rank in range(nprocs):
+            e = dict(base)
+            e["RANK"] = str(rank)
+            e["LOCAL_RANK"] = str(rank)
+            kwargs = {}
+            if tag_output:
+                kwargs = dict(stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, bufsize=1)
+            procs.append(subprocess.Popen(list(cmd), env=e, cwd=cwd, **kwargs))
+        deadline = None if timeout is None else time.monotonic() + timeout
+        exit_code = 0
+        pending = set(range(nprocs))
+        readers = []
+        if tag_output:
+            import threading
+
+            def pump(rank: int, p: subprocess.Popen) -> None:
+                assert p.stdout is not None
+                for line in p.stdout:
+                    sys.stdout.write(f"[{rank}] {line}")
+                    sys.stdout.flush()
+
+            for r, p in enumerate(procs):
+                t = threading.Thread(target=pump, args=(r, p), daemon=True)
+                t.start()
+                readers.append(t)
+        while pending:
+            for r in list(pending):
+                rc = procs[r].poll()
+                if rc is None:
+                    continue
+                pending.discard(r)
+                if rc != 0 and exit_code == 0:
+                    exit_code = rc if rc > 0 else 128 - rc
+                    sys.stderr.write(f"[launch] rank {r} exited with code {rc}; terminating the job\n")
+                    _terminate(procs, pending)
+            if deadline is not None and time.monotonic() > deadline and pending:
+                sys.stderr.write(f"[launch] timeout after {timeout} s; terminating ranks {sorted(pending)}\n")
+                _terminate(procs, pending)
+                exit_code = exit_code or 124
+            time.sleep(0.02)
+        for t in readers:
+            t.join(timeout=1.0)
+        return exit_code
+    except KeyboardInterrupt:
+        _terminate(procs, set(range(len(procs))))
+        return 130
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        _cleanup_shm(job_id)
+
+
+def _terminate(procs: List[subprocess.Popen], pending: set) -> None:
+    for r in list(pending):
+        if procs[r].poll() is None:
+            try:
+                procs[r].send_signal(signal.SIGTERM)
+            except OSError:
+                pass
+    t0 = time.monotonic()
+    while time.monotonic() - t0 < 5.0 and any(procs[r].poll() is None for r in pending):
+        time.sleep(0.05)
+    for r in list(pending):
+        if procs[r].poll() is None:
+            procs[r].kill()
+
+
+def main(argv: Optional[Sequence[str]] = None) -> int:
+    ap = argparse.ArgumentParser(prog="python -m mpi4torch_b200.launch", description=__doc__.split("\n\n")[0])
+    ap.add_argument("-np", "-n", "--nproc", dest="np", type=int, required=True, help="number of ranks")
+    ap.add_argument("--timeout", type=float, default=None, help="kill the job after this many seconds")
+    ap.add_argument("--tag-output", action="store_true", help="prefix every output line with its rank")
+    ap.add_argument("-m", dest="module", default=None, help="run a module (python -m) instead of a script")
+    ap.add_argument("rest", nargs=argparse.REMAINDER, help="script and its arguments")
+    args = ap.parse_args(argv)
+    rest = list(args.rest)
+    if rest and rest[0] == "--":
+        rest = rest[1:]
+    if args.module:
+        cmd = [sys.executable, "-m", args.module] + rest
+    else:
+        if not rest:
+            ap.error("no script given")
+        cmd = [sys.executable] + rest if rest[0].endswith(".py") else rest
+    return launch(args.np, cmd, timeout=args.timeout, tag_output=args.tag_output)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
