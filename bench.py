@@ -1,0 +1,216 @@
+#!/usr/bin/env python
+"""Headline benchmark (driver contract: see the task brief / DESIGN.md).
+
+Flagship step = BASELINE.json config "4096x4096 linear layer: Allreduce(params)
+-> GEMM fused, loss Allreduce backward": every rank holds a 4096x4096 bf16
+weight and a private batch; one step averages the weights (Allreduce fused into
+the GEMM operand path), runs the forward GEMM, all-reduces the scalar loss,
+back-propagates (wgrad GEMM + the adjoint Allreduce) and applies SGD.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: under torchrun)
+    python bench.py --impl reference ...                      (reference arm)
+
+Prints ONE JSON line on rank 0.  `value` = samples/s over the whole job, timed
+on the device (CUDA events, max over ranks); `e2e` = the same step through the
+public API including per-step H2D of the batch from pinned memory and D2H of
+the loss.  Extra keys report the Allreduce fwd+bwd bus bandwidth sweep and the
+CPU linear-regression step/s named by BASELINE.json's metric string.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dp_linear4096_train_samples_per_s"
+IN_F = OUT_F = 4096
+PER_GPU_BATCH = 8192
+POOL = 4  # rotating input batches: 4 x (64 MiB x + 64 MiB t) >> 126 MB L2
+
+
+def reference_arm(args) -> int:
+    why = ("reference cannot be built: csrc/extension.cpp needs <mpi.h> and the image ships no MPI "
+           "(pip install --no-index --no-deps of /root/reference fails with 'mpi.h: No such file or directory'); "
+           "see DESIGN.md")
+    ref_dir = os.path.join(ROOT, "baseline", "_ref", "mpi4torch")
+    if os.path.isdir(ref_dir):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+            import mpi4torch  # noqa: F401
+
+            why = "reference imported unexpectedly; no MPI launcher (mpirun) exists in this image to run it"
+        except Exception as exc:  # pragma: no cover
+            why = f"reference import failed: {type(exc).__name__}: {exc}"[:300]
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the allreduce sweep / regression extras")
+    ap.add_argument("--unfused", action="store_true", help="force the unfused Allreduce + GEMM composition")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"metric": METRIC, "error": "no CUDA device visible"}), flush=True)
+        return 1
+    args.warmup = max(args.warmup, 3)
+
+    import mpi4torch_b200 as m4t
+    from mpi4torch_b200.models import DPLinearModel
+    from mpi4torch_b200.utils import ClockSampler
+
+    comm = m4t.COMM_WORLD
+    rank, size = comm.rank, comm.size
+    if size != args.gpus and rank == 0:
+        sys.stderr.write(f"[bench] warning: --gpus {args.gpus} but world size is {size}\n")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    assert m4t.cuda_backend_ready(), "native CUDA backend missing: refusing to benchmark a fallback"
+    _C = m4t._C
+    B = args.batch
+
+    torch.manual_seed(1234 + rank)
+    model = DPLinearModel(IN_F, OUT_F, comm, device=dev, dtype=torch.bfloat16, lr=1e-5, fused=not args.unfused)
+    xs = [torch.randn(B, IN_F, device=dev, dtype=torch.bfloat16) for _ in range(POOL)]
+    ts = [torch.randn(B, OUT_F, device=dev, dtype=torch.bfloat16) for _ in range(POOL)]
+
+    def step(i: int):
+        return model.train_step(xs[i % POOL], ts[i % POOL])
+
+    def max_ranks(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64)
+        return float(comm.Allreduce(t, m4t.MPI_MAX)[0])
+
+    # ---------------- device-timed region ----------------
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    comm.Barrier()
+    sampler = ClockSampler(gpu_index=dev.index).start() if rank == 0 else None
+    launches0 = _C.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    comm.Barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    comm.Barrier()
+    dev_ms = max_ranks(e0.elapsed_time(e1))
+    launches = _C.kernel_launch_count() - launches0
+    final_loss = float(loss)
+
+    # ---------------- end-to-end region (public API + H2D/D2H every step) ----------------
+    pin_x = [torch.randn(B, IN_F, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    pin_t = [torch.randn(B, OUT_F, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    dx = [torch.empty(B, IN_F, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    dt_ = [torch.empty(B, OUT_F, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i: int):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            dx[b].copy_(pin_x[b], non_blocking=True)
+            dt_[b].copy_(pin_t[b], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_steps(n: int) -> float:
+        last = 0.0
+        for b in range(2):
+            consumed[b].record()
+        prefetch(0)
+        for i in range(n):
+            b = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)
+            torch.cuda.current_stream().wait_event(ready[b])
+            value = model.train_step(dx[b], dt_[b])
+            consumed[b].record()
+            last = float(value)  # D2H read of the step's result
+        return last
+
+    e2e_steps(args.warmup)
+    torch.cuda.synchronize()
+    comm.Barrier()
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = max_ranks(time.perf_counter() - t0)
+    comm.Barrier()
+    clocks = sampler.stop() if sampler is not None else None
+
+    total_samples = float(B) * size * args.steps
+    value = total_samples / (dev_ms * 1e-3)
+    e2e_value = total_samples / e2e_s
+    flops_per_step = 2 * 2.0 * B * IN_F * OUT_F  # forward GEMM + wgrad GEMM, per GPU
+    out = {
+        "metric": METRIC,
+        "value": value,
+        "unit": "samples/s",
+        "n_gpus": size,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "bf16",
+        "data": "synthetic (random-init 4096x4096 weight, random batches)",
+        "impl": "ours",
+        "config": {
+            "model": "dp_linear_4096x4096 (Allreduce(params)->GEMM, loss Allreduce, SGD)",
+            "global_batch": B * size,
+            "seq_len": 1,
+            "parallelism": f"dp{size}",
+            "per_gpu_batch": B,
+            "cold_cache": f"inputs rotate over {POOL} batches (>= {POOL * 2 * B * IN_F * 2 >> 20} MiB) > 126 MB L2",
+            "fused_forward": bool(model.fused and size > 1),
+            "heap_mode": m4t.heap_mode(),
+            "nvls": m4t.has_nvls(),
+        },
+        "tflops_per_gpu": flops_per_step * args.steps / (dev_ms * 1e-3) / 1e12,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_value,
+            "unit": "samples/s",
+            "h2d_bytes_per_step": 2 * B * IN_F * 2,
+            "d2h_bytes_per_step": 4,
+            "ms_per_step": e2e_s * 1e3 / args.steps,
+        },
+        "final_loss": final_loss,
+    }
+    if not args.no_extras:
+        try:
+            from benchmarks.extras import allreduce_busbw_sweep
+
+            out["allreduce_fwd_bwd_busbw_gbs"] = allreduce_busbw_sweep(comm, dev, quick=True)
+        except Exception as exc:  # pragma: no cover
+            out["allreduce_fwd_bwd_busbw_gbs"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

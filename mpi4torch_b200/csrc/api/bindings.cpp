@@ -114,6 +114,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     else if (key == "force_algo") t.force_algo = static_cast<int>(value);
     else TORCH_CHECK(false, "unknown tuning key ", key);
   });
+  m.def("kernel_launch_count", [] { return static_cast<int64_t>(kernel_launch_count()); },
+        "Kernels launched by this library in this process.");
   m.def("check_device_error", [] {
     World& w = World::instance();
     if (w.cuda_ready()) w.cuda()->check_device_error();

@@ -18,6 +18,7 @@
 // is reduced exactly once by its owner, so all ranks obtain identical bits -
 // required for lock-step optimisers (reference doc/examples.rst:46-65).
 #include <algorithm>
+#include <atomic>
 
 #include "kernels.h"
 #include "vec_ops.cuh"
@@ -239,9 +240,16 @@ void launch_nvls(NvlsKind k, const ArArgs& a, int blocks, cudaStream_t s) {
 void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, what << " launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
 }
 
 }  // namespace
+
+namespace {
+std::atomic<unsigned long long> g_kernel_launches{0};
+}
+unsigned long long kernel_launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
+void note_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 
 bool nvls_supported(DType dt, ReduceOp op) { return nvls_kind(dt, op) != NvlsKind::NONE; }
 

@@ -24,6 +24,11 @@ struct DeviceComm {
   int sm_count;
 };
 
+// Number of kernels this library has launched in this process (bench.py's
+// "gpu_launches" evidence).
+unsigned long long kernel_launch_count();
+void note_kernel_launch();
+
 enum class ArAlgo : int { AUTO = 0, ONESHOT = 1, TWOSHOT = 2, NVLS = 3, LOCAL = 4 };
 
 // True if the (dtype, op) pair has an in-switch multimem.ld_reduce form we emit.

@@ -90,6 +90,7 @@ namespace {
 void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, what << " launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
 }
 
 P2pArgs make_args(const SyncCtx& sync, const P2pChannel& ch, void* user, int64_t bytes,

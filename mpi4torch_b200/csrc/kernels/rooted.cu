@@ -112,6 +112,7 @@ template <DType DT, ReduceOp OP> struct LaunchReduce {
 void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, what << " launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
 }
 
 RootedArgs make_args(const DeviceComm& dc, void* buf, int64_t n, DType dt, int root, int& blocks) {

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kThreads) zero_kernel(char* p, int64_t bytes, 
 void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, what << " launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
 }
 
 int64_t gcd64(int64_t a, int64_t b) {

@@ -1,0 +1,249 @@
+"""Coverage the reference's suite lacks (SURVEY section 4 "gaps"): non-SUM ops,
+integer / 16-bit dtypes, non-contiguous inputs, fused epilogues, large
+messages, double backward, error paths, pickling."""
+import io
+import pickle
+import unittest
+
+import torch
+
+import mpi4torch_b200 as m4t
+from common import DEVICE, comm, rand
+
+P, R = comm.size, comm.rank
+
+
+def per_rank(rank, n, dtype):
+    base = (torch.arange(n, dtype=torch.int64) * 3 + 5 * rank) % 11 - 4  # small ints incl. 0 and negatives
+    if dtype == torch.bool:
+        return (base % 2 == 0).to(DEVICE)
+    if dtype == torch.uint8:
+        return (base + 4).to(dtype).to(DEVICE)
+    return base.to(dtype).to(DEVICE)
+
+
+def reference_reduce(op, dtype, n):
+    xs = [per_rank(p, n, dtype) for p in range(P)]
+    work = torch.float64 if dtype.is_floating_point else (torch.bool if dtype == torch.bool else torch.int64)
+    acc = xs[0].to(work)
+    if op in (m4t.MPI_LAND, m4t.MPI_LOR, m4t.MPI_LXOR):
+        acc = acc != 0
+    for x in xs[1:]:
+        x = x.to(work)
+        if op == m4t.MPI_SUM:
+            acc = (acc + x) if dtype != torch.bool else (acc | x)
+        elif op == m4t.MPI_PROD:
+            acc = (acc * x) if dtype != torch.bool else (acc & x)
+        elif op == m4t.MPI_MAX:
+            acc = torch.maximum(acc, x)
+        elif op == m4t.MPI_MIN:
+            acc = torch.minimum(acc, x)
+        elif op == m4t.MPI_LAND:
+            acc = acc & (x != 0)
+        elif op == m4t.MPI_LOR:
+            acc = acc | (x != 0)
+        elif op == m4t.MPI_LXOR:
+            acc = acc ^ (x != 0)
+        elif op == m4t.MPI_BAND:
+            acc = acc & x
+        elif op == m4t.MPI_BOR:
+            acc = acc | x
+        elif op == m4t.MPI_BXOR:
+            acc = acc ^ x
+    return acc.to(dtype)
+
+
+class TestOpsAndDtypes(unittest.TestCase):
+    def test_arithmetic_ops_all_dtypes(self):
+        dtypes = [torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64, torch.float32, torch.float64,
+                  torch.bfloat16, torch.float16]
+        for dt in dtypes:
+            for op in (m4t.MPI_SUM, m4t.MPI_PROD, m4t.MPI_MAX, m4t.MPI_MIN):
+                if dt == torch.uint8 and op == m4t.MPI_PROD:
+                    continue  # wraps differently per world size; covered by int32
+                if dt in (torch.int8,) and op == m4t.MPI_PROD and P > 3:
+                    continue
+                y = comm.Allreduce(per_rank(R, 37, dt), op)
+                self.assertTrue(torch.equal(y, reference_reduce(op, dt, 37)), f"{dt} op {op}")
+
+    def test_logical_and_bitwise_ops(self):
+        for dt in (torch.uint8, torch.int32, torch.int64, torch.bool):
+            for op in (m4t.MPI_LAND, m4t.MPI_LOR, m4t.MPI_LXOR, m4t.MPI_BAND, m4t.MPI_BOR, m4t.MPI_BXOR):
+                y = comm.Allreduce(per_rank(R, 29, dt), op)
+                self.assertTrue(torch.equal(y, reference_reduce(op, dt, 29)), f"{dt} op {op}")
+
+    def test_logical_ops_on_floats(self):
+        for op in (m4t.MPI_LAND, m4t.MPI_LOR, m4t.MPI_LXOR):
+            y = comm.Allreduce(per_rank(R, 13, torch.float64), op)
+            self.assertTrue(torch.equal(y, reference_reduce(op, torch.float64, 13)))
+
+    def test_bitwise_on_float_and_loc_ops_raise(self):
+        x = rand(4)
+        for op in (m4t.MPI_BAND, m4t.MPI_BOR, m4t.MPI_BXOR, m4t.MPI_MINLOC, m4t.MPI_MAXLOC, 99, -1):
+            with self.assertRaises((ValueError, RuntimeError, IndexError)):
+                comm.Allreduce(x, op)
+
+    def test_unsupported_dtype_raises(self):
+        with self.assertRaises((ValueError, RuntimeError)):
+            comm.Allreduce(torch.zeros(3, dtype=torch.complex64, device=DEVICE), m4t.MPI_SUM)
+
+    def test_reduce_and_rooted_ops_non_sum(self):
+        x = per_rank(R, 21, torch.int32)
+        y = comm.Reduce_(x.clone(), m4t.MPI_MAX, P - 1)
+        if R == P - 1:
+            self.assertTrue(torch.equal(y, reference_reduce(m4t.MPI_MAX, torch.int32, 21)))
+        else:
+            self.assertTrue(torch.equal(y, torch.zeros_like(y)))
+
+    def test_non_sum_backward_raises_only_when_run(self):
+        x = rand(5, requires_grad=True)
+        y = comm.Allreduce(x, m4t.MPI_MAX)  # forward is fine
+        with self.assertRaises(RuntimeError):
+            y.sum().backward()
+
+
+class TestShapesAndLayouts(unittest.TestCase):
+    def test_non_contiguous_input(self):
+        x = (torch.arange(24, dtype=torch.double).reshape(4, 6) + R).to(DEVICE).t()
+        y = comm.Allreduce(x, m4t.MPI_SUM)
+        expect = sum((torch.arange(24, dtype=torch.double).reshape(4, 6) + p).to(DEVICE).t() for p in range(P))
+        self.assertTrue(torch.equal(y, expect))
+
+    def test_scalar_and_empty_tensors(self):
+        s = torch.tensor(float(R + 1), dtype=torch.double, device=DEVICE)
+        self.assertEqual(comm.Allreduce(s, m4t.MPI_SUM).item(), P * (P + 1) / 2)
+        e = torch.empty(0, 3, dtype=torch.double, device=DEVICE)
+        self.assertEqual(list(comm.Allreduce(e, m4t.MPI_SUM).shape), [0, 3])
+        g = comm.Allgather(torch.empty(2, 0, dtype=torch.double, device=DEVICE), 1)
+        self.assertEqual(list(g.shape), [2, 0])
+
+    def test_negative_axes(self):
+        x = (torch.arange(6, dtype=torch.double).reshape(2, 3) + 10 * R).to(DEVICE)
+        y = comm.Allgather(x, -1)
+        expect = torch.cat([(torch.arange(6, dtype=torch.double).reshape(2, 3) + 10 * p).to(DEVICE) for p in range(P)], dim=1)
+        self.assertTrue(torch.equal(y, expect))
+
+    def test_large_message_two_phase_path(self):
+        n = 300_001  # > 256 KiB of float64, odd length
+        x = (torch.arange(n, dtype=torch.double) % 1000 + R).to(DEVICE)
+        y = comm.Allreduce(x, m4t.MPI_SUM)
+        expect = P * (torch.arange(n, dtype=torch.double) % 1000).to(DEVICE) + P * (P - 1) / 2
+        self.assertTrue(torch.equal(y, expect))
+
+    def test_large_bf16_matches_fp32_reference(self):
+        n = 200_003
+        g = torch.Generator().manual_seed(1234)
+        xs = [torch.randn(n, generator=g).to(torch.bfloat16) for _ in range(P)]
+        y = comm.Allreduce(xs[R].to(DEVICE), m4t.MPI_SUM)
+        ref = sum(x.float() for x in xs)
+        # fp32 accumulation, one rounding at the end
+        self.assertTrue(torch.allclose(y.float().cpu(), ref, rtol=2 ** -7, atol=2 ** -7))
+        self.assertTrue(torch.equal(y.cpu(), comm.Bcast_(y.clone(), 0).cpu()))
+
+    def test_gather_scatter_integer_dtype(self):
+        x = (torch.arange(12, dtype=torch.int32).reshape(3, 4) + 100 * R).to(DEVICE)
+        y = comm.Allgather(x, 0)
+        self.assertTrue(torch.equal(y, torch.cat([(torch.arange(12, dtype=torch.int32).reshape(3, 4) + 100 * p).to(DEVICE)
+                                                  for p in range(P)], dim=0)))
+        z = comm.Alltoall(y, 1, 0, 3)
+        self.assertEqual(list(z.shape), [3, 4 * P])
+
+
+class TestFusedEpilogue(unittest.TestCase):
+    def test_scale_and_accumulate_forward_backward(self):
+        x = rand(33, requires_grad=True)
+        acc = rand(33, requires_grad=True)
+        y = comm.AllreduceFused(x, m4t.MPI_SUM, 1.0 / P, acc)
+        plain = comm.Allreduce(x.detach(), m4t.MPI_SUM) / P + acc.detach()
+        self.assertTrue(torch.allclose(y.detach(), plain, rtol=1e-14, atol=1e-14))
+        y.sum().backward()
+        self.assertTrue(torch.allclose(x.grad, torch.ones_like(x)))  # (1/P) * Allreduce(ones)
+        self.assertTrue(torch.equal(acc.grad, torch.ones_like(acc)))
+
+    def test_mean_of_parameters_is_identical_everywhere(self):
+        w = rand(1000)
+        m = comm.AllreduceFused(w, m4t.MPI_SUM, 1.0 / P, None)
+        self.assertTrue(torch.equal(m, comm.Bcast_(m.clone(), 0)))
+
+
+class TestHigherOrder(unittest.TestCase):
+    def test_double_backward_through_allreduce(self):
+        x = rand(6, requires_grad=True)
+        y = comm.Allreduce(x * x, m4t.MPI_SUM).sum()
+        (g,) = torch.autograd.grad(y, x, create_graph=True)
+        self.assertTrue(torch.allclose(g, 2 * P * x))
+        (h,) = torch.autograd.grad(g.sum(), x)
+        self.assertTrue(torch.allclose(h, 2.0 * P * torch.ones_like(x)))
+
+    def test_double_backward_through_allgather(self):
+        x = rand(2, 3, requires_grad=True)
+        y = (comm.Allgather(x, 0) ** 2).sum()
+        (g,) = torch.autograd.grad(y, x, create_graph=True)
+        self.assertTrue(torch.allclose(g, 2 * P * x))
+        (h,) = torch.autograd.grad(g.sum(), x)
+        self.assertTrue(torch.allclose(h, 2.0 * P * torch.ones_like(x)))
+
+
+class TestErrorsAndMisc(unittest.TestCase):
+    def test_scatter_count_mismatch_raises_on_every_rank(self):
+        x = rand(2, P + 1) if R == 0 else rand(1)
+        with self.assertRaises((ValueError, RuntimeError)):
+            comm.Scatter(x, 1, 1, 0)  # sum(numelem) = P != P + 1
+
+    def test_alltoall_count_mismatch_raises(self):
+        with self.assertRaises((ValueError, RuntimeError)):
+            comm.Alltoall(rand(2, 2 * P + 1), 0, 1, 2)
+
+    def test_root_out_of_range(self):
+        with self.assertRaises((ValueError, RuntimeError, IndexError)):
+            comm.Bcast_(rand(2), P)
+
+    def test_communicator_pickles_and_unpickles(self):
+        c = torch.ops.mpi4torch_b200.COMM_WORLD()
+        c2 = pickle.loads(pickle.dumps(c))
+        self.assertEqual(c2.GetRank(), R)
+        self.assertEqual(c2.GetSize(), P)
+
+    def test_scripted_module_with_communicator_round_trips(self):
+        class M(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.comm = torch.ops.mpi4torch_b200.COMM_WORLD()
+
+            def forward(self, x):
+                return self.comm.Allreduce(x, 2)
+
+        buf = io.BytesIO()
+        torch.jit.save(torch.jit.script(M()), buf)
+        buf.seek(0)
+        loaded = torch.jit.load(buf)
+        x = rand(4)
+        self.assertTrue(torch.equal(loaded(x), comm.Allreduce(x, m4t.MPI_SUM)))
+
+    def test_rank_size_and_barrier(self):
+        self.assertEqual(comm.size, P)
+        self.assertTrue(0 <= comm.rank < comm.size)
+        comm.Barrier()
+        self.assertIn("rank", comm.describe())
+
+    def test_mpi4py_shim(self):
+        class FakeComm:
+            def Get_size(self):
+                return P
+
+            def Get_rank(self):
+                return R
+
+        c = m4t.comm_from_mpi4py(FakeComm())
+        self.assertEqual((c.rank, c.size), (R, P))
+
+        class Wrong(FakeComm):
+            def Get_size(self):
+                return P + 1
+
+        with self.assertRaises(RuntimeError):
+            m4t.comm_from_mpi4py(Wrong())
+
+
+if __name__ == "__main__":
+    unittest.main()

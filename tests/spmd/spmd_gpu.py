@@ -1,0 +1,159 @@
+"""GPU-only checks of the NVLink backend: every allreduce algorithm against a
+plain fp32 PyTorch reference, misaligned / ragged tensors, big messages,
+stream semantics, host-staging toggle, large point-to-point transfers."""
+import os
+import unittest
+
+import torch
+
+import mpi4torch_b200 as m4t
+from common import DEVICE, comm
+
+P, R = comm.size, comm.rank
+CUDA = DEVICE.type == "cuda"
+_C = m4t._C
+
+
+def make(rank, n, dtype, seed=0):
+    g = torch.Generator().manual_seed(1000 * seed + rank)
+    if dtype.is_floating_point:
+        return torch.randn(n, generator=g).to(dtype)
+    return torch.randint(-50, 50, (n,), generator=g).to(dtype)
+
+
+def reference_sum(n, dtype, seed=0):
+    acc = torch.zeros(n, dtype=torch.float64)
+    for p in range(P):
+        acc += make(p, n, dtype, seed).double()
+    return acc
+
+
+@unittest.skipUnless(CUDA, "needs the CUDA backend")
+class TestBackendBringUp(unittest.TestCase):
+    def test_backend_is_native(self):
+        self.assertTrue(m4t.cuda_backend_ready())
+        if R == 0:
+            print(f"[gpu] {comm.describe()} heap_mode={m4t.heap_mode()} nvls={m4t.has_nvls()}", flush=True)
+        self.assertIn(m4t.heap_mode(), ("vmm+multicast", "vmm", "cudaIpc"))
+
+
+@unittest.skipUnless(CUDA, "needs the CUDA backend")
+class TestAllreduceAlgorithms(unittest.TestCase):
+    sizes = [1, 7, 8, 255, 4096, 65537, 1 << 20, (1 << 22) + 3]
+
+    def _run(self, algo, dtype, sizes):
+        _C.set_tuning("force_algo", algo)
+        try:
+            for n in sizes:
+                x = make(R, n, dtype).to(DEVICE)
+                y = comm.Allreduce(x, m4t.MPI_SUM)
+                ref = reference_sum(n, dtype)
+                got = y.double().cpu()
+                if dtype in (torch.float64, torch.int32, torch.int64):
+                    ok = torch.allclose(got, ref, rtol=1e-12, atol=1e-9)
+                elif dtype == torch.float32:
+                    ok = torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+                else:
+                    ok = torch.allclose(got, ref, rtol=2 ** -6, atol=2 ** -5)
+                self.assertTrue(ok, f"algo {algo} {dtype} n={n}: max err {(got - ref).abs().max().item()}")
+                # all ranks must hold identical bits
+                self.assertTrue(torch.equal(y, comm.Bcast_(y.clone(), 0)), f"algo {algo} {dtype} n={n} differs across ranks")
+        finally:
+            _C.set_tuning("force_algo", 0)
+
+    def test_oneshot(self):
+        for dt in (torch.float32, torch.bfloat16, torch.float64, torch.int32):
+            self._run(1, dt, [n for n in self.sizes if n <= (1 << 20)])
+
+    def test_twoshot(self):
+        for dt in (torch.float32, torch.bfloat16, torch.float16, torch.float64, torch.int64):
+            self._run(2, dt, self.sizes)
+
+    def test_nvls_or_auto(self):
+        algo = 3 if m4t.has_nvls() else 0
+        for dt in (torch.float32, torch.bfloat16, torch.float16):
+            self._run(algo, dt, self.sizes)
+
+    def test_min_max_16bit(self):
+        for op, fn in ((m4t.MPI_MAX, torch.maximum), (m4t.MPI_MIN, torch.minimum)):
+            for dt in (torch.bfloat16, torch.float16):
+                n = 100_003
+                x = make(R, n, dt).to(DEVICE)
+                y = comm.Allreduce(x, op)
+                ref = make(0, n, dt)
+                for p in range(1, P):
+                    ref = fn(ref, make(p, n, dt))
+                self.assertTrue(torch.equal(y.cpu(), ref))
+
+    def test_misaligned_views(self):
+        base = make(R, 10_007, torch.float32).to(DEVICE)
+        x = base[3:]  # 12-byte offset: not 16-byte aligned
+        y = comm.Allreduce(x, m4t.MPI_SUM)
+        ref = reference_sum(10_007, torch.float32)[3:]
+        self.assertTrue(torch.allclose(y.double().cpu(), ref, rtol=1e-5, atol=1e-5))
+
+    def test_fused_scale_accumulate_bf16(self):
+        n = 300_001
+        x = make(R, n, torch.bfloat16).to(DEVICE)
+        acc = make(R, n, torch.bfloat16, seed=5).to(DEVICE)
+        y = comm.AllreduceFused(x, m4t.MPI_SUM, 1.0 / P, acc)
+        ref = reference_sum(n, torch.bfloat16) / P + make(R, n, torch.bfloat16, seed=5).double()
+        self.assertTrue(torch.allclose(y.double().cpu(), ref, rtol=2 ** -6, atol=2 ** -5))
+
+    def test_large_message(self):
+        n = int(os.environ.get("M4T_TEST_BIG_ELEMS", str(32 * 1024 * 1024 + 5)))
+        x = torch.full((n,), float(R + 1), dtype=torch.bfloat16, device=DEVICE)
+        y = comm.Allreduce(x, m4t.MPI_SUM)
+        self.assertTrue(bool((y == P * (P + 1) / 2).all()))
+
+    def test_back_to_back_ops_reuse_staging_safely(self):
+        outs = []
+        for k in range(12):
+            x = torch.full((50_000 + k,), float(R + k), dtype=torch.float32, device=DEVICE)
+            outs.append((k, comm.Allreduce(x, m4t.MPI_SUM)))
+        for k, y in outs:
+            self.assertTrue(bool((y == P * k + P * (P - 1) / 2).all()), f"iteration {k}")
+
+    def test_collectives_on_a_side_stream(self):
+        s = torch.cuda.Stream()
+        x = torch.full((1 << 18,), float(R), dtype=torch.float32, device=DEVICE)
+        with torch.cuda.stream(s):
+            y = comm.Allreduce(x, m4t.MPI_SUM)
+        z = comm.Allreduce(x + 1, m4t.MPI_SUM)  # default stream, chained after the side stream
+        s.synchronize()
+        torch.cuda.synchronize()
+        self.assertTrue(bool((y == P * (P - 1) / 2).all()))
+        self.assertTrue(bool((z == P * (P - 1) / 2 + P).all()))
+
+
+@unittest.skipUnless(CUDA, "needs the CUDA backend")
+class TestHostStagingToggle(unittest.TestCase):
+    def test_staged_path_gives_the_same_answer(self):
+        x = make(R, 5000, torch.float32).to(DEVICE)
+        a = comm.Allreduce(x, m4t.MPI_SUM)
+        m4t.deactivate_cuda_aware_mpi_support()
+        try:
+            b = comm.Allreduce(x, m4t.MPI_SUM)
+            self.assertEqual(b.device, x.device)
+        finally:
+            m4t.activate_nvlink_transport()
+        self.assertTrue(torch.allclose(a, b, rtol=1e-5, atol=1e-5))
+
+
+@unittest.skipUnless(CUDA, "needs the CUDA backend")
+class TestLargeP2P(unittest.TestCase):
+    def test_80mb_ring(self):
+        n = 10_000_000  # the reference's message size (tests/test_nonblocking.py:9)
+        right, left = (R + 1) % P, (R + P - 1) % P
+        x = (torch.arange(n, dtype=torch.double, device=DEVICE) + R).requires_grad_()
+        s = comm.Isend(x, right, 0)
+        r = comm.Irecv(m4t.JoinDummies(torch.empty_like(x), [s.dummy]), left, 0)
+        sent = comm.Wait(m4t.JoinDummiesHandle(s, [r.dummy]))
+        got = comm.Wait(m4t.JoinDummiesHandle(r, [sent]))
+        (got * R).sum().backward()
+        self.assertTrue(torch.equal(got.detach(), torch.arange(n, dtype=torch.double, device=DEVICE) + left))
+        self.assertTrue(torch.equal(x.grad, right * torch.ones_like(x)))
+
+
+if __name__ == "__main__":
+    unittest.main()

@@ -1,0 +1,75 @@
+"""Single-process unit tests: world-size-1 semantics, 16-bit conversions of the
+CPU backend against torch, TorchScript parity, API surface."""
+import torch
+
+import mpi4torch_b200 as m4t
+
+
+def test_api_surface_matches_reference():
+    # reference src/__init__.py:5-25
+    for name in ["MPI_MAX", "MPI_MIN", "MPI_SUM", "MPI_PROD", "MPI_LAND", "MPI_BAND", "MPI_LOR", "MPI_BOR", "MPI_LXOR",
+                 "MPI_BXOR", "MPI_MINLOC", "MPI_MAXLOC", "WaitHandle", "JoinDummies", "JoinDummiesHandle",
+                 "MPI_Communicator", "COMM_WORLD", "comm_from_mpi4py", "deactivate_cuda_aware_mpi_support"]:
+        assert hasattr(m4t, name), name
+    assert [m4t.MPI_MAX, m4t.MPI_MIN, m4t.MPI_SUM, m4t.MPI_PROD, m4t.MPI_LAND, m4t.MPI_BAND, m4t.MPI_LOR, m4t.MPI_BOR,
+            m4t.MPI_LXOR, m4t.MPI_BXOR, m4t.MPI_MINLOC, m4t.MPI_MAXLOC] == list(range(12))
+    comm = m4t.COMM_WORLD
+    for method in ["Allreduce", "Bcast_", "Reduce_", "Gather", "Allgather", "Scatter", "Alltoall", "Isend", "Irecv",
+                   "Wait", "Send", "Recv", "Reduce_scatter", "AllreduceFused", "Barrier"]:
+        assert hasattr(comm, method), method
+
+
+def test_world_of_one_is_identity():
+    comm = m4t.COMM_WORLD
+    assert (comm.rank, comm.size) == (0, 1)
+    x = torch.rand(3, 4, dtype=torch.double, requires_grad=True)
+    y = comm.Allreduce(x, m4t.MPI_SUM)
+    assert torch.equal(y, x)
+    y.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    assert torch.equal(comm.Allgather(x.detach(), 1), x.detach())
+    assert torch.equal(comm.Alltoall(x.detach(), 0, 1, 4), x.detach())
+
+
+def test_half_precision_roundtrip_matches_torch():
+    # The CPU backend converts bf16/f16 <-> fp32 with its own bit-level code
+    # (csrc/runtime/reduce_ops.h); scale=1 allreduce at world size 1 exercises
+    # load -> fp32 -> store for every representable input class.
+    comm = m4t.COMM_WORLD
+    for dt in (torch.float16, torch.bfloat16):
+        bits = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16)
+        x = bits.view(dt)
+        y = comm.AllreduceFused(x, m4t.MPI_SUM, 1.0, None)
+        same = (y.view(torch.int16) == x.view(torch.int16)) | (torch.isnan(x.float()) & torch.isnan(y.float()))
+        assert bool(same.all()), dt
+        # a non-trivial scale must match torch's own rounding of the fp32 product
+        z = comm.AllreduceFused(x, m4t.MPI_SUM, 0.3, None)
+        ref = (x.float() * torch.tensor(0.3, dtype=torch.float32)).to(dt)
+        ok = (z.view(torch.int16) == ref.view(torch.int16)) | (torch.isnan(ref.float()) & torch.isnan(z.float()))
+        assert bool(ok.all()), dt
+
+
+def test_script_class_is_usable_from_torchscript():
+    @torch.jit.script
+    def f(t: torch.Tensor, c: m4t.MPI_Communicator) -> torch.Tensor:
+        h = c.Isend(t, c.rank, 1)
+        r = c.Recv(torch.empty_like(t), c.rank, 1)
+        return c.Wait(h) + r
+
+    t = torch.arange(5, dtype=torch.double)
+    assert torch.equal(f(t, m4t.COMM_WORLD), 2 * t)
+
+
+def test_node_names_are_kept_for_profilers():
+    comm = m4t.COMM_WORLD
+    x = torch.rand(4, dtype=torch.double, requires_grad=True)
+    assert "MPIAllreduceSumBackward" in comm.Allreduce(x, m4t.MPI_SUM).grad_fn.name()
+    assert "MPIGatherBackward" in comm.Gather(x, 0, 0).grad_fn.name()
+    assert "MPIAlltoallBackward" in comm.Alltoall(x.reshape(2, 2), 0, 1, 2).grad_fn.name()
+
+
+def test_host_staging_toggle_exists():
+    m4t.deactivate_cuda_aware_mpi_support()
+    x = torch.rand(4)
+    assert torch.equal(m4t.COMM_WORLD.Allreduce(x, m4t.MPI_SUM), x)
+    m4t.activate_nvlink_transport()
