@@ -85,6 +85,11 @@ __global__ void __launch_bounds__(kThreads) allreduce_oneshot_kernel(const ArArg
 }
 
 // TWOSHOT (NK == NONE) and NVLS (NK != NONE) share the chunked three-phase pipeline.
+// Every phase keeps kUnroll independent 16-byte requests in flight per thread:
+// the NVLink round trip is ~2 us, so memory-level parallelism, not the
+// instruction count, sets the bandwidth.
+constexpr int kUnroll = 4;
+
 template <DType DT, ReduceOp OP, NvlsKind NK>
 __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArgs a) {
   using V = VecOf<DT>;
@@ -105,55 +110,98 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
   for (int64_t base = 0; base < a.nvec; base += a.chunk_vecs) {
     const int64_t cc = min(a.chunk_vecs, a.nvec - base);
     const int64_t L = (cc + P - 1) / P;  // shard length inside this chunk
+    // items of this thread in the all-shard phases (A, C): (w, q) pairs, q fastest
+    const int64_t nw = first < L ? (L - first + gstride - 1) / gstride : 0;
+    const int64_t nitems = nw * P;
     // ---- phase A: stage my part of every shard (block b owns pattern b of each shard)
-    for (int64_t w = first; w < L; w += gstride) {
-#pragma unroll 1
-      for (int q = 0; q < P; ++q) {
-        const int64_t i = static_cast<int64_t>(q) * L + w;
-        if (i < cc) st_vec(my_in + (base + i) * 16, load_private<DT>(a.in, base + i, a.n, al));
+    for (int64_t j0 = 0; j0 < nitems; j0 += kUnroll) {
+      Vec16 v[kUnroll];
+      int64_t idx[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t j = j0 + u;
+        const int64_t i = (j % P) * L + first + (j / P) * gstride;
+        idx[u] = (j < nitems && i < cc) ? i : -1;
+        if (idx[u] >= 0) v[u] = load_private<DT>(a.in, base + idx[u], a.n, al);
       }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (idx[u] >= 0) st_vec(my_in + (base + idx[u]) * 16, v[u]);
     }
     block_barrier_all(c, fb, bar++);
     // ---- phase B: reduce shard r
-    for (int64_t w = first; w < L; w += gstride) {
-      const int64_t i = static_cast<int64_t>(r) * L + w;
-      if (i >= cc) continue;
-      const int64_t off = (base + i) * 16;
+    for (int64_t w0 = 0; w0 < nw; w0 += kUnroll) {
+      int64_t off[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t i = static_cast<int64_t>(r) * L + first + (w0 + u) * gstride;
+        off[u] = (w0 + u < nw && i < cc) ? (base + i) * 16 : -1;
+      }
       if constexpr (NK != NvlsKind::NONE) {
-        Vec16 v = multimem_ld_reduce_vec<NK>(a.mc_heap + in_off + off);
-        if (a.epi.has_scale) {
-          typename V::A acc[V::N];
-          V::unpack(v, acc);
-          apply_scale<DT>(acc, a.epi);
-          v = V::pack(acc);
+        Vec16 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (off[u] >= 0) v[u] = multimem_ld_reduce_vec<NK>(a.mc_heap + in_off + off[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (off[u] < 0) continue;
+          if (a.epi.has_scale) {
+            typename V::A acc[V::N];
+            V::unpack(v[u], acc);
+            apply_scale<DT>(acc, a.epi);
+            v[u] = V::pack(acc);
+          }
+          multimem_st_vec(a.mc_heap + out_off + off[u], v[u]);
         }
-        multimem_st_vec(a.mc_heap + out_off + off, v);
       } else {
-        typename V::A acc[V::N];
-        init_from<DT, OP>(acc, ld_vec_sys(a.heap[0] + in_off + off));
+        typename V::A acc[kUnroll][V::N];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (off[u] >= 0) init_from<DT, OP>(acc[u], ld_vec_sys(a.heap[0] + in_off + off[u]));
 #pragma unroll 1
-        for (int p = 1; p < P; ++p) combine_into<DT, OP>(acc, ld_vec_sys(a.heap[p] + in_off + off));
-        apply_scale<DT>(acc, a.epi);
-        st_vec(my_out + off, V::pack(acc));
+        for (int p = 1; p < P; ++p) {
+          Vec16 v[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (off[u] >= 0) v[u] = ld_vec_sys(a.heap[p] + in_off + off[u]);
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (off[u] >= 0) combine_into<DT, OP>(acc[u], v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          if (off[u] < 0) continue;
+          apply_scale<DT>(acc[u], a.epi);
+          st_vec(my_out + off[u], V::pack(acc[u]));
+        }
       }
     }
     block_barrier_all(c, fb, bar++);
     // ---- phase C: collect all shards (NVLS: already in my HBM; TWOSHOT: pull from owners)
-    for (int64_t w = first; w < L; w += gstride) {
-#pragma unroll 1
-      for (int q = 0; q < P; ++q) {
-        const int64_t i = static_cast<int64_t>(q) * L + w;
-        if (i >= cc) continue;
-        const int64_t off = (base + i) * 16;
-        const char* src = (NK != NvlsKind::NONE) ? my_out : (a.heap[q] + out_off);
-        Vec16 v = ld_vec_sys(src + off);
+    for (int64_t j0 = 0; j0 < nitems; j0 += kUnroll) {
+      Vec16 v[kUnroll];
+      int64_t idx[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t j = j0 + u;
+        const int q = static_cast<int>(j % P);
+        const int64_t i = static_cast<int64_t>(q) * L + first + (j / P) * gstride;
+        idx[u] = (j < nitems && i < cc) ? i : -1;
+        if (idx[u] >= 0) {
+          const char* src = (NK != NvlsKind::NONE) ? my_out : (a.heap[q] + out_off);
+          v[u] = ld_vec_sys(src + (base + idx[u]) * 16);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (idx[u] < 0) continue;
         if (a.epi.acc) {
           typename V::A acc[V::N];
-          V::unpack(v, acc);
-          apply_accumulate<DT>(acc, a.epi, base + i, a.n, al);
-          v = V::pack(acc);
+          V::unpack(v[u], acc);
+          apply_accumulate<DT>(acc, a.epi, base + idx[u], a.n, al);
+          v[u] = V::pack(acc);
         }
-        store_private<DT>(a.out, base + i, a.n, al, v);
+        store_private<DT>(a.out, base + idx[u], a.n, al, v[u]);
       }
     }
   }

@@ -1,0 +1,392 @@
+// tcgen05 GEMM for the linear layer:  C[M,N] = A[M,K] * B[N,K]^T   (bf16 in,
+// fp32 accumulate in TMEM, bf16 out) - and its fused form, where the B operand
+// is the rank-average of every rank's weight and is produced INSIDE the same
+// kernel by communication warps (fused_allreduce_gemm, below).
+//
+// Structure (one persistent CTA per SM, 128x256 output tiles, BK = 64):
+//   warp 0      TMA producer   : cp.async.bulk.tensor A/B tiles -> 4-stage smem ring
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (UMMA 128x256x16),
+//                                accumulators double-buffered in TMEM (2 x 256 columns)
+//   warps 2..5  epilogue       : tcgen05.ld -> bf16 -> 16-byte global stores,
+//                                overlapping the next tile's MMAs
+//   warps 6..9  communication  : (fused kernel only) NVLS reduce of weight panels:
+//                                multimem.ld_reduce over all ranks' weights ->
+//                                x 1/size -> multimem.st into every rank's W_avg ->
+//                                multimem.red on the panel counter.  The TMA
+//                                producer polls that counter before loading a
+//                                panel, so the all-reduce of panel p+1.. overlaps
+//                                the MMAs on panel p.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+
+#include "kernels.h"
+#include "tcgen05_ptx.cuh"
+#include "vec_ops.cuh"
+
+namespace m4t {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kABytes = BM * BK * 2;   // 16 KiB
+constexpr int kBBytes = BN * BK * 2;   // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kGemmWarps = 6;
+constexpr int kCommWarps = 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+  void* C;
+  int M, N, K;
+  int ldc;
+  // fused mode ----------------------------------------------------------------
+  const uint32_t* panel_flags;  // [N / BN] counters in local HBM (written through multicast)
+  uint32_t panel_target;        // a panel is ready when its counter >= target (wrap-safe)
+};
+
+struct CommArgs {
+  SyncCtx sync;
+  char* mc_heap;        // multicast mapping of the symmetric heap
+  char* my_heap;
+  int64_t w_off;        // byte offset of the (staged) weight inside every rank's heap
+  int64_t wavg_off;     // byte offset of the W_avg buffer inside every rank's heap
+  int64_t flags_off;    // byte offset of the panel counters
+  float scale;
+  int do_barrier;       // 1: cross-rank barrier before the first multimem.ld_reduce
+};
+
+struct __align__(8) SharedBarriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return static_cast<uint32_t>(float_to_bf16_bits(lo)) | (static_cast<uint32_t>(float_to_bf16_bits(hi)) << 16);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__((kGemmWarps + (FUSED ? kCommWarps : 0)) * 32, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmArgs g, const CommArgs cm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SharedBarriers* bars = reinterpret_cast<SharedBarriers*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&bars->full[s], 1);
+      tc::mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      tc::mbar_init(&bars->tmem_full[a], 1);
+      tc::mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<kTmemCols>(&bars->tmem_base);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t / m_tiles;  // M fastest: a wave works on few weight panels
+        const int m_blk = t - n_blk * m_tiles;
+        if (FUSED) {
+          // the weight panel must have been all-reduced (by every rank) first
+          const uint32_t* flag = g.panel_flags + n_blk;
+          while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - g.panel_target) < 0) {
+          }
+          tc::fence_proxy_async();  // generic-proxy writes (multimem.st) -> async-proxy reads (TMA)
+        }
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tc::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          tc::mbar_arrive_expect_tx(&bars->full[stage], kStageBytes);
+          tc::tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * BK, m_blk * BM);
+          tc::tma_load_2d(sb, &tmap_b, &bars->full[stage], kb * BK, n_blk * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer =============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+        tc::tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tc::mbar_wait(&bars->full[stage], phase);
+          tc::tcgen05_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t adesc = tc::make_smem_desc_k_sw128(sa);
+          const uint64_t bdesc = tc::make_smem_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+            tc::umma_bf16_ss(tmem_d, adesc + koff, bdesc + koff, idesc, (kb | k) ? 1u : 0u);
+          }
+          tc::umma_commit(&bars->empty[stage]);  // smem stage reusable once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp < kGemmWarps) {
+    // =========================== epilogue ===============================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int n_blk = t / m_tiles;
+      const int m_blk = t - n_blk * m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      tc::mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc::tcgen05_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      uint16_t* crow = static_cast<uint16_t*>(g.C) + static_cast<int64_t>(row) * g.ldc + n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32);
+        tc::tmem_ld_32x32b_x32(taddr, r);
+        tc::tmem_ld_wait();
+        if (row < g.M) {
+          const int col0 = n_blk * BN + c * 32;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (col0 + v * 8 + 8 <= g.N) {
+              Vec16 o;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o.w[e] = pack_bf16x2(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+              st_vec(crow + c * 32 + v * 8, o);
+            }
+          }
+        }
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->tmem_empty[acc]);
+    }
+  } else if (FUSED) {
+    // =========================== communication ==========================
+    // All-reduce the weight, panel by panel (panel = BN rows of W).  Rank r owns
+    // rows [r*BN/P, (r+1)*BN/P) of every panel; CTA b handles the 16-byte
+    // vectors v = b, b+G, ... of that slice, so "block b on every rank" is a
+    // closed group and a per-block barrier is all the ordering needed.
+    const SyncCtx& c = cm.sync;
+    const int P = c.size, r = c.rank;
+    const int ct = threadIdx.x - kGemmWarps * 32;  // 0..127
+    constexpr int kCommThreads = kCommWarps * 32;
+    unsigned long long fb = 0;
+    if (cm.do_barrier) {
+      // every rank's weight (in its heap) is final before anyone reduces it
+      fb = read_flag_base(c);
+      asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
+      if (ct < P && ct != r) {
+        const uint32_t v = static_cast<uint32_t>(fb + 1ull);
+        st_release_sys_u32(c.pads[ct] + blockIdx.x * kMaxGpuPeers + r, v);
+        wait_flag_ge(c.pads[r] + blockIdx.x * kMaxGpuPeers + ct, v, c);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
+    }
+    const int64_t row_bytes = static_cast<int64_t>(g.K) * 2;
+    const int rows_per_rank = BN / P;                      // host guarantees divisibility
+    const int64_t slice_vecs = rows_per_rank * row_bytes / 16;
+    DevEpilogue e;
+    e.scale_f = cm.scale;
+    e.scale_d = cm.scale;
+    e.has_scale = 1;
+    e.acc = nullptr;
+    uint32_t* mc_flags = reinterpret_cast<uint32_t*>(cm.mc_heap + cm.flags_off);
+    for (int p = 0; p < n_tiles; ++p) {
+      const int64_t base = (static_cast<int64_t>(p) * BN + static_cast<int64_t>(r) * rows_per_rank) * row_bytes;
+      for (int64_t v = static_cast<int64_t>(blockIdx.x) * kCommThreads + ct; v < slice_vecs;
+           v += static_cast<int64_t>(gridDim.x) * kCommThreads) {
+        Vec16 x = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(cm.mc_heap + cm.w_off + base + v * 16);
+        float a[8];
+        VecOf<DType::BF16>::unpack(x, a);
+        apply_scale<DType::BF16>(a, e);
+        multimem_st_vec(cm.mc_heap + cm.wavg_off + base + v * 16, VecOf<DType::BF16>::pack(a));
+      }
+      // publish: my part of panel p is in every rank's W_avg
+      asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
+      if (ct == 0) {
+        __threadfence_system();
+        asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_flags + p), "r"(1u) : "memory");
+      }
+    }
+    if (cm.do_barrier && ct == 0) {
+      // advance the communicator's flag/op counters exactly like finish_op()
+      __threadfence();
+      const unsigned int prev = atomicAdd(c.done_ctr, 1u);
+      if (prev == gridDim.x - 1) {
+        *c.done_ctr = 0;
+        __threadfence();
+        atomicAdd(c.counters + 0, 1ull);
+        atomicAdd(c.counters + 1, 1ull);
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    M4T_CHECK(e == cudaSuccess && q == cudaDriverEntryPointSuccess && p, "cuTensorMapEncodeTiled unavailable");
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128-byte swizzle.
+CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M4T_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " << static_cast<int>(r));
+  return m;
+}
+
+void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  M4T_CHECK(e == cudaSuccess, what << " launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
+}
+
+template <bool FUSED> void configure_once() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
+  });
+}
+
+}  // namespace
+
+bool gemm_bf16_tn_supported(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C, int64_t lda,
+                            int64_t ldb, int64_t ldc) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return M > 0 && N > 0 && K > 0 && (K % 8) == 0 && (N % 8) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 8) == 0 &&
+         al16(A) && al16(B) && al16(C) && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31);
+}
+
+void launch_gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream) {
+  M4T_CHECK(gemm_bf16_tn_supported(M, N, K, A, B, C, lda, ldb, ldc), "unsupported GEMM shape/alignment for the tcgen05 path");
+  configure_once<false>();
+  const CUtensorMap ta = make_tmap(A, M, K, lda, BM);
+  const CUtensorMap tb = make_tmap(B, N, K, ldb, BN);
+  GemmArgs g{};
+  g.C = C;
+  g.M = static_cast<int>(M);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldc = static_cast<int>(ldc);
+  g.panel_flags = nullptr;
+  g.panel_target = 0;
+  CommArgs cm{};
+  const int tiles = static_cast<int>(((M + BM - 1) / BM) * ((N + BN - 1) / BN));
+  const int grid = std::max(1, std::min(tiles, sm_count));
+  gemm_bf16_tn_kernel<false><<<grid, kGemmWarps * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  check_launch("gemm_bf16_tn");
+}
+
+// y = x @ mean_ranks(W)^T in ONE kernel.  `w_off`/`wavg_off`/`flags_off` are
+// byte offsets inside the symmetric heap (identical on all ranks); the weight
+// must already be staged at w_off on every rank.
+void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
+                                 int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
+                                 uint32_t panel_target, float scale, cudaStream_t stream) {
+  M4T_CHECK(dc.mc_heap != nullptr, "the fused Allreduce->GEMM kernel needs the NVLS multicast mapping");
+  const int P = dc.sync.size;
+  M4T_CHECK(BN % P == 0 && N % BN == 0 && (K * 2) % 16 == 0, "fused Allreduce->GEMM: N must be a multiple of 256 and 256 % ranks == 0");
+  const char* wavg = dc.heap[dc.sync.rank] + wavg_off;
+  M4T_CHECK(gemm_bf16_tn_supported(M, N, K, x, wavg, y, ldx, K, ldy), "unsupported GEMM shape/alignment for the fused path");
+  configure_once<true>();
+  const CUtensorMap ta = make_tmap(x, M, K, ldx, BM);
+  const CUtensorMap tb = make_tmap(wavg, N, K, K, BN);
+  GemmArgs g{};
+  g.C = y;
+  g.M = static_cast<int>(M);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldc = static_cast<int>(ldy);
+  g.panel_flags = reinterpret_cast<const uint32_t*>(dc.heap[dc.sync.rank] + flags_off);
+  g.panel_target = panel_target;
+  CommArgs cm{};
+  cm.sync = dc.sync;
+  cm.mc_heap = dc.mc_heap;
+  cm.my_heap = dc.heap[dc.sync.rank];
+  cm.w_off = w_off;
+  cm.wavg_off = wavg_off;
+  cm.flags_off = flags_off;
+  cm.scale = scale;
+  cm.do_barrier = 1;
+  // the grid must be identical on every rank (per-block barrier + counter targets)
+  const int grid = std::min(dc.sm_count, kMaxChannels);
+  gemm_bf16_tn_kernel<true><<<grid, (kGemmWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  check_launch("fused_allreduce_gemm");
+}
+
+int fused_gemm_grid(const DeviceComm& dc) { return std::min(dc.sm_count, kMaxChannels); }
+
+}  // namespace m4t

@@ -84,6 +84,20 @@ void launch_p2p_send(const SyncCtx& sync, const P2pChannel& ch, const void* src,
 void launch_p2p_recv(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64_t bytes,
                      unsigned long long first_chunk, int blocks, cudaStream_t stream);
 
+// ---- tcgen05 GEMM + fused Allreduce->GEMM (gemm_tcgen05.cu) --------------------
+bool gemm_bf16_tn_supported(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C, int64_t lda,
+                            int64_t ldb, int64_t ldc);
+// C[M,N] = A[M,K] * B[N,K]^T, bf16 in / fp32 accumulate (TMEM) / bf16 out.
+void launch_gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream);
+// y = x @ (scale * sum_ranks W)^T in one kernel; W staged at heap offset w_off on every rank.
+void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
+                                 int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
+                                 uint32_t panel_target, float scale, cudaStream_t stream);
+int fused_gemm_grid(const DeviceComm& dc);
+// Plain device copy into the heap (used to stage the weight for the fused kernel).
+void launch_copy_bytes(void* dst, const void* src, int64_t bytes, int sm_count, cudaStream_t stream);
+
 // Fills `n` bytes with zero (used for non-root results / backward recv buffers).
 void launch_zero(void* p, int64_t bytes, int sm_count, cudaStream_t stream);
 

@@ -324,6 +324,38 @@ void build_pull_args(SlabArgs& a, const PullPlan& plan, const void* in, void* ou
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(kThreads) copy_bytes_kernel(char* dst, const char* src, int64_t bytes, int aligned) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (aligned) {
+    const int64_t nvec = bytes / 16;
+    int64_t i = tid;
+    // 4 independent 16-byte loads in flight per thread
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      const Vec16 a = ld_vec_stream(src + i * 16), b = ld_vec_stream(src + (i + stride) * 16),
+                  c = ld_vec_stream(src + (i + 2 * stride) * 16), d = ld_vec_stream(src + (i + 3 * stride) * 16);
+      st_vec(dst + i * 16, a);
+      st_vec(dst + (i + stride) * 16, b);
+      st_vec(dst + (i + 2 * stride) * 16, c);
+      st_vec(dst + (i + 3 * stride) * 16, d);
+    }
+    for (; i < nvec; i += stride) st_vec(dst + i * 16, ld_vec_stream(src + i * 16));
+    for (int64_t j = nvec * 16 + tid; j < bytes; j += stride) dst[j] = src[j];
+  } else {
+    for (int64_t j = tid; j < bytes; j += stride) dst[j] = src[j];
+  }
+}
+}  // namespace
+
+void launch_copy_bytes(void* dst, const void* src, int64_t bytes, int sm_count, cudaStream_t stream) {
+  if (bytes <= 0) return;
+  const int aligned = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0;
+  const int blocks = static_cast<int>(std::min<int64_t>((bytes / 64 + kThreads) / kThreads, 4LL * sm_count));
+  copy_bytes_kernel<<<blocks, kThreads, 0, stream>>>(static_cast<char*>(dst), static_cast<const char*>(src), bytes, aligned);
+  check_launch("copy_bytes");
+}
+
 void launch_zero(void* p, int64_t bytes, int sm_count, cudaStream_t stream) {
   if (bytes <= 0) return;
   const int aligned = (reinterpret_cast<uintptr_t>(p) & 15u) == 0;

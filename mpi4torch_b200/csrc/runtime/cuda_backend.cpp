@@ -40,7 +40,10 @@ CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) 
   const int64_t p2p_bytes = static_cast<int64_t>(P) * nslots_ * slot_bytes_;
   const int64_t stage_off = round_up64(p2p_off_ + p2p_bytes, 2 << 20);
   const int64_t half = P > 1 ? round_up64(env_i64("M4T_STAGE_MB", 2176) << 20, 2 << 20) : 0;
-  heap_ = std::make_unique<SymmHeap>(ctl_, device_, static_cast<size_t>(stage_off + 2 * half));
+  symm_off_ = stage_off + 2 * half;
+  symm_bytes_ = P > 1 ? round_up64(env_i64("M4T_SYMM_MB", 512) << 20, 2 << 20) : 0;
+  symm_cursor_ = 0;
+  heap_ = std::make_unique<SymmHeap>(ctl_, device_, static_cast<size_t>(symm_off_ + symm_bytes_));
 
   M4T_CUDA(cudaMalloc(&d_counters_, 2 * sizeof(unsigned long long)));
   M4T_CUDA(cudaMemset(d_counters_, 0, 2 * sizeof(unsigned long long)));
@@ -259,6 +262,59 @@ void CudaBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out,
 }
 
 // ---------------------------------------------------------------------------
+// tensor-core paths
+// ---------------------------------------------------------------------------
+int64_t CudaBackend::symm_alloc(int64_t bytes) {
+  const int64_t need = round_up64(std::max<int64_t>(bytes, 16), 1024);
+  M4T_CHECK(symm_cursor_ + need <= symm_bytes_, "symmetric user arena exhausted (" << symm_bytes_
+                                                    << " B); raise M4T_SYMM_MB");
+  const int64_t off = symm_off_ + symm_cursor_;
+  symm_cursor_ += need;
+  return off;
+}
+
+bool CudaBackend::fused_linear_available(int64_t N, int64_t K) const {
+  if (size() <= 1 || !has_nvls()) return false;
+  if (env_i64("M4T_FUSED_LINEAR", 1) == 0) return false;
+  if (N % 256 != 0 || 256 % size() != 0 || K % 64 != 0) return false;
+  const int64_t need = 3 * N * K * 2 + 4096;
+  return fused_.count((N << 32) | K) > 0 || symm_cursor_ + need + 4096 <= symm_bytes_;
+}
+
+void CudaBackend::gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                               int64_t ldb, int64_t ldc, cudaStream_t stream) {
+  M4T_CUDA(cudaSetDevice(device_));
+  launch_gemm_bf16_tn(A, B, C, M, N, K, lda, ldb, ldc, dc_.sm_count, stream);
+}
+
+const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
+                                                int64_t ldx, int64_t ldy, float scale, cudaStream_t stream) {
+  check_device_error();
+  M4T_CHECK(fused_linear_available(N, K), "fused Allreduce->GEMM unavailable for N=" << N << " K=" << K);
+  M4T_CUDA(cudaSetDevice(device_));
+  const int64_t key = (N << 32) | K;
+  auto it = fused_.find(key);
+  if (it == fused_.end()) {
+    FusedLinearState st;
+    st.w_off = symm_alloc(N * K * 2);
+    st.wavg_off[0] = symm_alloc(N * K * 2);
+    st.wavg_off[1] = symm_alloc(N * K * 2);
+    st.flags_off = symm_alloc((N / 256) * 4);
+    it = fused_.emplace(key, st).first;
+  }
+  FusedLinearState& st = it->second;
+  chain(stream);
+  // stage this rank's weight where the switch can read it
+  launch_copy_bytes(symm_ptr(st.w_off), w, N * K * 2, dc_.sm_count, stream);
+  const int par = static_cast<int>(st.calls & 1);
+  st.calls += 1;
+  const uint32_t target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
+  launch_fused_allreduce_gemm(dc_, x, y, M, N, K, ldx, ldy, st.w_off, st.wavg_off[par], st.flags_off, target, scale,
+                              stream);
+  return symm_ptr(st.wavg_off[par]);
+}
+
+// ---------------------------------------------------------------------------
 // point-to-point
 // ---------------------------------------------------------------------------
 cudaStream_t CudaBackend::send_stream(int peer) {
@@ -306,6 +362,7 @@ int64_t CudaBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag
   M4T_CUDA(cudaStreamWaitEvent(ss, ready, 0));
   free_event(ready);
   const unsigned long long first = send_chunks_[dest];
+  M4T_LOG("rank %d isend -> %d tag %ld bytes %ld first_chunk %llu stream %p", rank(), dest, (long)tag, (long)bytes, first, (void*)user);
   launch_p2p_send(dc_.sync, send_channel(dest), buf, bytes, first, tune_.p2p_blocks, ss);
   send_chunks_[dest] += static_cast<unsigned long long>(p2p_num_chunks(bytes, slot_bytes_));
   Request rq;
@@ -341,6 +398,8 @@ void CudaBackend::launch_recv(const MsgDesc& d, int source, void* dst, cudaEvent
   std::memcpy(&first, d.inline_data, sizeof(first));
   M4T_CHECK(first == recv_chunks_[source], "p2p FIFO out of sync with rank " << source << " (expected chunk "
                                                << recv_chunks_[source] << ", message starts at " << first << ")");
+  M4T_LOG("rank %d launch_recv <- %d tag %ld bytes %ld first_chunk %llu dst %p ready %p", rank(), source, (long)d.tag,
+          (long)d.bytes, first, dst, (void*)ready);
   launch_p2p_recv(dc_.sync, recv_channel(source), dst, static_cast<int64_t>(d.bytes), first, tune_.p2p_blocks, rs);
   recv_chunks_[source] += static_cast<unsigned long long>(p2p_num_chunks(static_cast<int64_t>(d.bytes), slot_bytes_));
   M4T_CUDA(cudaEventRecord(done, rs));
@@ -407,6 +466,7 @@ int64_t CudaBackend::irecv(void* buf, int64_t bytes, int source, int64_t tag, vo
   rq.ready = new_event();
   M4T_CUDA(cudaEventRecord(rq.ready, static_cast<cudaStream_t>(stream)));
   const int64_t id = next_request_++;
+  M4T_LOG("rank %d irecv <- %d tag %ld bytes %ld req %ld buf %p stream %p", rank(), source, (long)tag, (long)bytes, (long)id, buf, stream);
   // an earlier unexpected message with this tag?
   auto& ux = unexpected_[source];
   for (auto it = ux.begin(); it != ux.end(); ++it) {
@@ -437,6 +497,8 @@ void CudaBackend::wait(int64_t request, void* stream) {
   }
   Request rq = it->second;
   requests_.erase(it);
+  M4T_LOG("rank %d wait req %ld (%s peer %d tag %ld) stream %p", rank(), (long)request, rq.is_recv ? "recv" : "send", rq.peer,
+          (long)rq.tag, stream);
   M4T_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), rq.done, 0));
   free_event(rq.done);
   free_event(rq.ready);

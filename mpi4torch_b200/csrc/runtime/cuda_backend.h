@@ -58,6 +58,19 @@ class CudaBackend final : public Backend {
                       ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream);
   ArAlgo pick_algo(int64_t bytes, DType dt, ReduceOp op) const;
 
+  // ---- tensor-core paths -------------------------------------------------------
+  // Collective-order bump allocation inside the heap's persistent user arena
+  // (every rank must call it with the same sizes in the same order).
+  int64_t symm_alloc(int64_t bytes);
+  char* symm_ptr(int64_t off) const { return dc_.heap[dc_.sync.rank] + off; }
+  bool fused_linear_available(int64_t N, int64_t K) const;
+  // y[M,N] = x[M,K] @ (scale * sum_ranks w[N,K])^T; returns the address of the
+  // averaged weight (valid until the call after next).
+  const void* fused_allreduce_linear(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
+                                     int64_t ldx, int64_t ldy, float scale, cudaStream_t stream);
+  void gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    int64_t ldc, cudaStream_t stream);
+
   // Throws if a device-side wait timed out since the last check.
   void check_device_error();
   // Symmetric scratch for fused kernels (e.g. Allreduce->GEMM): bytes inside the current staging half.
@@ -118,6 +131,13 @@ class CudaBackend final : public Backend {
   std::vector<std::list<Unexpected>> unexpected_;   // per source
   int64_t next_request_ = 1;
   std::vector<cudaEvent_t> event_pool_;
+
+  struct FusedLinearState {
+    int64_t w_off = 0, wavg_off[2] = {0, 0}, flags_off = 0;
+    uint64_t calls = 0;
+  };
+  std::unordered_map<int64_t, FusedLinearState> fused_;  // key = N << 32 | K
+  int64_t symm_off_ = 0, symm_cursor_ = 0, symm_bytes_ = 0;
 };
 
 }  // namespace m4t

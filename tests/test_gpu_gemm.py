@@ -1,0 +1,53 @@
+"""tcgen05 GEMM numerics against a plain fp32 PyTorch reference."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w):
+    return (x.float() @ w.float().t())
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 64), (256, 512, 128), (384, 256, 4096), (4096, 4096, 4096),
+                                   (8192, 4096, 4096), (130, 264, 72), (1, 8, 8), (1000, 1000, 1000)])
+def test_gemm_bf16_tn_matches_fp32_reference(shape):
+    import mpi4torch_b200 as m4t  # noqa: F401
+
+    m4t.COMM_WORLD  # bring the backend up
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    assert torch.ops.mpi4torch_b200.gemm_bf16_tn_supported(x, w)
+    y = torch.ops.mpi4torch_b200.gemm_bf16_tn(x, w)
+    torch.cuda.synchronize()
+    ref = _ref(x, w)
+    err = (y.float() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err / scale < 2e-2, f"{shape}: max abs err {err} vs scale {scale}"
+    # structured check: identity-like weight reproduces the input exactly
+    if N == K:
+        eye = torch.eye(N, device="cuda", dtype=torch.bfloat16)
+        assert torch.equal(torch.ops.mpi4torch_b200.gemm_bf16_tn(x, eye), x)
+
+
+def test_gemm_speed_report():
+    import mpi4torch_b200 as m4t  # noqa: F401
+
+    m4t.COMM_WORLD
+    M, N, K = 8192, 4096, 4096
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    for name, fn in (("tcgen05", lambda: torch.ops.mpi4torch_b200.gemm_bf16_tn(x, w)), ("cublas", lambda: x @ w.t())):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print(f"[gemm] {name}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
