@@ -43,6 +43,7 @@ struct ArArgs {
   int64_t chunk_vecs;  // vectors per chunk (all shards together)
   int64_t slot_bytes;  // ONESHOT: bytes per rank slot
   int aligned;         // in/out/acc 16-byte aligned
+  int skip_mask;       // debug only (M4T_AR_DEBUG_SKIP): bit0 skip phase A, bit1 B, bit2 C
 };
 
 template <DType DT, ReduceOp OP>
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
     const int64_t nw = first < L ? (L - first + gstride - 1) / gstride : 0;
     const int64_t nitems = nw * P;
     // ---- phase A: stage my part of every shard (block b owns pattern b of each shard)
-    for (int64_t j0 = 0; j0 < nitems; j0 += kUnroll) {
+    for (int64_t j0 = (a.skip_mask & 1) ? nitems : 0; j0 < nitems; j0 += kUnroll) {
       Vec16 v[kUnroll];
       int64_t idx[kUnroll];
 #pragma unroll
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
     }
     block_barrier_all(c, fb, bar++);
     // ---- phase B: reduce shard r
-    for (int64_t w0 = 0; w0 < nw; w0 += kUnroll) {
+    for (int64_t w0 = (a.skip_mask & 2) ? nw : 0; w0 < nw; w0 += kUnroll) {
       int64_t off[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
     }
     block_barrier_all(c, fb, bar++);
     // ---- phase C: collect all shards (NVLS: already in my HBM; TWOSHOT: pull from owners)
-    for (int64_t j0 = 0; j0 < nitems; j0 += kUnroll) {
+    for (int64_t j0 = (a.skip_mask & 4) ? nitems : 0; j0 < nitems; j0 += kUnroll) {
       Vec16 v[kUnroll];
       int64_t idx[kUnroll];
 #pragma unroll
@@ -337,6 +338,7 @@ void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n
   a.nvec = (n * dtype_size(dt) + 15) / 16;
   a.slot_bytes = ((a.nvec * 16 + 127) / 128) * 128;
   a.aligned = is_aligned16(in) && is_aligned16(out) && (!epi.accumulate || is_aligned16(epi.accumulate));
+  a.skip_mask = static_cast<int>(env_i64("M4T_AR_DEBUG_SKIP", 0));
   M4T_CHECK(allreduce_stage_bytes(n, dt, algo, dc.sync.size) <= dc.half_bytes,
             "allreduce of " << n << " elements does not fit the staging half (" << dc.half_bytes << " B)");
   blocks = std::max(1, std::min(blocks, kMaxChannels));
