@@ -77,6 +77,12 @@ def _bootstrap() -> None:
 
     Replaces ``MPI_Init_thread`` at import (reference csrc/extension.cpp:1323-1394).
     """
+    # Kernels of different ranks/streams wait on each other; a lazily loaded
+    # kernel whose load needs the device to drain could deadlock against a
+    # spinning one.  Ask for eager loading when the context does not exist yet
+    # (the pairs that matter are additionally preloaded natively).
+    if not torch.cuda.is_initialized():
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     want_cuda = os.environ.get("M4T_CUDA", "1") != "0" and torch.cuda.is_available()
     device = 0
     if want_cuda:

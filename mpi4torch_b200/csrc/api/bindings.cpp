@@ -108,6 +108,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     if (key == "oneshot_max_bytes") t.oneshot_max_bytes = value;
     else if (key == "chunk_bytes") t.chunk_bytes = value;
     else if (key == "ar_blocks") t.ar_blocks = static_cast<int>(value);
+    else if (key == "pipe_min_bytes") t.pipe_min_bytes = value;
+    else if (key == "nvls_min_ranks") t.nvls_min_ranks = static_cast<int>(value);
     else if (key == "oneshot_blocks") t.oneshot_blocks = static_cast<int>(value);
     else if (key == "slab_blocks") t.slab_blocks = static_cast<int>(value);
     else if (key == "p2p_blocks") t.p2p_blocks = static_cast<int>(value);

@@ -128,6 +128,29 @@ Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scal
   return r.from_comm(out);
 }
 
+void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale) {
+  TORCH_CHECK(param.is_contiguous() && param.sizes() == grad.sizes() && param.scalar_type() == grad.scalar_type() &&
+                  param.device() == grad.device(),
+              "mpi4torch_b200: allreduce_axpy_ needs a contiguous parameter and a gradient of the same shape/dtype/device");
+  const DType dt = to_dtype(param.scalar_type());
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  Route r(*world_, param);
+  Tensor gin = r.to_comm(grad);
+  Epilogue epi;
+  epi.scale = scale;
+  epi.has_scale = true;
+  if (r.staged) {
+    Tensor p = param.cpu();
+    epi.accumulate = p.data_ptr();
+    r.be->allreduce(gin.data_ptr(), p.data_ptr(), gin.numel(), dt, ReduceOp::SUM, epi, nullptr);
+    param.copy_(p);
+  } else {
+    // out aliases accumulate: every element is read then written by the same thread
+    epi.accumulate = param.data_ptr();
+    r.be->allreduce(gin.data_ptr(), param.data_ptr(), gin.numel(), dt, ReduceOp::SUM, epi, r.stream);
+  }
+}
+
 void Communicator::raw_bcast_(Tensor& work, int64_t root) {
   TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Bcast_ root ", root, " out of range");
   const DType dt = to_dtype(work.scalar_type());

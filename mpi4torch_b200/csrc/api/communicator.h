@@ -46,6 +46,8 @@ struct Communicator : torch::CustomClassHolder {
   // ---- raw (non-differentiable) data paths, used by the autograd functions ---
   Tensor raw_allreduce(const Tensor& input, int64_t op, double scale, bool has_scale,
                        const c10::optional<Tensor>& accumulate);
+  // param <- param + scale * Allreduce(grad, SUM), written in place (no autograd)
+  void raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale);
   void raw_bcast_(Tensor& work, int64_t root);
   void raw_reduce_(Tensor& work, int64_t op, int64_t root);
   Tensor raw_gather(const Tensor& input, int64_t axis, int64_t root, bool all);

@@ -10,6 +10,7 @@
 
 #include "../runtime/cuda_backend.h"
 #include "../runtime/world.h"
+#include "communicator.h"
 
 namespace m4t {
 
@@ -73,9 +74,67 @@ std::tuple<Tensor, Tensor> allreduce_linear_fused(const Tensor& x, const Tensor&
   return {y, w_avg};
 }
 
+// Training forward of the data-parallel linear layer with everything fused:
+//   W_avg = scale * sum_ranks W          (inside the GEMM kernel when NVLS is up)
+//   y     = x @ W_avg^T                  (tcgen05, never stored)
+//   dy    = grad_scale * (y - target)    (GEMM epilogue)
+//   loss  = loss_scale * sum((y-target)^2)  (GEMM epilogue, one atomic per warp per tile)
+// Returns (dy, loss[1] fp32, W_avg).
+std::tuple<Tensor, Tensor, Tensor> linear_mse_forward(const Tensor& x, const Tensor& w, const Tensor& target, double scale,
+                                                      double loss_scale, double grad_scale, bool allow_fused) {
+  check_2d_bf16(x, "x");
+  check_2d_bf16(w, "w");
+  check_2d_bf16(target, "target");
+  TORCH_CHECK(x.size(1) == w.size(1) && target.size(0) == x.size(0) && target.size(1) == w.size(0),
+              "mpi4torch_b200: linear_mse_forward shape mismatch");
+  c10::cuda::CUDAGuard guard(x.device());
+  cudaStream_t stream = c10::cuda::getCurrentCUDAStream(x.device().index()).stream();
+  Tensor dy = at::empty({x.size(0), w.size(0)}, x.options());
+  Tensor loss = at::zeros({1}, x.options().dtype(at::kFloat));
+  MseEpilogue mse;
+  mse.target = target.data_ptr();
+  mse.ldt = target.stride(0);
+  mse.loss_acc = loss.data_ptr<float>();
+  mse.loss_scale = static_cast<float>(loss_scale);
+  mse.grad_scale = static_cast<float>(grad_scale);
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  CudaBackend& be = backend();
+  Tensor w_avg;
+  if (allow_fused && be.size() > 1 && x.is_contiguous() && w.is_contiguous() && be.fused_linear_available(w.size(0), w.size(1))) {
+    const void* wavg = be.fused_allreduce_linear(x.data_ptr(), w.data_ptr(), dy.data_ptr(), x.size(0), w.size(0), x.size(1),
+                                                 x.stride(0), dy.stride(0), static_cast<float>(scale), stream, &mse);
+    w_avg = torch::from_blob(const_cast<void*>(wavg), {w.size(0), w.size(1)}, w.options());
+  } else {
+    if (be.size() > 1) {
+      w_avg = at::empty_like(w, at::MemoryFormat::Contiguous);
+      Tensor wc = w.contiguous();
+      Epilogue epi;
+      epi.scale = scale;
+      epi.has_scale = true;
+      be.allreduce(wc.data_ptr(), w_avg.data_ptr(), wc.numel(), DType::BF16, ReduceOp::SUM, epi, stream);
+    } else {
+      w_avg = w;
+    }
+    be.gemm_bf16_tn(x.data_ptr(), w_avg.data_ptr(), dy.data_ptr(), x.size(0), w_avg.size(0), x.size(1), x.stride(0),
+                    w_avg.stride(0), dy.stride(0), stream, &mse);
+  }
+  return {dy, loss, w_avg};
+}
+
+// param <- param + scale * Allreduce(grad): the gradient all-reduce with the
+// optimizer update as its epilogue, in place.
+void allreduce_axpy_(Tensor param, const Tensor& grad, double scale) {
+  auto comm = c10::make_intrusive<Communicator>();
+  comm->raw_allreduce_axpy_(param, grad, scale);
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
+  m.def("linear_mse_forward(Tensor x, Tensor w, Tensor target, float scale, float loss_scale, float grad_scale, "
+        "bool allow_fused) -> (Tensor, Tensor, Tensor)",
+        &linear_mse_forward);
+  m.def("allreduce_axpy_(Tensor(a!) param, Tensor grad, float scale) -> ()", &allreduce_axpy_);
   m.def("gemm_bf16_tn(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn);
   m.def("gemm_bf16_tn_supported(Tensor x, Tensor w) -> bool", &gemm_bf16_tn_ok);
   m.def("allreduce_linear_supported(Tensor x, Tensor w) -> bool", &allreduce_linear_supported);

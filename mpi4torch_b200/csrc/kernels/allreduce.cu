@@ -209,6 +209,165 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
   finish_op(c, static_cast<unsigned int>(bar));
 }
 
+// ---------------------------------------------------------------------------
+// Pipelined two-shot / NVLS allreduce.  One CTA = two 512-thread roles:
+//   L (local)  : A(c) stage chunk c into my heap; C(c-1) copy reduced chunk c-1
+//                out of my heap with the epilogue.            HBM-bound.
+//   N (network): B(c) multimem.ld_reduce + multimem.st (or P peer loads +
+//                store, then peers pull in C).                NVLink-bound.
+// The roles are decoupled by chunk-indexed flags in two pads (A-done, B-done),
+// exchanged with the same-index CTA of every peer, so the NVLink phase of chunk
+// c overlaps the HBM phases of chunks c+1 / c-1 instead of alternating with
+// them.  Flags are monotone (flag_base + chunk + 1): no resets, no grid sync.
+// ---------------------------------------------------------------------------
+constexpr int kRoleThreads = 512;
+constexpr int kPipeUnroll = 4;
+
+__device__ __forceinline__ void role_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kRoleThreads) : "memory"); }
+
+template <DType DT, ReduceOp OP, NvlsKind NK>
+__global__ void __launch_bounds__(2 * kRoleThreads, 1) allreduce_pipelined_kernel(const ArArgs a) {
+  using V = VecOf<DT>;
+  const SyncCtx& c = a.sync;
+  const unsigned long long fb = read_flag_base(c);
+  const int par = static_cast<int>(read_op_count(c) & 1ull);
+  const int P = c.size, r = c.rank;
+  const bool al = a.aligned != 0;
+  const int64_t in_off = a.stage_off + static_cast<int64_t>(par) * a.half_bytes;
+  const int64_t out_off = in_off + ((a.nvec * 16 + 127) / 128) * 128;
+  char* my_in = a.heap[r] + in_off;
+  char* my_out = a.heap[r] + out_off;
+  const bool is_net = threadIdx.x >= kRoleThreads;
+  const int t = threadIdx.x - (is_net ? kRoleThreads : 0);
+  const int64_t gstride = static_cast<int64_t>(gridDim.x) * kRoleThreads;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * kRoleThreads + t;
+  const int64_t nchunks = (a.nvec + a.chunk_vecs - 1) / a.chunk_vecs;
+  // flag slots of this CTA's channel: pad A at heap offset 0, pad B at kPadBOffset
+  const int64_t slot = static_cast<int64_t>(blockIdx.x) * kMaxGpuPeers;
+  constexpr int64_t kPadBOffset = 64 * 1024;
+
+  auto flag_a = [&](int owner, int src) { return c.pads[owner] + slot + src; };
+  auto flag_b = [&](int owner, int src) {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c.pads[owner]) + kPadBOffset) + slot + src;
+  };
+
+  if (!is_net) {
+    // ============================ role L ============================
+    for (int64_t ck = 0; ck <= nchunks; ++ck) {
+      if (ck < nchunks) {
+        // ---- A(ck): stage my pattern of every shard
+        const int64_t base = ck * a.chunk_vecs;
+        const int64_t cc = min(a.chunk_vecs, a.nvec - base);
+        const int64_t L = (cc + P - 1) / P;
+        const int64_t nw = first < L ? (L - first + gstride - 1) / gstride : 0;
+        const int64_t nitems = nw * P;
+        for (int64_t j0 = 0; j0 < nitems; j0 += kPipeUnroll) {
+          Vec16 v[kPipeUnroll];
+          int64_t idx[kPipeUnroll];
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u) {
+            const int64_t j = j0 + u;
+            const int64_t i = (j % P) * L + first + (j / P) * gstride;
+            idx[u] = (j < nitems && i < cc) ? i : -1;
+            if (idx[u] >= 0) v[u] = load_private<DT>(a.in, base + idx[u], a.n, al);
+          }
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u)
+            if (idx[u] >= 0) st_vec(my_in + (base + idx[u]) * 16, v[u]);
+        }
+        role_sync(1);
+        if (t < P) st_release_sys_u32(flag_a(t, r), static_cast<uint32_t>(fb + ck + 1));
+      }
+      if (ck > 0) {
+        // ---- C(ck-1): reduced chunk is in my heap (NVLS) or at its owners (two-shot)
+        const int64_t cprev = ck - 1;
+        if (t < P) wait_flag_ge(flag_b(r, t), static_cast<uint32_t>(fb + cprev + 1), c);
+        role_sync(1);
+        const int64_t base = cprev * a.chunk_vecs;
+        const int64_t cc = min(a.chunk_vecs, a.nvec - base);
+        const int64_t L = (cc + P - 1) / P;
+        const int64_t nw = first < L ? (L - first + gstride - 1) / gstride : 0;
+        const int64_t nitems = nw * P;
+        for (int64_t j0 = 0; j0 < nitems; j0 += kPipeUnroll) {
+          Vec16 v[kPipeUnroll];
+          int64_t idx[kPipeUnroll];
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u) {
+            const int64_t j = j0 + u;
+            const int q = static_cast<int>(j % P);
+            const int64_t i = static_cast<int64_t>(q) * L + first + (j / P) * gstride;
+            idx[u] = (j < nitems && i < cc) ? i : -1;
+            if (idx[u] >= 0) {
+              const char* src = (NK != NvlsKind::NONE) ? my_out : (a.heap[q] + out_off);
+              v[u] = ld_vec_sys(src + (base + idx[u]) * 16);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u) {
+            if (idx[u] < 0) continue;
+            if (a.epi.acc) {
+              typename V::A acc[V::N];
+              V::unpack(v[u], acc);
+              apply_accumulate<DT>(acc, a.epi, base + idx[u], a.n, al);
+              v[u] = V::pack(acc);
+            }
+            store_private<DT>(a.out, base + idx[u], a.n, al, v[u]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================ role N ============================
+    for (int64_t ck = 0; ck < nchunks; ++ck) {
+      if (t < P) wait_flag_ge(flag_a(r, t), static_cast<uint32_t>(fb + ck + 1), c);
+      role_sync(2);
+      const int64_t base = ck * a.chunk_vecs;
+      const int64_t cc = min(a.chunk_vecs, a.nvec - base);
+      const int64_t L = (cc + P - 1) / P;
+      const int64_t nw = first < L ? (L - first + gstride - 1) / gstride : 0;
+      for (int64_t w0 = 0; w0 < nw; w0 += kPipeUnroll) {
+        int64_t off[kPipeUnroll];
+#pragma unroll
+        for (int u = 0; u < kPipeUnroll; ++u) {
+          const int64_t i = static_cast<int64_t>(r) * L + first + (w0 + u) * gstride;
+          off[u] = (w0 + u < nw && i < cc) ? (base + i) * 16 : -1;
+        }
+        if constexpr (NK != NvlsKind::NONE) {
+          Vec16 v[kPipeUnroll];
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u)
+            if (off[u] >= 0) v[u] = multimem_ld_reduce_vec<NK>(a.mc_heap + in_off + off[u]);
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u) {
+            if (off[u] < 0) continue;
+            if (a.epi.has_scale) {
+              typename V::A acc[V::N];
+              V::unpack(v[u], acc);
+              apply_scale<DT>(acc, a.epi);
+              v[u] = V::pack(acc);
+            }
+            multimem_st_vec(a.mc_heap + out_off + off[u], v[u]);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < kPipeUnroll; ++u) {
+            if (off[u] < 0) continue;
+            typename V::A acc[V::N];
+            init_from<DT, OP>(acc, ld_vec_sys(a.heap[0] + in_off + off[u]));
+#pragma unroll 1
+            for (int p = 1; p < P; ++p) combine_into<DT, OP>(acc, ld_vec_sys(a.heap[p] + in_off + off[u]));
+            apply_scale<DT>(acc, a.epi);
+            st_vec(my_out + off[u], V::pack(acc));
+          }
+        }
+      }
+      role_sync(2);
+      if (t < P) st_release_sys_u32(flag_b(t, r), static_cast<uint32_t>(fb + ck + 1));
+    }
+  }
+  finish_op(c, static_cast<unsigned int>(nchunks));
+}
+
 template <DType DT, ReduceOp OP>
 __global__ void __launch_bounds__(kThreads) local_epilogue_kernel(const void* in, void* out, int64_t n,
                                                                    int64_t nvec, DevEpilogue epi, int aligned) {
@@ -256,6 +415,40 @@ NvlsKind nvls_kind(DType dt, ReduceOp op) {
     if (dt == DType::F16) return NvlsKind::MIN_F16;
   }
   return NvlsKind::NONE;
+}
+
+template <DType DT, ReduceOp OP> struct LaunchPipelinedTwoshot {
+  static void run(const ArArgs& a, int blocks, cudaStream_t s) {
+    allreduce_pipelined_kernel<DT, OP, NvlsKind::NONE><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+  }
+};
+
+void launch_nvls_pipelined(NvlsKind k, const ArArgs& a, int blocks, cudaStream_t s) {
+  switch (k) {
+    case NvlsKind::ADD_F32:
+      allreduce_pipelined_kernel<DType::F32, ReduceOp::SUM, NvlsKind::ADD_F32><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    case NvlsKind::ADD_BF16:
+      allreduce_pipelined_kernel<DType::BF16, ReduceOp::SUM, NvlsKind::ADD_BF16><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    case NvlsKind::ADD_F16:
+      allreduce_pipelined_kernel<DType::F16, ReduceOp::SUM, NvlsKind::ADD_F16><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    case NvlsKind::MAX_BF16:
+      allreduce_pipelined_kernel<DType::BF16, ReduceOp::MAX, NvlsKind::MAX_BF16><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    case NvlsKind::MIN_BF16:
+      allreduce_pipelined_kernel<DType::BF16, ReduceOp::MIN, NvlsKind::MIN_BF16><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    case NvlsKind::MAX_F16:
+      allreduce_pipelined_kernel<DType::F16, ReduceOp::MAX, NvlsKind::MAX_F16><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    case NvlsKind::MIN_F16:
+      allreduce_pipelined_kernel<DType::F16, ReduceOp::MIN, NvlsKind::MIN_F16><<<blocks, 2 * kRoleThreads, 0, s>>>(a);
+      break;
+    default:
+      M4T_CHECK(false, "no NVLS kernel for this dtype/op");
+  }
 }
 
 void launch_nvls(NvlsKind k, const ArArgs& a, int blocks, cudaStream_t s) {
@@ -356,12 +549,20 @@ void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n
   a.chunk_vecs = std::max<int64_t>(1, std::min(cv, std::max<int64_t>(a.nvec, 1)));
   const int64_t shard = (a.chunk_vecs + P - 1) / P;
   blocks = static_cast<int>(std::min<int64_t>(blocks, std::max<int64_t>(1, (shard + kThreads - 1) / kThreads)));
+  // Pipelined role-split kernels: one 1024-thread CTA per SM, >= 2 chunks to overlap.
+  const bool pipelined = env_i64("M4T_AR_PIPE", 1) != 0 && a.nvec > a.chunk_vecs;
+  if (pipelined) blocks = std::min(blocks, dc.sm_count);
   if (algo == ArAlgo::NVLS) {
     M4T_CHECK(dc.mc_heap != nullptr, "NVLS allreduce requested but no multicast mapping exists");
-    launch_nvls(nvls_kind(dt, op), a, blocks, stream);
+    if (pipelined) launch_nvls_pipelined(nvls_kind(dt, op), a, blocks, stream);
+    else launch_nvls(nvls_kind(dt, op), a, blocks, stream);
     check_launch("allreduce_nvls");
   } else {
-    M4T_DISPATCH_DTYPE_OP(dt, op, LaunchTwoshot, a, blocks, stream);
+    if (pipelined) {
+      M4T_DISPATCH_DTYPE_OP(dt, op, LaunchPipelinedTwoshot, a, blocks, stream);
+    } else {
+      M4T_DISPATCH_DTYPE_OP(dt, op, LaunchTwoshot, a, blocks, stream);
+    }
     check_launch("allreduce_twoshot");
   }
 }

@@ -46,6 +46,12 @@ struct GemmArgs {
   void* C;
   int M, N, K;
   int ldc;
+  // fused MSE epilogue (EPI == 1): C receives dL/dy = grad_scale * (y - T),
+  // loss_acc accumulates loss_scale * sum((y - T)^2); y itself is never stored
+  const void* T;
+  int ldt;
+  float* loss_acc;
+  float loss_scale, grad_scale;
   // fused mode ----------------------------------------------------------------
   const uint32_t* panel_flags;  // [N / BN] counters in local HBM (written through multicast)
   uint32_t panel_target;        // a panel is ready when its counter >= target (wrap-safe)
@@ -74,7 +80,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return static_cast<uint32_t>(float_to_bf16_bits(lo)) | (static_cast<uint32_t>(float_to_bf16_bits(hi)) << 16);
 }
 
-template <bool FUSED>
+template <bool FUSED, int EPI>
 __global__ void __launch_bounds__((kGemmWarps + (FUSED ? kCommWarps : 0)) * 32, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmArgs g, const CommArgs cm) {
@@ -185,6 +191,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc::tcgen05_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
       uint16_t* crow = static_cast<uint16_t*>(g.C) + static_cast<int64_t>(row) * g.ldc + n_blk * BN;
+      const uint16_t* trow = nullptr;
+      float loss_part = 0.f;
+      if (EPI == 1) trow = static_cast<const uint16_t*>(g.T) + static_cast<int64_t>(row) * g.ldt + n_blk * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -197,13 +206,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int v = 0; v < 4; ++v) {
             if (col0 + v * 8 + 8 <= g.N) {
               Vec16 o;
+              if (EPI == 1) {
+                // dL/dy = grad_scale * (y - t); loss += (y - t)^2
+                const Vec16 tv = ld_vec_stream(trow + c * 32 + v * 8);
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o.w[e] = pack_bf16x2(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+                for (int e = 0; e < 4; ++e) {
+                  const float d0 = __uint_as_float(r[v * 8 + 2 * e]) - bf16_bits_to_float(static_cast<uint16_t>(tv.w[e] & 0xffffu));
+                  const float d1 = __uint_as_float(r[v * 8 + 2 * e + 1]) - bf16_bits_to_float(static_cast<uint16_t>(tv.w[e] >> 16));
+                  loss_part = fmaf(d0, d0, loss_part);
+                  loss_part = fmaf(d1, d1, loss_part);
+                  o.w[e] = pack_bf16x2(d0 * g.grad_scale, d1 * g.grad_scale);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  o.w[e] = pack_bf16x2(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+              }
               st_vec(crow + c * 32 + v * 8, o);
             }
           }
         }
+      }
+      if (EPI == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+        if (lane == 0) atomicAdd(g.loss_acc, loss_part * g.loss_scale);
       }
       tc::tcgen05_fence_before();
       __syncwarp();
@@ -312,10 +339,10 @@ void check_launch(const char* what) {
   note_kernel_launch();
 }
 
-template <bool FUSED> void configure_once() {
+template <bool FUSED, int EPI> void configure_once() {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<FUSED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
   });
 }
@@ -330,9 +357,8 @@ bool gemm_bf16_tn_supported(int64_t M, int64_t N, int64_t K, const void* A, cons
 }
 
 void launch_gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
-                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream) {
+                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream, const MseEpilogue* mse) {
   M4T_CHECK(gemm_bf16_tn_supported(M, N, K, A, B, C, lda, ldb, ldc), "unsupported GEMM shape/alignment for the tcgen05 path");
-  configure_once<false>();
   const CUtensorMap ta = make_tmap(A, M, K, lda, BM);
   const CUtensorMap tb = make_tmap(B, N, K, ldb, BN);
   GemmArgs g{};
@@ -346,7 +372,18 @@ void launch_gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64
   CommArgs cm{};
   const int tiles = static_cast<int>(((M + BM - 1) / BM) * ((N + BN - 1) / BN));
   const int grid = std::max(1, std::min(tiles, sm_count));
-  gemm_bf16_tn_kernel<false><<<grid, kGemmWarps * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  if (mse) {
+    g.T = mse->target;
+    g.ldt = static_cast<int>(mse->ldt);
+    g.loss_acc = mse->loss_acc;
+    g.loss_scale = mse->loss_scale;
+    g.grad_scale = mse->grad_scale;
+    configure_once<false, 1>();
+    gemm_bf16_tn_kernel<false, 1><<<grid, kGemmWarps * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  } else {
+    configure_once<false, 0>();
+    gemm_bf16_tn_kernel<false, 0><<<grid, kGemmWarps * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  }
   check_launch("gemm_bf16_tn");
 }
 
@@ -355,13 +392,12 @@ void launch_gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64
 // must already be staged at w_off on every rank.
 void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
                                  int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
-                                 uint32_t panel_target, float scale, cudaStream_t stream) {
+                                 uint32_t panel_target, float scale, cudaStream_t stream, const MseEpilogue* mse) {
   M4T_CHECK(dc.mc_heap != nullptr, "the fused Allreduce->GEMM kernel needs the NVLS multicast mapping");
   const int P = dc.sync.size;
   M4T_CHECK(BN % P == 0 && N % BN == 0 && (K * 2) % 16 == 0, "fused Allreduce->GEMM: N must be a multiple of 256 and 256 % ranks == 0");
   const char* wavg = dc.heap[dc.sync.rank] + wavg_off;
   M4T_CHECK(gemm_bf16_tn_supported(M, N, K, x, wavg, y, ldx, K, ldy), "unsupported GEMM shape/alignment for the fused path");
-  configure_once<true>();
   const CUtensorMap ta = make_tmap(x, M, K, ldx, BM);
   const CUtensorMap tb = make_tmap(wavg, N, K, K, BN);
   GemmArgs g{};
@@ -383,7 +419,18 @@ void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, i
   cm.do_barrier = 1;
   // the grid must be identical on every rank (per-block barrier + counter targets)
   const int grid = std::min(dc.sm_count, kMaxChannels);
-  gemm_bf16_tn_kernel<true><<<grid, (kGemmWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  if (mse) {
+    g.T = mse->target;
+    g.ldt = static_cast<int>(mse->ldt);
+    g.loss_acc = mse->loss_acc;
+    g.loss_scale = mse->loss_scale;
+    g.grad_scale = mse->grad_scale;
+    configure_once<true, 1>();
+    gemm_bf16_tn_kernel<true, 1><<<grid, (kGemmWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  } else {
+    configure_once<true, 0>();
+    gemm_bf16_tn_kernel<true, 0><<<grid, (kGemmWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  }
   check_launch("fused_allreduce_gemm");
 }
 

@@ -75,6 +75,8 @@ struct P2pChannel {
   int64_t slot_bytes;
   int nslots;
 };
+// Forces both p2p kernels to be loaded (lazy module loading hazard, see p2p.cu).
+void preload_p2p_kernels();
 // Chunks a message of `bytes` occupies in the ring (>= 1: empty messages carry a flag).
 int64_t p2p_num_chunks(int64_t bytes, int64_t slot_bytes);
 // Sender: copies `bytes` from `src` into the ring, chunk by chunk, publishing head flags.
@@ -87,13 +89,21 @@ void launch_p2p_recv(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64
 // ---- tcgen05 GEMM + fused Allreduce->GEMM (gemm_tcgen05.cu) --------------------
 bool gemm_bf16_tn_supported(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C, int64_t lda,
                             int64_t ldb, int64_t ldc);
+// Optional fused MSE epilogue: instead of y the kernel stores dL/dy =
+// grad_scale * (y - target) and adds loss_scale * sum((y - target)^2) to *loss_acc.
+struct MseEpilogue {
+  const void* target;
+  int64_t ldt;
+  float* loss_acc;
+  float loss_scale, grad_scale;
+};
 // C[M,N] = A[M,K] * B[N,K]^T, bf16 in / fp32 accumulate (TMEM) / bf16 out.
 void launch_gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
-                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream);
+                         int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream, const MseEpilogue* mse = nullptr);
 // y = x @ (scale * sum_ranks W)^T in one kernel; W staged at heap offset w_off on every rank.
 void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
                                  int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
-                                 uint32_t panel_target, float scale, cudaStream_t stream);
+                                 uint32_t panel_target, float scale, cudaStream_t stream, const MseEpilogue* mse = nullptr);
 int fused_gemm_grid(const DeviceComm& dc);
 // Plain device copy into the heap (used to stage the weight for the fused kernel).
 void launch_copy_bytes(void* dst, const void* src, int64_t bytes, int sm_count, cudaStream_t stream);

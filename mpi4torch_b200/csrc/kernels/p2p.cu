@@ -112,6 +112,17 @@ P2pArgs make_args(const SyncCtx& sync, const P2pChannel& ch, void* user, int64_t
 
 }  // namespace
 
+// With CUDA's lazy module loading the first launch of a kernel loads it, which
+// can need the device to drain - fatal if the other kernel of the pair is
+// already spinning on the ring.  Load both before any message is sent.
+void preload_p2p_kernels() {
+  cudaFuncAttributes attr;
+  cudaError_t e = cudaFuncGetAttributes(&attr, p2p_send_kernel);
+  M4T_CHECK(e == cudaSuccess, "loading p2p_send_kernel failed: " << cudaGetErrorString(e));
+  e = cudaFuncGetAttributes(&attr, p2p_recv_kernel);
+  M4T_CHECK(e == cudaSuccess, "loading p2p_recv_kernel failed: " << cudaGetErrorString(e));
+}
+
 void launch_p2p_send(const SyncCtx& sync, const P2pChannel& ch, const void* src, int64_t bytes,
                      unsigned long long first_chunk, int blocks, cudaStream_t stream) {
   P2pArgs a = make_args(sync, ch, const_cast<void*>(src), bytes, first_chunk, true);

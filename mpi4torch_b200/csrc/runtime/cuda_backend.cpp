@@ -25,8 +25,10 @@ CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) 
   M4T_CHECK(P <= kMaxGpuPeers, "the NVLink backend supports up to " << kMaxGpuPeers << " ranks (got " << P << ")");
   M4T_CUDA(cudaSetDevice(device_));
   tune_.oneshot_max_bytes = env_i64("M4T_ONESHOT_MAX_KB", 256) * 1024;
-  tune_.chunk_bytes = env_i64("M4T_CHUNK_KB", 8192) * 1024;
-  tune_.ar_blocks = static_cast<int>(env_i64("M4T_AR_BLOCKS", 128));
+  tune_.chunk_bytes = env_i64("M4T_CHUNK_KB", 0) * 1024;
+  tune_.pipe_min_bytes = env_i64("M4T_PIPE_MIN_MB", 32) << 20;
+  tune_.nvls_min_ranks = static_cast<int>(env_i64("M4T_NVLS_MIN_RANKS", 4));
+  tune_.ar_blocks = static_cast<int>(env_i64("M4T_AR_BLOCKS", 148));
   tune_.oneshot_blocks = static_cast<int>(env_i64("M4T_ONESHOT_BLOCKS", 32));
   tune_.slab_blocks = static_cast<int>(env_i64("M4T_SLAB_BLOCKS", 128));
   tune_.p2p_blocks = static_cast<int>(env_i64("M4T_P2P_BLOCKS", 16));
@@ -74,6 +76,20 @@ CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) 
 
   send_streams_.assign(static_cast<size_t>(P), nullptr);
   recv_streams_.assign(static_cast<size_t>(P), nullptr);
+  // Create every side stream and a pool of events NOW: resource creation can
+  // synchronise the device, and doing it lazily between an Isend (whose kernel
+  // may be spinning on a full ring) and the matching Irecv would stall the
+  // very kernel that is waiting for that receive.
+  for (int p = 0; p < P; ++p) {
+    M4T_CUDA(cudaStreamCreateWithFlags(&send_streams_[p], cudaStreamNonBlocking));
+    M4T_CUDA(cudaStreamCreateWithFlags(&recv_streams_[p], cudaStreamNonBlocking));
+  }
+  preload_p2p_kernels();
+  for (int i = 0; i < 64; ++i) {
+    cudaEvent_t e;
+    M4T_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    event_pool_.push_back(e);
+  }
   send_chunks_.assign(static_cast<size_t>(P), 0ull);
   recv_chunks_.assign(static_cast<size_t>(P), 0ull);
   send_seq_.assign(static_cast<size_t>(P), 0ull);
@@ -143,12 +159,13 @@ void CudaBackend::free_event(cudaEvent_t e) {
 ArAlgo CudaBackend::pick_algo(int64_t bytes, DType dt, ReduceOp op) const {
   if (size() == 1) return ArAlgo::LOCAL;
   const bool nvls_ok = has_nvls() && nvls_supported(dt, op);
+  const bool nvls_pays = nvls_ok && size() >= tune_.nvls_min_ranks;
   if (tune_.force_algo == 1) return ArAlgo::ONESHOT;
   if (tune_.force_algo == 2) return ArAlgo::TWOSHOT;
   if (tune_.force_algo == 3 && nvls_ok) return ArAlgo::NVLS;
   const int64_t oneshot_cap = dc_.half_bytes / size() - 128;
   if (bytes <= tune_.oneshot_max_bytes && bytes <= oneshot_cap) return ArAlgo::ONESHOT;
-  return nvls_ok ? ArAlgo::NVLS : ArAlgo::TWOSHOT;
+  return nvls_pays ? ArAlgo::NVLS : ArAlgo::TWOSHOT;
 }
 
 void CudaBackend::allreduce_algo(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
@@ -183,9 +200,15 @@ void CudaBackend::allreduce_algo(const void* in, void* out, int64_t n, DType dt,
 
 void CudaBackend::allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
                             void* stream) {
-  const ArAlgo algo = pick_algo(n * dtype_size(dt), dt, op);
+  const int64_t bytes = n * dtype_size(dt);
+  const ArAlgo algo = pick_algo(bytes, dt, op);
   const int blocks = algo == ArAlgo::ONESHOT ? tune_.oneshot_blocks : tune_.ar_blocks;
-  allreduce_algo(in, out, n, dt, op, epi, algo, blocks, tune_.chunk_bytes, static_cast<cudaStream_t>(stream));
+  // Every cross-rank barrier costs several microseconds, so mid-size messages
+  // run as ONE chunk (two barriers); large ones are cut into ~8 chunks for the
+  // role-split kernel whose flags are off the critical path.
+  int64_t chunk = tune_.chunk_bytes;
+  if (chunk <= 0) chunk = bytes >= tune_.pipe_min_bytes ? ((bytes / 8 + (1 << 20) - 1) >> 20 << 20) : (int64_t{1} << 40);
+  allreduce_algo(in, out, n, dt, op, epi, algo, blocks, chunk, static_cast<cudaStream_t>(stream));
 }
 
 void CudaBackend::bcast(void* buf, int64_t n, DType dt, int root, void* stream) {
@@ -282,13 +305,14 @@ bool CudaBackend::fused_linear_available(int64_t N, int64_t K) const {
 }
 
 void CudaBackend::gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
-                               int64_t ldb, int64_t ldc, cudaStream_t stream) {
+                               int64_t ldb, int64_t ldc, cudaStream_t stream, const MseEpilogue* mse) {
   M4T_CUDA(cudaSetDevice(device_));
-  launch_gemm_bf16_tn(A, B, C, M, N, K, lda, ldb, ldc, dc_.sm_count, stream);
+  launch_gemm_bf16_tn(A, B, C, M, N, K, lda, ldb, ldc, dc_.sm_count, stream, mse);
 }
 
 const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
-                                                int64_t ldx, int64_t ldy, float scale, cudaStream_t stream) {
+                                                int64_t ldx, int64_t ldy, float scale, cudaStream_t stream,
+                                                const MseEpilogue* mse) {
   check_device_error();
   M4T_CHECK(fused_linear_available(N, K), "fused Allreduce->GEMM unavailable for N=" << N << " K=" << K);
   M4T_CUDA(cudaSetDevice(device_));
@@ -310,7 +334,7 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
   st.calls += 1;
   const uint32_t target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
   launch_fused_allreduce_gemm(dc_, x, y, M, N, K, ldx, ldy, st.w_off, st.wavg_off[par], st.flags_off, target, scale,
-                              stream);
+                              stream, mse);
   return symm_ptr(st.wavg_off[par]);
 }
 
@@ -432,7 +456,9 @@ bool CudaBackend::progress_source(int source, bool blocking) {
   u.tag = d.tag;
   u.bytes = static_cast<int64_t>(d.bytes);
   u.temp = nullptr;
-  if (u.bytes > 0) M4T_CUDA(cudaMalloc(&u.temp, static_cast<size_t>(u.bytes)));
+  // stream-ordered allocation: a plain cudaMalloc could synchronise with the
+  // sender's spinning kernel
+  if (u.bytes > 0) M4T_CUDA(cudaMallocAsync(&u.temp, static_cast<size_t>(u.bytes), recv_stream(source)));
   u.done = new_event();
   launch_recv(d, source, u.temp, nullptr, u.done);
   unexpected_[source].push_back(u);

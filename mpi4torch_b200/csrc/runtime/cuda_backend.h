@@ -19,7 +19,9 @@ namespace m4t {
 
 struct CudaTuning {
   int64_t oneshot_max_bytes;   // M4T_ONESHOT_MAX_KB
-  int64_t chunk_bytes;         // M4T_CHUNK_KB   (two-shot / NVLS pipeline step)
+  int64_t chunk_bytes;         // M4T_CHUNK_KB   (0 = auto: one chunk, or bytes/8 when pipelined)
+  int64_t pipe_min_bytes;      // M4T_PIPE_MIN_MB: messages >= this use the role-split pipelined kernel
+  int nvls_min_ranks;          // M4T_NVLS_MIN_RANKS: in-switch reduction only pays off from this world size
   int ar_blocks;               // M4T_AR_BLOCKS  (two-shot / NVLS grid)
   int oneshot_blocks;          // M4T_ONESHOT_BLOCKS
   int slab_blocks;             // M4T_SLAB_BLOCKS
@@ -67,9 +69,10 @@ class CudaBackend final : public Backend {
   // y[M,N] = x[M,K] @ (scale * sum_ranks w[N,K])^T; returns the address of the
   // averaged weight (valid until the call after next).
   const void* fused_allreduce_linear(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
-                                     int64_t ldx, int64_t ldy, float scale, cudaStream_t stream);
+                                     int64_t ldx, int64_t ldy, float scale, cudaStream_t stream,
+                                     const MseEpilogue* mse = nullptr);
   void gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                    int64_t ldc, cudaStream_t stream);
+                    int64_t ldc, cudaStream_t stream, const MseEpilogue* mse = nullptr);
 
   // Throws if a device-side wait timed out since the last check.
   void check_device_error();
