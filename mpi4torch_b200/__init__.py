@@ -55,6 +55,7 @@ __all__ = [
     "cuda_backend_ready",
     "has_nvls",
     "heap_mode",
+    "symmetric_empty",
 ]
 
 # The reference's integer op constants (reference csrc/extension.cpp:1424-1435).
@@ -296,6 +297,17 @@ def __getattr__(name: str):
         globals()["COMM_WORLD"] = world
         return world
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def symmetric_empty(shape, dtype=torch.float32) -> torch.Tensor:
+    """Uninitialised CUDA tensor inside the symmetric heap's persistent arena.
+
+    Collective in spirit: all ranks must allocate the same sizes in the same
+    order so offsets agree.  Kernels that need peer-visible inputs (the fused
+    Allreduce->GEMM layer) use such tensors in place instead of staging a copy.
+    """
+    _ensure_world()
+    return torch.ops.mpi4torch_b200.symmetric_empty(list(shape), dtype)
 
 
 def comm_from_mpi4py(comm) -> MPI_Communicator:

@@ -4,6 +4,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <numeric>
 
 #include "../runtime/cuda_backend.h"
@@ -73,6 +75,22 @@ struct Route {
   Tensor from_comm(const Tensor& t) const { return staged ? t.to(device) : t; }
 };
 
+// NVTX range per op: shows up in Nsight timelines / ncu range
+// filters; costs nothing when no tool is attached.  M4T_NVTX=0 disables.
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_enabled()) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+  static bool nvtx_enabled() {
+    static const bool v = env_i64("M4T_NVTX", 1) != 0;
+    return v;
+  }
+};
+
 int64_t wrap_axis(int64_t axis, int64_t ndim, const char* what) {
   TORCH_CHECK(ndim > 0, "mpi4torch_b200: ", what, " needs a tensor with at least one dimension");
   TORCH_CHECK(axis >= -ndim && axis < ndim, "mpi4torch_b200: ", what, " axis ", axis, " out of range for a ", ndim,
@@ -106,6 +124,7 @@ std::string Communicator::Describe() const {
 
 Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scale, bool has_scale,
                                    const c10::optional<Tensor>& accumulate) {
+  NvtxRange nvtx_range_("m4t::Allreduce");
   const ReduceOp op = to_op(op_);
   const DType dt = to_dtype(input.scalar_type());
   check_op_dtype(op, dt);
@@ -129,6 +148,7 @@ Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scal
 }
 
 void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale) {
+  NvtxRange nvtx_range_("m4t::AllreduceAxpy");
   TORCH_CHECK(param.is_contiguous() && param.sizes() == grad.sizes() && param.scalar_type() == grad.scalar_type() &&
                   param.device() == grad.device(),
               "mpi4torch_b200: allreduce_axpy_ needs a contiguous parameter and a gradient of the same shape/dtype/device");
@@ -152,6 +172,7 @@ void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double
 }
 
 void Communicator::raw_bcast_(Tensor& work, int64_t root) {
+  NvtxRange nvtx_range_("m4t::Bcast_");
   TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Bcast_ root ", root, " out of range");
   const DType dt = to_dtype(work.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
@@ -166,6 +187,7 @@ void Communicator::raw_bcast_(Tensor& work, int64_t root) {
 }
 
 void Communicator::raw_reduce_(Tensor& work, int64_t op_, int64_t root) {
+  NvtxRange nvtx_range_("m4t::Reduce_");
   TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Reduce_ root ", root, " out of range");
   const ReduceOp op = to_op(op_);
   const DType dt = to_dtype(work.scalar_type());
@@ -182,6 +204,7 @@ void Communicator::raw_reduce_(Tensor& work, int64_t op_, int64_t root) {
 }
 
 Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root, bool all) {
+  NvtxRange nvtx_range_("m4t::Gather");
   TORCH_CHECK(all || (root >= 0 && root < size_), "mpi4torch_b200: Gather root ", root, " out of range");
   const DType dt = to_dtype(input.scalar_type());
   const int64_t axis = wrap_axis(axis_, input.dim(), all ? "Allgather" : "Gather");
@@ -213,6 +236,7 @@ Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root
 }
 
 Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t numelem, int64_t root) {
+  NvtxRange nvtx_range_("m4t::Scatter");
   TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Scatter root ", root, " out of range");
   TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Scatter numelem must be non-negative");
   const DType dt = to_dtype(input.scalar_type());
@@ -255,6 +279,7 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
 }
 
 Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int64_t scatteraxis_, int64_t numelem) {
+  NvtxRange nvtx_range_("m4t::Alltoall");
   TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Alltoall numelem must be non-negative");
   const DType dt = to_dtype(input.scalar_type());
   const int64_t nd = input.dim();
@@ -293,6 +318,7 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
 }
 
 Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_t axis_, int64_t numelem) {
+  NvtxRange nvtx_range_("m4t::Reduce_scatter");
   TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Reduce_scatter numelem must be non-negative");
   const ReduceOp op = to_op(op_);
   const DType dt = to_dtype(input.scalar_type());
@@ -347,6 +373,7 @@ Tensor make_descriptor(int64_t req, int kind, int64_t peer, int64_t tag, const T
 }  // namespace
 
 std::vector<Tensor> Communicator::raw_isend(const Tensor& input, int64_t dest, int64_t tag) {
+  NvtxRange nvtx_range_("m4t::Isend");
   TORCH_CHECK(dest >= 0 && dest < size_, "mpi4torch_b200: Isend destination ", dest, " out of range");
   to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
@@ -358,6 +385,7 @@ std::vector<Tensor> Communicator::raw_isend(const Tensor& input, int64_t dest, i
 }
 
 std::vector<Tensor> Communicator::raw_irecv(const Tensor& input, int64_t source, int64_t tag) {
+  NvtxRange nvtx_range_("m4t::Irecv");
   TORCH_CHECK(source >= 0 && source < size_, "mpi4torch_b200: Irecv source ", source, " out of range");
   to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
@@ -375,6 +403,7 @@ std::vector<Tensor> Communicator::raw_irecv(const Tensor& input, int64_t source,
 }
 
 Tensor Communicator::raw_wait(const std::vector<Tensor>& handle) {
+  NvtxRange nvtx_range_("m4t::Wait");
   TORCH_CHECK(handle.size() == 3, "mpi4torch_b200: a raw wait handle consists of exactly 3 tensors");
   const Tensor& desc = handle[0];
   TORCH_CHECK(desc.device().is_cpu() && desc.scalar_type() == at::kDouble && desc.numel() == 7,

@@ -121,6 +121,21 @@ std::tuple<Tensor, Tensor, Tensor> linear_mse_forward(const Tensor& x, const Ten
   return {dy, loss, w_avg};
 }
 
+// Tensor backed by the symmetric heap's persistent arena (same offset on every
+// rank when all ranks allocate in the same order).  Kernels that need peer- or
+// switch-visible inputs use such tensors in place instead of staging them.
+Tensor symmetric_empty(c10::IntArrayRef shape, c10::ScalarType dtype) {
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  CudaBackend& be = backend();
+  int64_t numel = 1;
+  for (int64_t d : shape) numel *= d;
+  const int64_t bytes = numel * static_cast<int64_t>(c10::elementSize(dtype));
+  auto opts = at::TensorOptions().dtype(dtype).device(c10::Device(c10::kCUDA, static_cast<c10::DeviceIndex>(be.device())));
+  if (be.size() <= 1) return at::empty(shape, opts);  // no peers: ordinary memory is as good
+  const int64_t off = be.symm_alloc(bytes);
+  return torch::from_blob(be.symm_ptr(off), shape, opts);
+}
+
 // param <- param + scale * Allreduce(grad): the gradient all-reduce with the
 // optimizer update as its epilogue, in place.
 void allreduce_axpy_(Tensor param, const Tensor& grad, double scale) {
@@ -135,6 +150,7 @@ TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
         "bool allow_fused) -> (Tensor, Tensor, Tensor)",
         &linear_mse_forward);
   m.def("allreduce_axpy_(Tensor(a!) param, Tensor grad, float scale) -> ()", &allreduce_axpy_);
+  m.def("symmetric_empty(int[] shape, ScalarType dtype) -> Tensor", &symmetric_empty);
   m.def("gemm_bf16_tn(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn);
   m.def("gemm_bf16_tn_supported(Tensor x, Tensor w) -> bool", &gemm_bf16_tn_ok);
   m.def("allreduce_linear_supported(Tensor x, Tensor w) -> bool", &allreduce_linear_supported);

@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(kThreads) allreduce_oneshot_kernel(const ArArg
   for (int64_t i = first; i < a.nvec; i += stride) {
     const Vec16 v = load_private<DT>(a.in, i, a.n, al);
     const int64_t off = half + static_cast<int64_t>(r) * a.slot_bytes + i * 16;
-    if (a.mc_heap) {
-      multimem_st_vec(a.mc_heap + off, v);
+    if (a.mc_heap && P >= 4) {
+      multimem_st_vec(a.mc_heap + off, v);  // one store, the switch replicates
     } else {
 #pragma unroll 1
       for (int p = 0; p < P; ++p) st_vec(a.heap[p] + off, v);

@@ -267,15 +267,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     e.has_scale = 1;
     e.acc = nullptr;
     uint32_t* mc_flags = reinterpret_cast<uint32_t*>(cm.mc_heap + cm.flags_off);
+    constexpr int kCU = 4;  // independent multimem.ld_reduce requests in flight per thread
+    const int64_t vstride = static_cast<int64_t>(gridDim.x) * kCommThreads;
     for (int p = 0; p < n_tiles; ++p) {
       const int64_t base = (static_cast<int64_t>(p) * BN + static_cast<int64_t>(r) * rows_per_rank) * row_bytes;
-      for (int64_t v = static_cast<int64_t>(blockIdx.x) * kCommThreads + ct; v < slice_vecs;
-           v += static_cast<int64_t>(gridDim.x) * kCommThreads) {
-        Vec16 x = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(cm.mc_heap + cm.w_off + base + v * 16);
-        float a[8];
-        VecOf<DType::BF16>::unpack(x, a);
-        apply_scale<DType::BF16>(a, e);
-        multimem_st_vec(cm.mc_heap + cm.wavg_off + base + v * 16, VecOf<DType::BF16>::pack(a));
+      for (int64_t v0 = static_cast<int64_t>(blockIdx.x) * kCommThreads + ct; v0 < slice_vecs; v0 += kCU * vstride) {
+        Vec16 x[kCU];
+#pragma unroll
+        for (int u = 0; u < kCU; ++u) {
+          const int64_t v = v0 + u * vstride;
+          if (v < slice_vecs) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(cm.mc_heap + cm.w_off + base + v * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < kCU; ++u) {
+          const int64_t v = v0 + u * vstride;
+          if (v >= slice_vecs) continue;
+          float a[8];
+          VecOf<DType::BF16>::unpack(x[u], a);
+          apply_scale<DType::BF16>(a, e);
+          multimem_st_vec(cm.mc_heap + cm.wavg_off + base + v * 16, VecOf<DType::BF16>::pack(a));
+        }
       }
       // publish: my part of panel p is in every rank's W_avg
       asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));

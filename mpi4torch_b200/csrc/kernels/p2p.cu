@@ -36,17 +36,33 @@ struct P2pArgs {
   int user_aligned;
 };
 
+// Block-cooperative copy with kCopyUnroll independent 16-byte requests in
+// flight per thread: a peer load takes ~2 us over NVLink, so bandwidth is set by
+// memory-level parallelism (512 threads x 8 x 16 B = 64 KiB in flight per CTA).
+constexpr int kCopyUnroll = 8;
+
 __device__ __forceinline__ void copy_bytes(char* dst, const char* src, int64_t bytes, bool vec, bool src_remote) {
   if (vec) {
     const int64_t nvec = bytes / 16;
-    for (int64_t i = threadIdx.x; i < nvec; i += kThreads) {
+    int64_t i = threadIdx.x;
+    for (; i + (kCopyUnroll - 1) * kThreads < nvec; i += kCopyUnroll * kThreads) {
+      Vec16 v[kCopyUnroll];
+#pragma unroll
+      for (int u = 0; u < kCopyUnroll; ++u) {
+        const char* p = src + (i + u * kThreads) * 16;
+        v[u] = src_remote ? ld_vec_sys(p) : ld_vec_stream(p);
+      }
+#pragma unroll
+      for (int u = 0; u < kCopyUnroll; ++u) st_vec(dst + (i + u * kThreads) * 16, v[u]);
+    }
+    for (; i < nvec; i += kThreads) {
       const Vec16 v = src_remote ? ld_vec_sys(src + i * 16) : ld_vec_stream(src + i * 16);
       st_vec(dst + i * 16, v);
     }
-    for (int64_t i = nvec * 16 + threadIdx.x; i < bytes; i += kThreads)
-      dst[i] = *reinterpret_cast<const volatile char*>(src + i);
+    for (int64_t j = nvec * 16 + threadIdx.x; j < bytes; j += kThreads)
+      dst[j] = *reinterpret_cast<const volatile char*>(src + j);
   } else {
-    for (int64_t i = threadIdx.x; i < bytes; i += kThreads) dst[i] = *reinterpret_cast<const volatile char*>(src + i);
+    for (int64_t j = threadIdx.x; j < bytes; j += kThreads) dst[j] = *reinterpret_cast<const volatile char*>(src + j);
   }
 }
 

@@ -84,8 +84,46 @@ __device__ __forceinline__ void item_to_offsets(const DevJob& j, int64_t local, 
   d_o = j.dst_off + i0 * j.ds[0] + i1 * j.ds[1] + i2 * j.ds[2] + v * vb;
 }
 
+// Loads kPullUnroll items before storing any: peer loads take ~2 us, so the
+// achievable NVLink bandwidth is proportional to the requests in flight.
+constexpr int kPullUnroll = 4;
+
+template <int VB> struct MoverReg;
+template <> struct MoverReg<16> {
+  using T = Vec16;
+  static __device__ __forceinline__ T ld(const char* s) { return ld_vec_sys(s); }
+  static __device__ __forceinline__ void st(char* d, const T& v) { st_vec(d, v); }
+};
+template <> struct MoverReg<8> {
+  using T = uint2;
+  static __device__ __forceinline__ T ld(const char* s) {
+    T v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(s) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(char* d, const T& v) {
+    asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(d), "r"(v.x), "r"(v.y) : "memory");
+  }
+};
+template <> struct MoverReg<4> {
+  using T = uint32_t;
+  static __device__ __forceinline__ T ld(const char* s) { return *reinterpret_cast<const volatile uint32_t*>(s); }
+  static __device__ __forceinline__ void st(char* d, const T& v) { *reinterpret_cast<uint32_t*>(d) = v; }
+};
+template <> struct MoverReg<2> {
+  using T = uint16_t;
+  static __device__ __forceinline__ T ld(const char* s) { return *reinterpret_cast<const volatile uint16_t*>(s); }
+  static __device__ __forceinline__ void st(char* d, const T& v) { *reinterpret_cast<uint16_t*>(d) = v; }
+};
+template <> struct MoverReg<1> {
+  using T = uint8_t;
+  static __device__ __forceinline__ T ld(const char* s) { return *reinterpret_cast<const volatile uint8_t*>(s); }
+  static __device__ __forceinline__ void st(char* d, const T& v) { *reinterpret_cast<uint8_t*>(d) = v; }
+};
+
 template <int VB>
 __global__ void __launch_bounds__(kThreads) slab_pull_kernel(const SlabArgs a) {
+  using MR = MoverReg<VB>;
   const SyncCtx& c = a.sync;
   unsigned long long fb = 0;
   int par = 0;
@@ -96,15 +134,28 @@ __global__ void __launch_bounds__(kThreads) slab_pull_kernel(const SlabArgs a) {
   }
   const int64_t half = a.stage_off + static_cast<int64_t>(par) * a.half_bytes;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
-  for (int64_t it = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; it < a.total_items; it += stride) {
-    int jx = 0;
+  for (int64_t it0 = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; it0 < a.total_items;
+       it0 += kPullUnroll * stride) {
+    typename MR::T v[kPullUnroll];
+    int64_t dof[kPullUnroll];
+#pragma unroll
+    for (int u = 0; u < kPullUnroll; ++u) {
+      const int64_t it = it0 + u * stride;
+      dof[u] = -1;
+      if (it < a.total_items) {
+        int jx = 0;
 #pragma unroll 1
-    while (jx + 1 < a.njobs && it >= a.jobs[jx + 1].item_begin) ++jx;
-    const DevJob& j = a.jobs[jx];
-    int64_t so, d_o;
-    item_to_offsets(j, it - j.item_begin, VB, so, d_o);
-    const char* src = (j.peer == c.rank || !a.do_barrier) ? a.in : (a.heap[j.peer] + half);
-    Mover<VB>::copy(a.out + d_o, src + so);
+        while (jx + 1 < a.njobs && it >= a.jobs[jx + 1].item_begin) ++jx;
+        const DevJob& j = a.jobs[jx];
+        int64_t so;
+        item_to_offsets(j, it - j.item_begin, VB, so, dof[u]);
+        const char* src = (j.peer == c.rank || !a.do_barrier) ? a.in : (a.heap[j.peer] + half);
+        v[u] = MR::ld(src + so);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPullUnroll; ++u)
+      if (dof[u] >= 0) MR::st(a.out + dof[u], v[u]);
   }
   if (a.do_barrier) finish_op(c, 1);
 }
@@ -165,12 +216,23 @@ __global__ void __launch_bounds__(kThreads) slab_reduce_vec_kernel(const ReduceA
     if constexpr (NK != NvlsKind::NONE) {
       V::unpack(multimem_ld_reduce_vec<NK>(a.mc_heap + half + so), acc);
     } else {
+      // peers in batches of four: four NVLink loads in flight, combined in rank order
       const char* s0 = (c.rank == 0 || !a.do_barrier) ? a.in : (a.heap[0] + half);
       init_from<DT, OP>(acc, ld_vec_sys(s0 + so));
 #pragma unroll 1
-      for (int p = 1; p < P; ++p) {
-        const char* sp = (p == c.rank) ? a.in : (a.heap[p] + half);
-        combine_into<DT, OP>(acc, ld_vec_sys(sp + so));
+      for (int p0 = 1; p0 < P; p0 += 4) {
+        Vec16 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u;
+          if (p < P) {
+            const char* sp = (p == c.rank) ? a.in : (a.heap[p] + half);
+            v[u] = ld_vec_sys(sp + so);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (p0 + u < P) combine_into<DT, OP>(acc, v[u]);
       }
     }
     apply_scale<DT>(acc, a.epi);

@@ -24,17 +24,17 @@ CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) 
   const int P = ctl.size();
   M4T_CHECK(P <= kMaxGpuPeers, "the NVLink backend supports up to " << kMaxGpuPeers << " ranks (got " << P << ")");
   M4T_CUDA(cudaSetDevice(device_));
-  tune_.oneshot_max_bytes = env_i64("M4T_ONESHOT_MAX_KB", 256) * 1024;
+  tune_.oneshot_max_bytes = env_i64("M4T_ONESHOT_MAX_KB", 2048) * 1024;
   tune_.chunk_bytes = env_i64("M4T_CHUNK_KB", 0) * 1024;
-  tune_.pipe_min_bytes = env_i64("M4T_PIPE_MIN_MB", 32) << 20;
+  tune_.pipe_min_bytes = env_i64("M4T_PIPE_MIN_MB", 512) << 20;
   tune_.nvls_min_ranks = static_cast<int>(env_i64("M4T_NVLS_MIN_RANKS", 4));
   tune_.ar_blocks = static_cast<int>(env_i64("M4T_AR_BLOCKS", 148));
   tune_.oneshot_blocks = static_cast<int>(env_i64("M4T_ONESHOT_BLOCKS", 32));
   tune_.slab_blocks = static_cast<int>(env_i64("M4T_SLAB_BLOCKS", 128));
-  tune_.p2p_blocks = static_cast<int>(env_i64("M4T_P2P_BLOCKS", 16));
+  tune_.p2p_blocks = static_cast<int>(env_i64("M4T_P2P_BLOCKS", 32));
   tune_.force_algo = static_cast<int>(env_i64("M4T_ALLREDUCE_ALGO", 0));
 
-  nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", 8))));
+  nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", 16))));
   slot_bytes_ = round_up64(std::max<int64_t>(4096, env_i64("M4T_P2P_SLOT_KB", 1024) * 1024), 128);
   p2p_head_off_ = kP2pHeadOff;
   p2p_tail_off_ = kP2pTailOff;
@@ -164,7 +164,9 @@ ArAlgo CudaBackend::pick_algo(int64_t bytes, DType dt, ReduceOp op) const {
   if (tune_.force_algo == 2) return ArAlgo::TWOSHOT;
   if (tune_.force_algo == 3 && nvls_ok) return ArAlgo::NVLS;
   const int64_t oneshot_cap = dc_.half_bytes / size() - 128;
-  if (bytes <= tune_.oneshot_max_bytes && bytes <= oneshot_cap) return ArAlgo::ONESHOT;
+  // one-shot ingress is (P-1) x bytes: bound that product (2 MiB by default),
+  // i.e. 2 MiB messages at P=2 but ~292 KiB at P=8
+  if (bytes * (size() - 1) <= tune_.oneshot_max_bytes && bytes <= oneshot_cap) return ArAlgo::ONESHOT;
   return nvls_pays ? ArAlgo::NVLS : ArAlgo::TWOSHOT;
 }
 
@@ -328,12 +330,21 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
   }
   FusedLinearState& st = it->second;
   chain(stream);
-  // stage this rank's weight where the switch can read it
-  launch_copy_bytes(symm_ptr(st.w_off), w, N * K * 2, dc_.sm_count, stream);
+  // The switch reads every rank's weight at ONE heap offset.  A weight that was
+  // allocated with symmetric_alloc() is used in place (zero copy); any other
+  // tensor is staged first.
+  int64_t w_off = st.w_off;
+  const char* wb = static_cast<const char*>(w);
+  const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
+  if (wb >= arena && wb + N * K * 2 <= arena + symm_bytes_) {
+    w_off = wb - dc_.heap[dc_.sync.rank];
+  } else {
+    launch_copy_bytes(symm_ptr(st.w_off), w, N * K * 2, dc_.sm_count, stream);
+  }
   const int par = static_cast<int>(st.calls & 1);
   st.calls += 1;
   const uint32_t target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
-  launch_fused_allreduce_gemm(dc_, x, y, M, N, K, ldx, ldy, st.w_off, st.wavg_off[par], st.flags_off, target, scale,
+  launch_fused_allreduce_gemm(dc_, x, y, M, N, K, ldx, ldy, w_off, st.wavg_off[par], st.flags_off, target, scale,
                               stream, mse);
   return symm_ptr(st.wavg_off[par]);
 }

@@ -18,7 +18,7 @@
 namespace m4t {
 
 struct CudaTuning {
-  int64_t oneshot_max_bytes;   // M4T_ONESHOT_MAX_KB
+  int64_t oneshot_max_bytes;   // M4T_ONESHOT_MAX_KB: bound on bytes x (P-1) for the one-shot path
   int64_t chunk_bytes;         // M4T_CHUNK_KB   (0 = auto: one chunk, or bytes/8 when pipelined)
   int64_t pipe_min_bytes;      // M4T_PIPE_MIN_MB: messages >= this use the role-split pipelined kernel
   int nvls_min_ranks;          // M4T_NVLS_MIN_RANKS: in-switch reduction only pays off from this world size

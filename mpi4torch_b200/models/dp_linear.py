@@ -21,14 +21,26 @@ from mpi4torch_b200.ops import allreduce_linear
 
 class DPLinearModel:
     def __init__(self, in_features: int = 4096, out_features: int = 4096, comm=None, device="cuda",
-                 dtype=torch.bfloat16, lr: float = 1e-4, seed: int = 0, fused: bool = True, fast: bool = True):
+                 dtype=torch.bfloat16, lr: float = 1e-4, seed: int = 0, fused: bool = True, fast: bool = True,
+                 overlap_slices: int = 4):
         self.comm = m4t.COMM_WORLD if comm is None else comm
         g = torch.Generator().manual_seed(seed)  # identical initial weights on every rank
         w = torch.randn(out_features, in_features, generator=g) * (in_features ** -0.5)
-        self.weight = w.to(device=device, dtype=dtype).requires_grad_()
+        dev = torch.device(device)
+        if (dev.type == "cuda" and dtype == torch.bfloat16 and self.comm.size > 1 and m4t.cuda_backend_ready()
+                and hasattr(torch.ops.mpi4torch_b200, "symmetric_empty")):
+            # keep the parameter in the symmetric heap: the fused Allreduce->GEMM
+            # kernel (and the NVSwitch) then read it in place, no staging copy
+            storage = torch.ops.mpi4torch_b200.symmetric_empty(list(w.shape), dtype)
+            storage.copy_(w.to(dtype))
+            self.weight = storage.requires_grad_()
+        else:
+            self.weight = w.to(device=device, dtype=dtype).requires_grad_()
         self.lr = lr
         self.fused = fused  # Allreduce->GEMM in one kernel when the NVLS path is up
         self.fast = fast    # fully fused training step (no autograd graph) when the inputs allow it
+        self.overlap_slices = overlap_slices  # wgrad/allreduce pipelining granularity (fast path)
+        self._side = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return allreduce_linear(x, self.weight, self.comm, force_unfused=not self.fused)
@@ -54,8 +66,29 @@ class DPLinearModel:
         dy, local, _w_avg = torch.ops.mpi4torch_b200.linear_mse_forward(
             x, self.weight, target, 1.0 / c.size, 1.0 / (B * c.size), 2.0 / B, self.fused)
         loss = c.Allreduce(local, m4t.MPI_SUM)
-        gw_local = dy.t() @ x
-        torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight, gw_local, -self.lr / c.size)
+        n_out = self.weight.shape[0]
+        slices = self.overlap_slices if (c.size > 1 and n_out % max(self.overlap_slices, 1) == 0) else 1
+        if slices <= 1:
+            gw_local = dy.t() @ x
+            torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight, gw_local, -self.lr / c.size)
+            return loss[0]
+        # Overlap the gradient all-reduce with the wgrad GEMM: W is updated in row
+        # slices; slice i's Allreduce(+SGD epilogue) runs on a side stream while the
+        # tensor cores compute slice i+1.
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        rows = n_out // slices
+        for i in range(slices):
+            gw_i = dy[:, i * rows:(i + 1) * rows].t() @ x
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight[i * rows:(i + 1) * rows], gw_i, -self.lr / c.size)
+                gw_i.record_stream(side)
+        main.wait_stream(side)
         return loss[0]
 
     def train_step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

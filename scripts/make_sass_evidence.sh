@@ -1,0 +1,43 @@
+#!/bin/bash
+# Extracts the SASS/PTX evidence the profiling recipe asks for (B200_PROFILING.md,
+# "What proves a Blackwell-native kernel") from the built extension into profiles/.
+set -eu
+SO=mpi4torch_b200/_lib/_m4t_C.so
+OUT=profiles/sass
+mkdir -p $OUT
+cuobjdump -sass $SO > /tmp/m4t_sass.txt
+python - <<'PY'
+import re, collections
+txt = open('/tmp/m4t_sass.txt').read()
+funcs = re.split(r'\n\s*Function : ', txt)
+want = {
+  'gemm_bf16_tn_kernelILb1ELi1E': 'fused_allreduce_gemm_mse',
+  'gemm_bf16_tn_kernelILb0ELi0E': 'gemm_tcgen05_plain',
+  'allreduce_pipelined_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_pipelined_bf16_sum',
+  'allreduce_twoshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_bf16_sum',
+  'allreduce_oneshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2E': 'allreduce_oneshot_bf16_sum',
+  'p2p_recv_kernel': 'p2p_recv',
+  'slab_pull_kernelILi16E': 'slab_pull_16B',
+  'bcast_kernel': 'bcast',
+}
+pat = re.compile(r'\b(UTCHMMA|UTCQMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|LDTM[.\w]*|STTM[.\w]*|UTCBAR[.\w]*|LDGMC[.\w]*|STG\.[\w.]*MC[\w.]*|REDG?[.\w]*MC[.\w]*|MULTIMEM[.\w]*|LDG\.E\.128[.\w]*|STG\.E\.128[.\w]*|SYNCS[.\w]*|HMMA[.\w]*|MEMBAR[.\w]*|ST\.E[.\w]*STRONG\.SYS|LD\.E[.\w]*STRONG\.SYS)\b')
+summary = []
+for f in funcs[1:]:
+    name = f.split('\n', 1)[0].strip()
+    for key, label in want.items():
+        if key in name:
+            ops = collections.Counter(m.group(1) for m in pat.finditer(f))
+            open(f'profiles/sass/{label}.sass', 'w').write('Function : ' + f)
+            summary.append((label, name, ops))
+            break
+with open('profiles/sass/SUMMARY.md', 'w') as out:
+    out.write('# SASS evidence (cuobjdump -sass of mpi4torch_b200/_lib/_m4t_C.so, sm_100a)\n\n')
+    out.write('PTX -> SASS: tcgen05.mma = UTCHMMA, tcgen05.ld = LDTM, TMA = UTMALDG, multimem.ld_reduce = LDGMC, '
+              'multimem.st / multimem.red = STG/RED with the .MC* modifiers, mbarrier = SYNCS.\n\n')
+    for label, name, ops in summary:
+        out.write(f'## {label}\n`{name[:160]}`\n\n')
+        for op, n in sorted(ops.items(), key=lambda kv: -kv[1]):
+            out.write(f'- `{op}` x {n}\n')
+        out.write('\n')
+print(open('profiles/sass/SUMMARY.md').read()[:3000])
+PY
