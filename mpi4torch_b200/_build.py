@@ -32,6 +32,7 @@ _SOURCES = [
     "kernels/rooted.cu",
     "kernels/p2p.cu",
     "kernels/gemm_tcgen05.cu",
+    "kernels/gemm_tcgen05_2cta.cu",
     "api/comm_raw.cpp",
     "api/autograd_ops.cpp",
     "api/fused_ops.cpp",

@@ -43,6 +43,21 @@ Tensor gemm_bf16_tn(const Tensor& x, const Tensor& w) {
   return y;
 }
 
+// Same GEMM on CTA pairs (cta_group::2); exposed separately for A/B testing.
+Tensor gemm_bf16_tn_2cta(const Tensor& x, const Tensor& w) {
+  check_2d_bf16(x, "x");
+  check_2d_bf16(w, "w");
+  TORCH_CHECK(x.size(1) == w.size(1), "mpi4torch_b200: inner dimensions differ");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor y = at::empty({x.size(0), w.size(0)}, x.options());
+  if (y.numel() == 0) return y;
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  launch_gemm_bf16_tn_2cta(x.data_ptr(), w.data_ptr(), y.data_ptr(), x.size(0), w.size(0), x.size(1), x.stride(0),
+                           w.stride(0), y.stride(0), backend().device_comm().sm_count,
+                           c10::cuda::getCurrentCUDAStream(x.device().index()).stream());
+  return y;
+}
+
 bool gemm_bf16_tn_ok(const Tensor& x, const Tensor& w) {
   if (!(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.scalar_type() == at::kBFloat16 &&
         w.scalar_type() == at::kBFloat16 && x.stride(1) == 1 && w.stride(1) == 1 && x.size(1) == w.size(1)))
@@ -152,6 +167,7 @@ TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
   m.def("allreduce_axpy_(Tensor(a!) param, Tensor grad, float scale) -> ()", &allreduce_axpy_);
   m.def("symmetric_empty(int[] shape, ScalarType dtype) -> Tensor", &symmetric_empty);
   m.def("gemm_bf16_tn(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn);
+  m.def("gemm_bf16_tn_2cta(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn_2cta);
   m.def("gemm_bf16_tn_supported(Tensor x, Tensor w) -> bool", &gemm_bf16_tn_ok);
   m.def("allreduce_linear_supported(Tensor x, Tensor w) -> bool", &allreduce_linear_supported);
   m.def("allreduce_linear_fused(Tensor x, Tensor w, float scale) -> (Tensor, Tensor)", &allreduce_linear_fused);

@@ -1,0 +1,297 @@
+// CTA-pair (cta_group::2) tcgen05 GEMM:  C[M,N] = A[M,K] * B[N,K]^T, bf16.
+//
+// Two SMs of one TPC form a cluster and share a 256x256 output tile: each CTA
+// stages its own 128 rows of A and HALF of the B tile (128 of 256 rows), the
+// leader CTA issues tcgen05.mma.cta_group::2 (UMMA 256x256x16) that reads both
+// halves, and each CTA keeps its 128x256 half of the accumulator in its own
+// TMEM.  Per FLOP this moves 2/3 of the L2->SMEM bytes of the single-CTA kernel
+// (gemm_tcgen05.cu) and a stage shrinks to 32 KiB, so the TMA ring is 6 deep
+// instead of 4 - the single-CTA kernel is L2/latency bound at ~1.4 PFLOP/s.
+//
+//   warp 0 (both CTAs)   TMA producer: cp.async.bulk.tensor ... cta_group::2,
+//                        transaction bytes credited to the LEADER's mbarrier
+//   warp 1 (leader)      MMA issuer; tcgen05.commit multicasts to both CTAs
+//   warps 2..5 (both)    epilogue on the CTA's own TMEM lanes; the peer's
+//                        "accumulator drained" arrive goes to the leader's
+//                        mbarrier through a mapa'd shared::cluster address
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "kernels.h"
+#include "tcgen05_ptx.cuh"
+#include "vec_ops.cuh"
+
+namespace m4t {
+
+namespace {
+
+constexpr int BMC = 128;        // rows of A per CTA
+constexpr int BM2 = 2 * BMC;    // cluster tile rows
+constexpr int BN = 256;         // cluster tile cols
+constexpr int BNH = BN / 2;     // B rows staged per CTA
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int kStages = 6;
+constexpr int kAccStages = 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kABytes = BMC * BK * 2;  // 16 KiB
+constexpr int kBBytes = BNH * BK * 2;  // 16 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kWarps = 6;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+
+struct Gemm2Args {
+  void* C;
+  int M, N, K;
+  int ldc;
+  const void* T;
+  int ldt;
+  float* loss_acc;
+  float loss_scale, grad_scale;
+};
+
+struct __align__(8) Bars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  return static_cast<uint32_t>(float_to_bf16_bits(lo)) | (static_cast<uint32_t>(float_to_bf16_bits(hi)) << 16);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const Gemm2Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars* bars = reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = tc::cluster_ctarank();
+  const bool leader = cta == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int m_tiles = (g.M + BM2 - 1) / BM2;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&bars->full[s], 1);
+      tc::mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      tc::mbar_init(&bars->tmem_full[a], 1);
+      tc::mbar_init(&bars->tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs (used in the leader)
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
+  tc::tcgen05_fence_before();
+  tc::cluster_sync();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int n_blk = t / m_tiles;
+        const int m_blk = t - n_blk * m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tc::mbar_wait(&bars->empty[stage], phase ^ 1);  // own copy, signalled by the multicast commit
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          if (leader) tc::mbar_arrive_expect_tx(&bars->full[stage], 2 * kStageBytes);  // both CTAs' bytes
+          tc::tma_load_2d_2sm(sa, &tmap_a, &bars->full[stage], kb * BK, m_blk * BM2 + static_cast<int>(cta) * BMC);
+          tc::tma_load_2d_2sm(sb, &tmap_b, &bars->full[stage], kb * BK, n_blk * BN + static_cast<int>(cta) * BNH);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM2, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);  // both CTAs drained this accumulator
+        tc::tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          tc::mbar_wait(&bars->full[stage], phase);
+          tc::tcgen05_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t adesc = tc::make_smem_desc_k_sw128(sa);
+          const uint64_t bdesc = tc::make_smem_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+            tc::umma_bf16_ss_2sm(tmem_d, adesc + koff, bdesc + koff, idesc, (kb | k) ? 1u : 0u);
+          }
+          tc::umma_commit_2sm(&bars->empty[stage]);  // frees the stage in BOTH CTAs
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::umma_commit_2sm(&bars->tmem_full[acc]);  // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs) =========================
+    const int q = warp & 3;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const int n_blk = t / m_tiles;
+      const int m_blk = t - n_blk * m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      tc::mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc::tcgen05_fence_after();
+      const int row = m_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
+      uint16_t* crow = static_cast<uint16_t*>(g.C) + static_cast<int64_t>(row) * g.ldc + n_blk * BN;
+      const uint16_t* trow = nullptr;
+      float loss_part = 0.f;
+      if (EPI == 1) trow = static_cast<const uint16_t*>(g.T) + static_cast<int64_t>(row) * g.ldt + n_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32);
+        tc::tmem_ld_32x32b_x32(taddr, r);
+        tc::tmem_ld_wait();
+        if (row < g.M) {
+          const int col0 = n_blk * BN + c * 32;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (col0 + v * 8 + 8 <= g.N) {
+              Vec16 o;
+              if (EPI == 1) {
+                const Vec16 tv = ld_vec_stream(trow + c * 32 + v * 8);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float d0 = __uint_as_float(r[v * 8 + 2 * e]) - bf16_bits_to_float(static_cast<uint16_t>(tv.w[e] & 0xffffu));
+                  const float d1 = __uint_as_float(r[v * 8 + 2 * e + 1]) - bf16_bits_to_float(static_cast<uint16_t>(tv.w[e] >> 16));
+                  loss_part = fmaf(d0, d0, loss_part);
+                  loss_part = fmaf(d1, d1, loss_part);
+                  o.w[e] = pack2(d0 * g.grad_scale, d1 * g.grad_scale);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  o.w[e] = pack2(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+              }
+              st_vec(crow + c * 32 + v * 8, o);
+            }
+          }
+        }
+      }
+      if (EPI == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+        if (lane == 0) atomicAdd(g.loss_acc, loss_part * g.loss_scale);
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        // "drained" is collected by the leader's barrier (count 8)
+        if (leader) tc::mbar_arrive(&bars->tmem_empty[acc]);
+        else tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bars->tmem_empty[acc]), 0));
+      }
+    }
+  }
+
+  tc::tcgen05_fence_before();
+  tc::cluster_sync();
+  if (warp == 1) tc::tmem_dealloc_2sm<kTmemCols>(tmem_base);
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled2() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    M4T_CHECK(e == cudaSuccess && q == cudaDriverEntryPointSuccess && p, "cuTensorMapEncodeTiled unavailable");
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+CUtensorMap make_tmap2(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled2()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M4T_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " << static_cast<int>(r));
+  return m;
+}
+
+template <int EPI> void configure2() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
+  });
+}
+
+}  // namespace
+
+void launch_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                              int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream, const MseEpilogue* mse) {
+  M4T_CHECK(gemm_bf16_tn_supported(M, N, K, A, B, C, lda, ldb, ldc), "unsupported GEMM shape/alignment for the tcgen05 path");
+  const CUtensorMap ta = make_tmap2(A, M, K, lda, BMC);
+  const CUtensorMap tb = make_tmap2(B, N, K, ldb, BNH);
+  Gemm2Args g{};
+  g.C = C;
+  g.M = static_cast<int>(M);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldc = static_cast<int>(ldc);
+  const int tiles = static_cast<int>(((M + BM2 - 1) / BM2) * ((N + BN - 1) / BN));
+  const int clusters = std::max(1, std::min(tiles, sm_count / 2));
+  if (mse) {
+    g.T = mse->target;
+    g.ldt = static_cast<int>(mse->ldt);
+    g.loss_acc = mse->loss_acc;
+    g.loss_scale = mse->loss_scale;
+    g.grad_scale = mse->grad_scale;
+    configure2<1>();
+    gemm_bf16_tn_2cta_kernel<1><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g);
+  } else {
+    configure2<0>();
+    gemm_bf16_tn_2cta_kernel<0><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g);
+  }
+  cudaError_t e = cudaGetLastError();
+  M4T_CHECK(e == cudaSuccess, "gemm_bf16_tn_2cta launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
+}
+
+}  // namespace m4t

@@ -309,7 +309,14 @@ bool CudaBackend::fused_linear_available(int64_t N, int64_t K) const {
 void CudaBackend::gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                                int64_t ldb, int64_t ldc, cudaStream_t stream, const MseEpilogue* mse) {
   M4T_CUDA(cudaSetDevice(device_));
-  launch_gemm_bf16_tn(A, B, C, M, N, K, lda, ldb, ldc, dc_.sm_count, stream, mse);
+  // CTA-pair kernel for anything big enough to fill the pairs; M4T_GEMM_2CTA=0/1 forces.
+  static const int64_t mode = env_i64("M4T_GEMM_2CTA", -1);
+  const bool big = M >= 512 && N >= 512;
+  if (mode == 1 || (mode < 0 && big && gemm_2cta_default_)) {
+    launch_gemm_bf16_tn_2cta(A, B, C, M, N, K, lda, ldb, ldc, dc_.sm_count, stream, mse);
+  } else {
+    launch_gemm_bf16_tn(A, B, C, M, N, K, lda, ldb, ldc, dc_.sm_count, stream, mse);
+  }
 }
 
 const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,

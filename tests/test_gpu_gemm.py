@@ -51,3 +51,40 @@ def test_gemm_speed_report():
         b.synchronize()
         ms = a.elapsed_time(b) / 10
         print(f"[gemm] {name}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 512, 256), (4096, 4096, 4096), (8192, 4096, 4096), (300, 520, 200)])
+def test_gemm_2cta_matches_fp32_reference(shape):
+    import mpi4torch_b200 as m4t  # noqa: F401
+
+    m4t.COMM_WORLD
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.ops.mpi4torch_b200.gemm_bf16_tn_2cta(x, w)
+    torch.cuda.synchronize()
+    ref = _ref(x, w)
+    err = (y.float() - ref).abs().max().item()
+    assert err / (ref.abs().max().item() + 1e-6) < 2e-2, f"{shape}: max abs err {err}"
+
+
+def test_gemm_2cta_speed_report():
+    import mpi4torch_b200 as m4t  # noqa: F401
+
+    m4t.COMM_WORLD
+    M, N, K = 8192, 4096, 4096
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    fn = lambda: torch.ops.mpi4torch_b200.gemm_bf16_tn_2cta(x, w)  # noqa: E731
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        fn()
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / 10
+    print(f"[gemm] tcgen05 cta_group::2: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
