@@ -23,6 +23,7 @@
 #include <unordered_map>
 
 #include "kernels.h"
+#include "fused_comm.cuh"
 #include "tcgen05_ptx.cuh"
 #include "vec_ops.cuh"
 
@@ -57,16 +58,6 @@ struct GemmArgs {
   uint32_t panel_target;        // a panel is ready when its counter >= target (wrap-safe)
 };
 
-struct CommArgs {
-  SyncCtx sync;
-  char* mc_heap;        // multicast mapping of the symmetric heap
-  char* my_heap;
-  int64_t w_off;        // byte offset of the (staged) weight inside every rank's heap
-  int64_t wavg_off;     // byte offset of the W_avg buffer inside every rank's heap
-  int64_t flags_off;    // byte offset of the panel counters
-  float scale;
-  int do_barrier;       // 1: cross-rank barrier before the first multimem.ld_reduce
-};
 
 struct __align__(8) SharedBarriers {
   uint64_t full[kStages];
@@ -238,74 +229,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (FUSED) {
     // =========================== communication ==========================
-    // All-reduce the weight, panel by panel (panel = BN rows of W).  Rank r owns
-    // rows [r*BN/P, (r+1)*BN/P) of every panel; CTA b handles the 16-byte
-    // vectors v = b, b+G, ... of that slice, so "block b on every rank" is a
-    // closed group and a per-block barrier is all the ordering needed.
-    const SyncCtx& c = cm.sync;
-    const int P = c.size, r = c.rank;
-    const int ct = threadIdx.x - kGemmWarps * 32;  // 0..127
-    constexpr int kCommThreads = kCommWarps * 32;
-    unsigned long long fb = 0;
-    if (cm.do_barrier) {
-      // every rank's weight (in its heap) is final before anyone reduces it
-      fb = read_flag_base(c);
-      asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
-      if (ct < P && ct != r) {
-        const uint32_t v = static_cast<uint32_t>(fb + 1ull);
-        st_release_sys_u32(c.pads[ct] + blockIdx.x * kMaxGpuPeers + r, v);
-        wait_flag_ge(c.pads[r] + blockIdx.x * kMaxGpuPeers + ct, v, c);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
-    }
-    const int64_t row_bytes = static_cast<int64_t>(g.K) * 2;
-    const int rows_per_rank = BN / P;                      // host guarantees divisibility
-    const int64_t slice_vecs = rows_per_rank * row_bytes / 16;
-    DevEpilogue e;
-    e.scale_f = cm.scale;
-    e.scale_d = cm.scale;
-    e.has_scale = 1;
-    e.acc = nullptr;
-    uint32_t* mc_flags = reinterpret_cast<uint32_t*>(cm.mc_heap + cm.flags_off);
-    constexpr int kCU = 4;  // independent multimem.ld_reduce requests in flight per thread
-    const int64_t vstride = static_cast<int64_t>(gridDim.x) * kCommThreads;
-    for (int p = 0; p < n_tiles; ++p) {
-      const int64_t base = (static_cast<int64_t>(p) * BN + static_cast<int64_t>(r) * rows_per_rank) * row_bytes;
-      for (int64_t v0 = static_cast<int64_t>(blockIdx.x) * kCommThreads + ct; v0 < slice_vecs; v0 += kCU * vstride) {
-        Vec16 x[kCU];
-#pragma unroll
-        for (int u = 0; u < kCU; ++u) {
-          const int64_t v = v0 + u * vstride;
-          if (v < slice_vecs) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(cm.mc_heap + cm.w_off + base + v * 16);
-        }
-#pragma unroll
-        for (int u = 0; u < kCU; ++u) {
-          const int64_t v = v0 + u * vstride;
-          if (v >= slice_vecs) continue;
-          float a[8];
-          VecOf<DType::BF16>::unpack(x[u], a);
-          apply_scale<DType::BF16>(a, e);
-          multimem_st_vec(cm.mc_heap + cm.wavg_off + base + v * 16, VecOf<DType::BF16>::pack(a));
-        }
-      }
-      // publish: my part of panel p is in every rank's W_avg
-      asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
-      if (ct == 0) {
-        __threadfence_system();
-        asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_flags + p), "r"(1u) : "memory");
-      }
-    }
-    if (cm.do_barrier && ct == 0) {
-      // advance the communicator's flag/op counters exactly like finish_op()
-      __threadfence();
-      const unsigned int prev = atomicAdd(c.done_ctr, 1u);
-      if (prev == gridDim.x - 1) {
-        *c.done_ctr = 0;
-        __threadfence();
-        atomicAdd(c.counters + 0, 1ull);
-        atomicAdd(c.counters + 1, 1ull);
-      }
-    }
+    comm_allreduce_panels<kCommWarps, BN>(cm, kGemmWarps * 32, n_tiles, g.K);
   }
 
   __syncthreads();
@@ -428,8 +352,10 @@ void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, i
   cm.flags_off = flags_off;
   cm.scale = scale;
   cm.do_barrier = 1;
+  cm.debug_skip = static_cast<int>(env_i64("M4T_FUSED_DEBUG", 0));
+  if (cm.debug_skip & 2) g.M = 0;  // timing experiment: communication only, no GEMM tiles
   // the grid must be identical on every rank (per-block barrier + counter targets)
-  const int grid = std::min(dc.sm_count, kMaxChannels);
+  const int grid = fused_gemm_grid(dc);
   if (mse) {
     g.T = mse->target;
     g.ldt = static_cast<int>(mse->ldt);
@@ -445,6 +371,6 @@ void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, i
   check_launch("fused_allreduce_gemm");
 }
 
-int fused_gemm_grid(const DeviceComm& dc) { return std::min(dc.sm_count, kMaxChannels); }
+int fused_gemm_grid(const DeviceComm& dc) { return std::min(dc.sm_count, kMaxChannels) & ~1; }
 
 }  // namespace m4t

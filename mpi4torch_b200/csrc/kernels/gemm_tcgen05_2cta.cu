@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "kernels.h"
+#include "fused_comm.cuh"
 #include "tcgen05_ptx.cuh"
 #include "vec_ops.cuh"
 
@@ -40,6 +41,7 @@ constexpr int kABytes = BMC * BK * 2;  // 16 KiB
 constexpr int kBBytes = BNH * BK * 2;  // 16 KiB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kWarps = 6;
+constexpr int kCommWarps = 4;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 
 struct Gemm2Args {
@@ -50,6 +52,8 @@ struct Gemm2Args {
   int ldt;
   float* loss_acc;
   float loss_scale, grad_scale;
+  const uint32_t* panel_flags;  // fused mode: per-panel counters (local HBM, written through multicast)
+  uint32_t panel_target;
 };
 
 struct __align__(8) Bars {
@@ -64,10 +68,10 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return static_cast<uint32_t>(float_to_bf16_bits(lo)) | (static_cast<uint32_t>(float_to_bf16_bits(hi)) << 16);
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWarps * 32, 1)
+template <bool FUSED, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kWarps + (FUSED ? kCommWarps : 0)) * 32, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const Gemm2Args g) {
+                         const Gemm2Args g, const CommArgs cm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars* bars = reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
@@ -110,6 +114,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int n_blk = t / m_tiles;
         const int m_blk = t - n_blk * m_tiles;
+        if (FUSED) {
+          // the weight panel (both halves) must have been all-reduced by every rank
+          const uint32_t* flag = g.panel_flags + n_blk;
+          while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - g.panel_target) < 0) {
+          }
+          tc::fence_proxy_async();
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&bars->empty[stage], phase ^ 1);  // own copy, signalled by the multicast commit
           uint8_t* sa = smem + stage * kStageBytes;
@@ -158,7 +169,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tc::umma_commit_2sm(&bars->tmem_full[acc]);  // accumulator ready in BOTH CTAs
       }
     }
-  } else {
+  } else if (warp < kWarps) {
     // ===================== epilogue (both CTAs) =========================
     const int q = warp & 3;
     int it = 0;
@@ -221,6 +232,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   }
 
+  else if (FUSED) {
+    // ===================== communication (both CTAs) ====================
+    comm_allreduce_panels<kCommWarps, BN>(cm, kWarps * 32, n_tiles, g.K);
+  }
+
   tc::tcgen05_fence_before();
   tc::cluster_sync();
   if (warp == 1) tc::tmem_dealloc_2sm<kTmemCols>(tmem_base);
@@ -254,10 +270,10 @@ CUtensorMap make_tmap2(const void* base, int64_t rows, int64_t cols, int64_t ld,
   return m;
 }
 
-template <int EPI> void configure2() {
+template <bool FUSED, int EPI> void configure2() {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<FUSED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
   });
 }
@@ -283,14 +299,62 @@ void launch_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int64_t M, 
     g.loss_acc = mse->loss_acc;
     g.loss_scale = mse->loss_scale;
     g.grad_scale = mse->grad_scale;
-    configure2<1>();
-    gemm_bf16_tn_2cta_kernel<1><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g);
+    configure2<false, 1>();
+    gemm_bf16_tn_2cta_kernel<false, 1><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, CommArgs{});
   } else {
-    configure2<0>();
-    gemm_bf16_tn_2cta_kernel<0><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g);
+    configure2<false, 0>();
+    gemm_bf16_tn_2cta_kernel<false, 0><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, CommArgs{});
   }
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "gemm_bf16_tn_2cta launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
+}
+
+// Fused Allreduce->GEMM on CTA pairs.  Same contract as launch_fused_allreduce_gemm.
+void launch_fused_allreduce_gemm_2cta(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
+                                      int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
+                                      uint32_t panel_target, float scale, cudaStream_t stream, const MseEpilogue* mse) {
+  M4T_CHECK(dc.mc_heap != nullptr, "the fused Allreduce->GEMM kernel needs the NVLS multicast mapping");
+  const int P = dc.sync.size;
+  M4T_CHECK(BN % P == 0 && N % BN == 0 && (K * 2) % 16 == 0, "fused Allreduce->GEMM: N must be a multiple of 256 and 256 % ranks == 0");
+  const char* wavg = dc.heap[dc.sync.rank] + wavg_off;
+  M4T_CHECK(gemm_bf16_tn_supported(M, N, K, x, wavg, y, ldx, K, ldy), "unsupported GEMM shape/alignment for the fused path");
+  const CUtensorMap ta = make_tmap2(x, M, K, ldx, BMC);
+  const CUtensorMap tb = make_tmap2(wavg, N, K, K, BNH);
+  Gemm2Args g{};
+  g.C = y;
+  g.M = static_cast<int>(M);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldc = static_cast<int>(ldy);
+  g.panel_flags = reinterpret_cast<const uint32_t*>(dc.heap[dc.sync.rank] + flags_off);
+  g.panel_target = panel_target;
+  CommArgs cm{};
+  cm.sync = dc.sync;
+  cm.mc_heap = dc.mc_heap;
+  cm.my_heap = dc.heap[dc.sync.rank];
+  cm.w_off = w_off;
+  cm.wavg_off = wavg_off;
+  cm.flags_off = flags_off;
+  cm.scale = scale;
+  cm.do_barrier = 1;
+  cm.debug_skip = static_cast<int>(env_i64("M4T_FUSED_DEBUG", 0));
+  if (cm.debug_skip & 2) g.M = 0;  // timing experiment: communication only, no GEMM tiles
+  const int grid = fused_gemm_grid(dc);  // identical on every rank, even (whole CTA pairs)
+  if (mse) {
+    g.T = mse->target;
+    g.ldt = static_cast<int>(mse->ldt);
+    g.loss_acc = mse->loss_acc;
+    g.loss_scale = mse->loss_scale;
+    g.grad_scale = mse->grad_scale;
+    configure2<true, 1>();
+    gemm_bf16_tn_2cta_kernel<true, 1><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  } else {
+    configure2<true, 0>();
+    gemm_bf16_tn_2cta_kernel<true, 0><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, cm);
+  }
+  cudaError_t e = cudaGetLastError();
+  M4T_CHECK(e == cudaSuccess, "fused_allreduce_gemm_2cta launch failed: " << cudaGetErrorString(e));
   note_kernel_launch();
 }
 

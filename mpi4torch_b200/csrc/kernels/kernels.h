@@ -107,6 +107,10 @@ void launch_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int64_t M, 
 void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
                                  int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
                                  uint32_t panel_target, float scale, cudaStream_t stream, const MseEpilogue* mse = nullptr);
+void launch_fused_allreduce_gemm_2cta(const DeviceComm& dc, const void* x, void* y, int64_t M, int64_t N, int64_t K,
+                                      int64_t ldx, int64_t ldy, int64_t w_off, int64_t wavg_off, int64_t flags_off,
+                                      uint32_t panel_target, float scale, cudaStream_t stream,
+                                      const MseEpilogue* mse = nullptr);
 int fused_gemm_grid(const DeviceComm& dc);
 // Plain device copy into the heap (used to stage the weight for the fused kernel).
 void launch_copy_bytes(void* dst, const void* src, int64_t bytes, int sm_count, cudaStream_t stream);

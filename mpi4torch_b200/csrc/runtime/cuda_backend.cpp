@@ -351,8 +351,14 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
   const int par = static_cast<int>(st.calls & 1);
   st.calls += 1;
   const uint32_t target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
-  launch_fused_allreduce_gemm(dc_, x, y, M, N, K, ldx, ldy, w_off, st.wavg_off[par], st.flags_off, target, scale,
-                              stream, mse);
+  static const int64_t fused_2cta = env_i64("M4T_FUSED_2CTA", 0);
+  if (fused_2cta) {
+    launch_fused_allreduce_gemm_2cta(dc_, x, y, M, N, K, ldx, ldy, w_off, st.wavg_off[par], st.flags_off, target,
+                                     scale, stream, mse);
+  } else {
+    launch_fused_allreduce_gemm(dc_, x, y, M, N, K, ldx, ldy, w_off, st.wavg_off[par], st.flags_off, target, scale,
+                                stream, mse);
+  }
   return symm_ptr(st.wavg_off[par]);
 }
 

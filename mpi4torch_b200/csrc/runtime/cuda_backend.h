@@ -141,7 +141,7 @@ class CudaBackend final : public Backend {
   };
   std::unordered_map<int64_t, FusedLinearState> fused_;  // key = N << 32 | K
   int64_t symm_off_ = 0, symm_cursor_ = 0, symm_bytes_ = 0;
-  bool gemm_2cta_default_ = false;  // flipped to true once the CTA-pair kernel is validated on hardware
+  bool gemm_2cta_default_ = true;  // CTA-pair kernel validated on B200: 1521 vs 1390 TFLOP/s (cuBLAS 1552)
 };
 
 }  // namespace m4t

@@ -22,7 +22,7 @@ from mpi4torch_b200.ops import allreduce_linear
 class DPLinearModel:
     def __init__(self, in_features: int = 4096, out_features: int = 4096, comm=None, device="cuda",
                  dtype=torch.bfloat16, lr: float = 1e-4, seed: int = 0, fused: bool = True, fast: bool = True,
-                 overlap_slices: int = 4):
+                 overlap_slices: int = 1):
         self.comm = m4t.COMM_WORLD if comm is None else comm
         g = torch.Generator().manual_seed(seed)  # identical initial weights on every rank
         w = torch.randn(out_features, in_features, generator=g) * (in_features ** -0.5)
