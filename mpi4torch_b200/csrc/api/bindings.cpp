@@ -118,6 +118,42 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("kernel_launch_count", [] { return static_cast<int64_t>(kernel_launch_count()); },
         "Kernels launched by this library in this process.");
+  // Slab-plan introspection (tests): every job as a dict of plain integers.
+  auto jobs_to_py = [](const std::vector<SlabJob>& jobs) {
+    py::list out;
+    for (const SlabJob& j : jobs) {
+      py::dict d;
+      d["peer"] = j.peer;
+      d["src_off"] = j.src_off;
+      d["dst_off"] = j.dst_off;
+      d["n"] = py::make_tuple(j.n[0], j.n[1], j.n[2]);
+      d["ss"] = py::make_tuple(j.ss[0], j.ss[1], j.ss[2]);
+      d["ds"] = py::make_tuple(j.ds[0], j.ds[1], j.ds[2]);
+      d["run"] = j.run;
+      out.append(d);
+    }
+    return out;
+  };
+  m.def("plan_gather", [jobs_to_py](int rank, int size, int root, int64_t before, int64_t after,
+                                     std::vector<int64_t> lens, bool all) {
+    PullPlan p = plan_gather(rank, size, root, before, after, lens, all);
+    return py::make_tuple(jobs_to_py(p.jobs), p.stage_elems, p.out_elems);
+  });
+  m.def("plan_scatter", [jobs_to_py](int rank, int size, int root, int64_t before, int64_t after,
+                                      std::vector<int64_t> counts) {
+    PullPlan p = plan_scatter(rank, size, root, before, after, counts);
+    return py::make_tuple(jobs_to_py(p.jobs), p.stage_elems, p.out_elems);
+  });
+  m.def("plan_alltoall", [jobs_to_py](int rank, int size, std::vector<int64_t> shape, int64_t g, int64_t s_,
+                                       std::vector<int64_t> glen, std::vector<int64_t> counts) {
+    PullPlan p = plan_alltoall(rank, size, shape, g, s_, glen, counts);
+    return py::make_tuple(jobs_to_py(p.jobs), p.stage_elems, p.out_elems);
+  });
+  m.def("plan_repartition", [jobs_to_py](int rank, int size, int64_t before, int64_t after, std::vector<int64_t> cur,
+                                          std::vector<int64_t> nw) {
+    PullPlan p = plan_repartition(rank, size, before, after, cur, nw);
+    return py::make_tuple(jobs_to_py(p.jobs), p.stage_elems, p.out_elems);
+  });
   m.def("check_device_error", [] {
     World& w = World::instance();
     if (w.cuda_ready()) w.cuda()->check_device_error();

@@ -116,7 +116,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (FUSED) {
           // the weight panel must have been all-reduced (by every rank) first
           const uint32_t* flag = g.panel_flags + n_blk;
-          while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - g.panel_target) < 0) {
+          // bounded like every other cross-rank wait: a peer that never publishes
+          // must end in an error, not in a hung GPU
+          if (static_cast<int32_t>(ld_acquire_sys_u32(flag) - g.panel_target) < 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned int spins = 0;
+            while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - g.panel_target) < 0) {
+              if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > cm.sync.timeout_ns) {
+                *reinterpret_cast<volatile int*>(cm.sync.err_flag) = kErrTimeout;
+                __threadfence_system();
+                __trap();
+              }
+            }
           }
           tc::fence_proxy_async();  // generic-proxy writes (multimem.st) -> async-proxy reads (TMA)
         }

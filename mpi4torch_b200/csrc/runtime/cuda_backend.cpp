@@ -301,6 +301,9 @@ int64_t CudaBackend::symm_alloc(int64_t bytes) {
 bool CudaBackend::fused_linear_available(int64_t N, int64_t K) const {
   if (size() <= 1 || !has_nvls()) return false;
   if (env_i64("M4T_FUSED_LINEAR", 1) == 0) return false;
+  // in-switch reduction only pays off from ~4 ranks (measured: at P=2 the
+  // separate peer-load allreduce + GEMM is as fast as the fused kernel)
+  if (size() < tune_.nvls_min_ranks && env_i64("M4T_FUSED_LINEAR", 1) != 2) return false;
   if (N % 256 != 0 || 256 % size() != 0 || K % 64 != 0) return false;
   const int64_t need = 3 * N * K * 2 + 4096;
   return fused_.count((N << 32) | K) > 0 || symm_cursor_ + need + 4096 <= symm_bytes_;
@@ -351,7 +354,7 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
   const int par = static_cast<int>(st.calls & 1);
   st.calls += 1;
   const uint32_t target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
-  static const int64_t fused_2cta = env_i64("M4T_FUSED_2CTA", 0);
+  static const int64_t fused_2cta = env_i64("M4T_FUSED_2CTA", 1);
   if (fused_2cta) {
     launch_fused_allreduce_gemm_2cta(dc_, x, y, M, N, K, ldx, ldy, w_off, st.wavg_off[par], st.flags_off, target,
                                      scale, stream, mse);
