@@ -11,8 +11,10 @@ import re, collections
 txt = open('/tmp/m4t_sass.txt').read()
 funcs = re.split(r'\n\s*Function : ', txt)
 want = {
-  'gemm_bf16_tn_kernelILb1ELi1E': 'fused_allreduce_gemm_mse',
-  'gemm_bf16_tn_kernelILb0ELi0E': 'gemm_tcgen05_plain',
+  'gemm_bf16_tn_2cta_kernelILb1ELi1E': 'fused_allreduce_gemm_mse_cta_pair',
+  'gemm_bf16_tn_2cta_kernelILb0ELi0E': 'gemm_tcgen05_cta_pair',
+  'gemm_bf16_tn_kernelILb1ELi1E': 'fused_allreduce_gemm_mse_single_cta',
+  'gemm_bf16_tn_kernelILb0ELi0E': 'gemm_tcgen05_single_cta',
   'allreduce_pipelined_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_pipelined_bf16_sum',
   'allreduce_twoshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_bf16_sum',
   'allreduce_oneshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2E': 'allreduce_oneshot_bf16_sum',
@@ -20,7 +22,7 @@ want = {
   'slab_pull_kernelILi16E': 'slab_pull_16B',
   'bcast_kernel': 'bcast',
 }
-pat = re.compile(r'\b(UTCHMMA|UTCQMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|LDTM[.\w]*|STTM[.\w]*|UTCBAR[.\w]*|LDGMC[.\w]*|STG\.[\w.]*MC[\w.]*|REDG?[.\w]*MC[.\w]*|MULTIMEM[.\w]*|LDG\.E\.128[.\w]*|STG\.E\.128[.\w]*|SYNCS[.\w]*|HMMA[.\w]*|MEMBAR[.\w]*|ST\.E[.\w]*STRONG\.SYS|LD\.E[.\w]*STRONG\.SYS)\b')
+pat = re.compile(r'\b(UTCHMMA[.\w]*|UTCQMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|LDTM[.\w]*|STTM[.\w]*|UTCBAR[.\w]*|LDGMC[.\w]*|STG\.[\w.]*MC[\w.]*|REDG?[.\w]*MC[.\w]*|MULTIMEM[.\w]*|LDG\.E\.128[.\w]*|STG\.E\.128[.\w]*|SYNCS[.\w]*|HMMA[.\w]*|MEMBAR[.\w]*|ST\.E[.\w]*STRONG\.SYS|LD\.E[.\w]*STRONG\.SYS)\b')
 summary = []
 for f in funcs[1:]:
     name = f.split('\n', 1)[0].strip()
