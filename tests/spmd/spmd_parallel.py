@@ -1,0 +1,100 @@
+"""Parallelism helpers built on the primitives: DataParallel wrapper, in-place
+gradient sync, ring exchange, sequence<->head exchange, fused-epilogue ops."""
+import unittest
+
+import torch
+
+import mpi4torch_b200 as m4t
+from mpi4torch_b200 import ops
+from mpi4torch_b200.parallel import DataParallel, heads_to_sequence, ring_exchange, sequence_to_heads, sync_gradients_
+from common import DEVICE, comm
+
+P, R = comm.size, comm.rank
+DT = torch.float64
+
+
+class TestDataParallel(unittest.TestCase):
+    def test_wrapper_trains_identically_on_all_ranks(self):
+        torch.manual_seed(5)  # same initial weights everywhere
+        net = DataParallel(torch.nn.Linear(6, 3).to(DT).to(DEVICE), comm)
+        opt = torch.optim.SGD(net.module.parameters(), lr=0.05)
+        g = torch.Generator().manual_seed(100 + R)  # different (fixed) data per rank
+        x = torch.randn(16, 6, generator=g, dtype=DT).to(DEVICE)
+        y = x.sum(dim=1, keepdim=True).expand(16, 3)
+        first = last = None
+        for _ in range(20):
+            opt.zero_grad()
+            loss = comm.Allreduce(((net(x) - y) ** 2).mean(), m4t.MPI_SUM) / P
+            loss.backward()
+            opt.step()
+            first = first if first is not None else loss.item()
+            last = loss.item()
+        self.assertLess(last, first)
+        for p in net.module.parameters():  # gradient sync fell out of the adjoint
+            self.assertTrue(torch.equal(p.detach(), comm.Bcast_(p.detach().clone(), 0)))
+
+    def test_gradient_equals_gradient_of_the_global_mean_loss(self):
+        torch.manual_seed(1)
+        lin = torch.nn.Linear(4, 2).to(DT).to(DEVICE)
+        net = DataParallel(lin, comm)
+        xs = [torch.randn(8, 4, generator=torch.Generator().manual_seed(p), dtype=DT).to(DEVICE) for p in range(P)]
+        comm.Allreduce(net(xs[R]).square().sum(), m4t.MPI_SUM).backward()
+        g_dp = lin.weight.grad.clone()
+        ref = torch.nn.Linear(4, 2).to(DT).to(DEVICE)
+        ref.load_state_dict(lin.state_dict())
+        sum(ref(x).square().sum() for x in xs).backward()
+        # d/dW_local of f(mean_ranks(W)) = (1/P) * sum of all ranks' gradients ... times P seeds
+        self.assertTrue(torch.allclose(g_dp, ref.weight.grad, rtol=1e-10, atol=1e-10))
+
+    def test_sync_gradients_inplace(self):
+        w = torch.nn.Parameter(torch.zeros(5, dtype=DT, device=DEVICE))
+        w.grad = torch.full((5,), float(R + 1), dtype=DT, device=DEVICE)
+        sync_gradients_([w], comm)
+        self.assertTrue(torch.equal(w.grad, torch.full_like(w.grad, (P + 1) / 2)))
+
+
+class TestRingAndSequence(unittest.TestCase):
+    def test_ring_exchange_is_differentiable(self):
+        a = torch.full((3,), float(R + 1), dtype=DT, device=DEVICE).requires_grad_()
+        b = ring_exchange(a, comm)
+        left = (R - 1) % P
+        self.assertTrue(torch.equal(b.detach(), torch.full_like(b, float(left + 1))))
+        (b * (R + 1)).sum().backward()
+        right = (R + 1) % P
+        self.assertTrue(torch.equal(a.grad, torch.full_like(a, float(right + 1))))
+
+    def test_sequence_heads_round_trip_and_values(self):
+        seq_local, heads = 3, 2 * P
+        x = (torch.arange(2 * seq_local * heads * 4, dtype=DT).reshape(2, seq_local, heads, 4) + 1000 * R).to(DEVICE)
+        y = sequence_to_heads(x, 1, 2, comm)  # [2, seq_local*P, heads/P, 4]
+        self.assertEqual(list(y.shape), [2, seq_local * P, 2, 4])
+        for p in range(P):
+            src = (torch.arange(2 * seq_local * heads * 4, dtype=DT).reshape(2, seq_local, heads, 4) + 1000 * p).to(DEVICE)
+            self.assertTrue(torch.equal(y[:, p * seq_local:(p + 1) * seq_local], src[:, :, 2 * R:2 * R + 2]))
+        self.assertTrue(torch.equal(heads_to_sequence(y, 1, 2, comm), x))
+
+
+class TestFunctionalOps(unittest.TestCase):
+    def test_allreduce_mean_and_sgd_step(self):
+        x = torch.full((7,), float(R), dtype=DT, device=DEVICE)
+        self.assertTrue(torch.equal(ops.allreduce_mean(x, comm), torch.full_like(x, (P - 1) / 2)))
+        p = torch.ones(7, dtype=DT, device=DEVICE)
+        g = torch.full((7,), float(R + 1), dtype=DT, device=DEVICE)
+        ops.allreduce_sgd_step_(p, g, lr=0.5, comm=comm)
+        self.assertTrue(torch.allclose(p, torch.full_like(p, 1.0 - 0.5 * (P + 1) / 2)))
+
+    def test_allreduce_linear_matches_composition_and_grads(self):
+        torch.manual_seed(11)
+        w = (torch.randn(5, 4, dtype=DT) + R).to(DEVICE).requires_grad_()
+        x = torch.randn(6, 4, dtype=DT, generator=torch.Generator().manual_seed(R)).to(DEVICE).requires_grad_()
+        y = ops.allreduce_linear(x, w, comm)
+        w_avg = comm.Allreduce(w.detach(), m4t.MPI_SUM) / P
+        self.assertTrue(torch.allclose(y.detach(), x.detach() @ w_avg.t(), rtol=1e-12, atol=1e-12))
+        y.sum().backward()
+        self.assertTrue(torch.allclose(x.grad, w_avg.sum(dim=0).expand(6, 4), rtol=1e-12, atol=1e-12))
+        expect_gw = comm.Allreduce(x.detach().sum(dim=0), m4t.MPI_SUM) / P
+        self.assertTrue(torch.allclose(w.grad, expect_gw.expand(5, 4), rtol=1e-12, atol=1e-12))
+
+
+if __name__ == "__main__":
+    unittest.main()
