@@ -29,6 +29,7 @@ _SOURCES = [
     "runtime/world.cpp",
     "kernels/allreduce.cu",
     "kernels/slab.cu",
+    "kernels/slab_push.cu",
     "kernels/rooted.cu",
     "kernels/p2p.cu",
     "kernels/gemm_tcgen05.cu",

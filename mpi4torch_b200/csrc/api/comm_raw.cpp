@@ -147,7 +147,7 @@ Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scal
   return r.from_comm(out);
 }
 
-void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale) {
+void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale, int64_t max_blocks) {
   NvtxRange nvtx_range_("m4t::AllreduceAxpy");
   TORCH_CHECK(param.is_contiguous() && param.sizes() == grad.sizes() && param.scalar_type() == grad.scalar_type() &&
                   param.device() == grad.device(),
@@ -167,7 +167,22 @@ void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double
   } else {
     // out aliases accumulate: every element is read then written by the same thread
     epi.accumulate = param.data_ptr();
-    r.be->allreduce(gin.data_ptr(), param.data_ptr(), gin.numel(), dt, ReduceOp::SUM, epi, r.stream);
+    CudaBackend* cb = dynamic_cast<CudaBackend*>(r.be);
+    if (cb != nullptr && max_blocks > 0) {
+      // small-footprint launch (few CTAs) so the collective can run under a GEMM
+      // on another stream without evicting it; must be the same on every rank
+      const int saved = cb->tuning().ar_blocks;
+      cb->tuning().ar_blocks = static_cast<int>(max_blocks);
+      try {
+        r.be->allreduce(gin.data_ptr(), param.data_ptr(), gin.numel(), dt, ReduceOp::SUM, epi, r.stream);
+      } catch (...) {
+        cb->tuning().ar_blocks = saved;
+        throw;
+      }
+      cb->tuning().ar_blocks = saved;
+    } else {
+      r.be->allreduce(gin.data_ptr(), param.data_ptr(), gin.numel(), dt, ReduceOp::SUM, epi, r.stream);
+    }
   }
 }
 

@@ -47,7 +47,7 @@ struct Communicator : torch::CustomClassHolder {
   Tensor raw_allreduce(const Tensor& input, int64_t op, double scale, bool has_scale,
                        const c10::optional<Tensor>& accumulate);
   // param <- param + scale * Allreduce(grad, SUM), written in place (no autograd)
-  void raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale);
+  void raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double scale, int64_t max_blocks = 0);
   void raw_bcast_(Tensor& work, int64_t root);
   void raw_reduce_(Tensor& work, int64_t op, int64_t root);
   Tensor raw_gather(const Tensor& input, int64_t axis, int64_t root, bool all);

@@ -153,9 +153,9 @@ Tensor symmetric_empty(c10::IntArrayRef shape, c10::ScalarType dtype) {
 
 // param <- param + scale * Allreduce(grad): the gradient all-reduce with the
 // optimizer update as its epilogue, in place.
-void allreduce_axpy_(Tensor param, const Tensor& grad, double scale) {
+void allreduce_axpy_(Tensor param, const Tensor& grad, double scale, int64_t max_blocks) {
   auto comm = c10::make_intrusive<Communicator>();
-  comm->raw_allreduce_axpy_(param, grad, scale);
+  comm->raw_allreduce_axpy_(param, grad, scale, max_blocks);
 }
 
 }  // namespace
@@ -164,7 +164,7 @@ TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
   m.def("linear_mse_forward(Tensor x, Tensor w, Tensor target, float scale, float loss_scale, float grad_scale, "
         "bool allow_fused) -> (Tensor, Tensor, Tensor)",
         &linear_mse_forward);
-  m.def("allreduce_axpy_(Tensor(a!) param, Tensor grad, float scale) -> ()", &allreduce_axpy_);
+  m.def("allreduce_axpy_(Tensor(a!) param, Tensor grad, float scale, int max_blocks=0) -> ()", &allreduce_axpy_);
   m.def("symmetric_empty(int[] shape, ScalarType dtype) -> Tensor", &symmetric_empty);
   m.def("gemm_bf16_tn(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn);
   m.def("gemm_bf16_tn_2cta(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn_2cta);

@@ -57,6 +57,9 @@ void launch_stage_in(const DeviceComm& dc, const void* in, int64_t bytes, int sm
 // Barrier + strided box pulls from peers' staging (Gather/Allgather/Scatter/Alltoall).
 void launch_slab_pull(const DeviceComm& dc, const PullPlan& plan, const void* in, void* out, DType dt,
                       int blocks, cudaStream_t stream);
+// Experimental Allgather by multicast push (slab_push.cu); false = not eligible, nothing launched.
+bool launch_allgather_push(const DeviceComm& dc, const PullPlan& plan, const void* in, void* out, DType dt, int blocks,
+                           cudaStream_t stream);
 // Barrier + reduce-scatter box (Allgather adjoint) with fused epilogue.
 void launch_slab_reduce(const DeviceComm& dc, const ReducePlan& plan, const void* in, void* out, DType dt,
                         ReduceOp op, const Epilogue& epi, bool use_nvls, int blocks, cudaStream_t stream);

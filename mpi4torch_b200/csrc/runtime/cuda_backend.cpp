@@ -265,6 +265,12 @@ void CudaBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt
             "collective stages " << plan.max_stage_elems * es << " B per rank but the staging half is "
                                  << dc_.half_bytes << " B; raise M4T_STAGE_MB");
   chain(s);
+  // experimental (M4T_AG_PUSH=1): Allgather as an NVSwitch multicast push; the
+  // eligibility test only looks at rank-independent quantities
+  static const bool ag_push = env_i64("M4T_AG_PUSH", 0) != 0;
+  if (ag_push && plan.replicated_output &&
+      launch_allgather_push(dc_, plan, in, out, dt, grid_for(plan.max_out_elems, es, tune_.slab_blocks), s))
+    return;
   if (plan.stage_elems > 0) launch_stage_in(dc_, in, plan.stage_elems * es, dc_.sm_count, s);
   launch_slab_pull(dc_, plan, in, out, dt, grid_for(plan.max_out_elems, es, tune_.slab_blocks), s);
 }

@@ -86,6 +86,7 @@ PullPlan plan_gather(int rank, int size, int root, int64_t before, int64_t after
   }
   plan.out_elems = i_receive ? before * total * after : 0;
   plan.max_out_elems = before * total * after;
+  plan.replicated_output = all;
   if (i_receive) {
     for (int p = 0; p < size; ++p) {
       if (axis_len[p] == 0 || before == 0 || after == 0) continue;

@@ -33,6 +33,7 @@ struct PullPlan {
   int64_t out_elems = 0;      // elements of the local output
   int64_t max_stage_elems = 0;  // max over ranks of stage_elems (symmetric heap sizing)
   int64_t max_out_elems = 0;    // max over ranks of out_elems (rank-independent grid sizing)
+  bool replicated_output = false;  // every rank receives the identical gathered tensor (Allgather)
 };
 
 // out = reduce over all peers p of staged_p[box]; all peers share one box shape.

@@ -40,6 +40,7 @@ class DPLinearModel:
         self.fused = fused  # Allreduce->GEMM in one kernel when the NVLS path is up
         self.fast = fast    # fully fused training step (no autograd graph) when the inputs allow it
         self.overlap_slices = overlap_slices  # wgrad/allreduce pipelining granularity (fast path)
+        self.overlap_blocks = 32              # CTAs of the overlapped allreduce (small footprint under the GEMM)
         self._side = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -86,7 +87,8 @@ class DPLinearModel:
             ev.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev)
-                torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight[i * rows:(i + 1) * rows], gw_i, -self.lr / c.size)
+                torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight[i * rows:(i + 1) * rows], gw_i, -self.lr / c.size,
+                                                         self.overlap_blocks)
                 gw_i.record_stream(side)
         main.wait_stream(side)
         return loss[0]
