@@ -277,6 +277,21 @@ class MPI_Communicator:
         """Host barrier over all ranks (control plane only)."""
         self._comm.Barrier()
 
+    def Split(self, color: int, key: int) -> "MPI_Communicator":
+        """``MPI_Comm_split``: ranks passing the same ``color`` (>= 0) form a new
+        communicator, ranked by ``(key, old rank)``; a negative colour
+        (``MPI_UNDEFINED``) yields a communicator containing only this rank.
+        Collective over this communicator.  The sub-communicator has its own control segment,
+        symmetric heap and device counters, so its collectives never alias the
+        parent's (the reference obtains sub-communicators from mpi4py,
+        ``src/__init__.py:247-261``)."""
+        return MPI_Communicator(self._comm.Split(color, key))
+
+    @property
+    def is_world(self) -> bool:
+        """True for :data:`COMM_WORLD` (fused GEMM ops and pickling need it)."""
+        return self._comm.IsWorld()
+
     def describe(self) -> str:
         return self._comm.Describe()
 

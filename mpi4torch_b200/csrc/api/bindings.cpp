@@ -65,11 +65,16 @@ TORCH_LIBRARY(mpi4torch_b200, m) {
       .def("Isend", &Communicator::Isend)
       .def("Irecv", &Communicator::Irecv)
       .def("Wait", &Communicator::Wait)
+      .def("Split", &Communicator::Split)
+      .def("IsWorld", &Communicator::IsWorld)
       .def("Barrier", &Communicator::Barrier)
       .def("Describe", &Communicator::Describe)
       // Only the world communicator exists, so pickling round-trips it by name
       // (the reference's unpickle test is inverted and always throws, :1292-1294).
-      .def_pickle([](const c10::intrusive_ptr<Communicator>&) -> std::string { return "MPI_COMM_WORLD"; },
+      .def_pickle([](const c10::intrusive_ptr<Communicator>& self) -> std::string {
+                    TORCH_CHECK(self->IsWorld(), "mpi4torch_b200: only the world communicator can be pickled");
+                    return "MPI_COMM_WORLD";
+                  },
                   [](std::string state) -> c10::intrusive_ptr<Communicator> {
                     TORCH_CHECK(state == "MPI_COMM_WORLD", "mpi4torch_b200: unknown pickled communicator '", state, "'");
                     return comm_world();

@@ -6,6 +6,7 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#include <algorithm>
 #include <numeric>
 
 #include "../runtime/cuda_backend.h"
@@ -49,12 +50,12 @@ struct Route {
   c10::Device device;
   c10::optional<c10::cuda::CUDAGuard> guard;
 
-  Route(World& w, const Tensor& t) : device(t.device()) {
+  Route(World& w, CommContext& cx, const Tensor& t) : device(t.device()) {
     if (t.is_cpu()) {
-      be = &w.cpu();
+      be = &cx.cpu();
     } else if (t.is_cuda()) {
-      if (!w.host_staging() && w.cuda_ready()) {
-        CudaBackend* cb = w.cuda();
+      if (!w.host_staging() && cx.cuda_ready()) {
+        CudaBackend* cb = cx.cuda();
         TORCH_CHECK(t.device().index() == cb->device(), "mpi4torch_b200: tensor lives on cuda:",
                     static_cast<int>(t.device().index()), " but this rank's communicator is bound to cuda:", cb->device());
         guard.emplace(t.device());
@@ -62,7 +63,7 @@ struct Route {
         be = cb;
       } else {
         staged = true;
-        be = &w.cpu();
+        be = &cx.cpu();
       }
     } else {
       TORCH_CHECK(false, "mpi4torch_b200: unsupported device ", t.device());
@@ -103,21 +104,55 @@ uint32_t ptr_hash(const void* p) { return static_cast<uint32_t>(reinterpret_cast
 }  // namespace
 
 Communicator::Communicator() : world_(&World::instance()) {
-  rank_ = world_->rank();
-  size_ = world_->size();
+  ctx_ = world_->ctx().get();
+  rank_ = ctx_->rank();
+  size_ = ctx_->size();
+}
+
+Communicator::Communicator(std::shared_ptr<CommContext> owned) : world_(&World::instance()), owned_(std::move(owned)) {
+  ctx_ = owned_.get();
+  rank_ = ctx_->rank();
+  size_ = ctx_->size();
+}
+
+c10::intrusive_ptr<Communicator> Communicator::Split(int64_t color, int64_t key) {
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  // one metadata round: everybody learns everybody's (color, key)
+  int64_t mine[2] = {color, key};
+  std::vector<int64_t> all(static_cast<size_t>(size_) * 2);
+  ctx_->control().allgather_i64(mine, 2, all.data());
+  std::vector<std::pair<int64_t, int64_t>> members;  // (key, old rank)
+  // a negative colour (MPI_UNDEFINED) still takes part in the exchange and gets
+  // a communicator that contains only itself (MPI_COMM_SELF)
+  for (int64_t p = 0; p < size_; ++p)
+    if (color >= 0 ? all[p * 2] == color : p == rank_) members.emplace_back(all[p * 2 + 1], p);
+  std::sort(members.begin(), members.end());
+  int new_rank = -1;
+  for (size_t i = 0; i < members.size(); ++i)
+    if (members[i].second == rank_) new_rank = static_cast<int>(i);
+  const uint64_t split_id = ctx_->next_split_id();  // identical on all ranks: Split is collective
+  const std::string job = ctx_->job_id() + "_s" + std::to_string(split_id) +
+                          (color >= 0 ? "c" + std::to_string(color) : "r" + std::to_string(rank_));
+  auto child = std::make_shared<CommContext>(new_rank, static_cast<int>(members.size()), job);
+  if (ctx_->cuda_ready()) {
+    // same device, smaller arenas than the world communicator's
+    child->init_cuda(ctx_->cuda()->device(), env_i64("M4T_SUB_STAGE_MB", 256), env_i64("M4T_SUB_SYMM_MB", 0));
+  }
+  world_->register_child(child);
+  return c10::make_intrusive<Communicator>(std::move(child));
 }
 
 c10::intrusive_ptr<Communicator> comm_world() { return c10::make_intrusive<Communicator>(); }
 
 void Communicator::Barrier() {
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  world_->control().barrier();
+  ctx_->control().barrier();
 }
 
 std::string Communicator::Describe() const {
   std::ostringstream o;
-  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << world_->job_id() << " | cpu: posix-shm";
-  if (world_->cuda_ready()) o << " | " << world_->cuda()->describe();
+  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << ctx_->job_id() << " | cpu: posix-shm";
+  if (ctx_->cuda_ready()) o << " | " << ctx_->cuda()->describe();
   if (world_->host_staging()) o << " | host staging forced";
   return o.str();
 }
@@ -129,7 +164,7 @@ Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scal
   const DType dt = to_dtype(input.scalar_type());
   check_op_dtype(op, dt);
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   Tensor in = r.to_comm(input);
   Tensor acc;
   Epilogue epi;
@@ -154,7 +189,7 @@ void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double
               "mpi4torch_b200: allreduce_axpy_ needs a contiguous parameter and a gradient of the same shape/dtype/device");
   const DType dt = to_dtype(param.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, param);
+  Route r(*world_, *ctx_, param);
   Tensor gin = r.to_comm(grad);
   Epilogue epi;
   epi.scale = scale;
@@ -191,7 +226,7 @@ void Communicator::raw_bcast_(Tensor& work, int64_t root) {
   TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Bcast_ root ", root, " out of range");
   const DType dt = to_dtype(work.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, work);
+  Route r(*world_, *ctx_, work);
   if (r.staged) {
     Tensor h = work.cpu();
     r.be->bcast(h.data_ptr(), h.numel(), dt, static_cast<int>(root), nullptr);
@@ -208,7 +243,7 @@ void Communicator::raw_reduce_(Tensor& work, int64_t op_, int64_t root) {
   const DType dt = to_dtype(work.scalar_type());
   check_op_dtype(op, dt);
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, work);
+  Route r(*world_, *ctx_, work);
   if (r.staged) {
     Tensor h = work.cpu();
     r.be->reduce(h.data_ptr(), h.numel(), dt, op, static_cast<int>(root), nullptr);
@@ -224,14 +259,14 @@ Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root
   const DType dt = to_dtype(input.scalar_type());
   const int64_t axis = wrap_axis(axis_, input.dim(), all ? "Allgather" : "Gather");
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   Tensor in = r.to_comm(input);
   const auto shape = in.sizes().vec();
   const Axis3 a3 = split_axis(shape, axis);
   // one metadata round: [axis length, before, after]
   int64_t mine[3] = {a3.axis, a3.before, a3.after};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
-  world_->control().allgather_i64(mine, 3, allmeta.data());
+  ctx_->control().allgather_i64(mine, 3, allmeta.data());
   std::vector<int64_t> lens(static_cast<size_t>(size_));
   for (int64_t p = 0; p < size_; ++p) {
     lens[p] = allmeta[p * 3];
@@ -256,7 +291,7 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
   TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Scatter numelem must be non-negative");
   const DType dt = to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   Tensor in = r.to_comm(input);
   // one metadata round: [numelem, ndim, sizes...]; only root's shape matters
   // (off-root tensors are placeholders, reference :786-796).
@@ -267,7 +302,7 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
   mine[1] = nd;
   for (int64_t i = 0; i < nd; ++i) mine[2 + i] = in.size(i);
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * kMetaWords);
-  world_->control().allgather_i64(mine.data(), kMetaWords, allmeta.data());
+  ctx_->control().allgather_i64(mine.data(), kMetaWords, allmeta.data());
   const int64_t* rootmeta = allmeta.data() + root * kMetaWords;
   const int64_t rnd = rootmeta[1];
   std::vector<int64_t> rshape(rootmeta + 2, rootmeta + 2 + rnd);
@@ -301,12 +336,12 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
   const int64_t gaxis = wrap_axis(gatheraxis_, nd, "Alltoall");
   const int64_t saxis = wrap_axis(scatteraxis_, nd, "Alltoall");
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   Tensor in = r.to_comm(input);
   const auto shape = in.sizes().vec();
   int64_t mine[2] = {numelem, shape[gaxis]};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 2);
-  world_->control().allgather_i64(mine, 2, allmeta.data());
+  ctx_->control().allgather_i64(mine, 2, allmeta.data());
   std::vector<int64_t> counts(static_cast<size_t>(size_)), glen(static_cast<size_t>(size_));
   for (int64_t p = 0; p < size_; ++p) {
     counts[p] = allmeta[p * 2];
@@ -340,13 +375,13 @@ Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_
   check_op_dtype(op, dt);
   const int64_t axis = wrap_axis(axis_, input.dim(), "Reduce_scatter");
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   Tensor in = r.to_comm(input);
   const auto shape = in.sizes().vec();
   const Axis3 a3 = split_axis(shape, axis);
   int64_t mine[3] = {numelem, a3.before * a3.after, a3.axis};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
-  world_->control().allgather_i64(mine, 3, allmeta.data());
+  ctx_->control().allgather_i64(mine, 3, allmeta.data());
   std::vector<int64_t> counts(static_cast<size_t>(size_));
   int64_t total = 0;
   for (int64_t p = 0; p < size_; ++p) {
@@ -392,7 +427,7 @@ std::vector<Tensor> Communicator::raw_isend(const Tensor& input, int64_t dest, i
   TORCH_CHECK(dest >= 0 && dest < size_, "mpi4torch_b200: Isend destination ", dest, " out of range");
   to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   Tensor buf = r.to_comm(input);
   if (buf.is_same(input)) buf = input.detach();  // own TensorImpl: the handle is an autograd output
   const int64_t req = r.be->isend(buf.data_ptr(), static_cast<int64_t>(buf.nbytes()), static_cast<int>(dest), tag, r.stream);
@@ -404,7 +439,7 @@ std::vector<Tensor> Communicator::raw_irecv(const Tensor& input, int64_t source,
   TORCH_CHECK(source >= 0 && source < size_, "mpi4torch_b200: Irecv source ", source, " out of range");
   to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, input);
+  Route r(*world_, *ctx_, input);
   // A non-contiguous (or host-staged) receive lands in a fresh buffer; callers
   // must use Wait's return value (same contract as the reference, :1256-1259).
   Tensor buf;
@@ -437,12 +472,12 @@ Tensor Communicator::raw_wait(const std::vector<Tensor>& handle) {
   void* stream = nullptr;
   c10::optional<c10::cuda::CUDAGuard> guard;
   if (buf.is_cuda()) {
-    TORCH_CHECK(world_->cuda_ready(), "mpi4torch_b200: CUDA wait handle without a CUDA backend");
+    TORCH_CHECK(ctx_->cuda_ready(), "mpi4torch_b200: CUDA wait handle without a CUDA backend");
     guard.emplace(buf.device());
     stream = c10::cuda::getCurrentCUDAStream(buf.device().index()).stream();
-    be = world_->cuda();
+    be = ctx_->cuda();
   } else {
-    be = &world_->cpu();
+    be = &ctx_->cpu();
   }
   be->wait(req, stream);
   if (kind == 0) return handle[2];

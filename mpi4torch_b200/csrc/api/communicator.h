@@ -14,7 +14,9 @@ namespace m4t {
 using torch::Tensor;
 
 struct Communicator : torch::CustomClassHolder {
-  Communicator();
+  Communicator();  // the world communicator
+  // a communicator over an existing context (created by Split)
+  explicit Communicator(std::shared_ptr<CommContext> owned);
 
   // rank/size are cached at construction (the reference re-queries MPI on every
   // access, csrc/extension.cpp:175-187).
@@ -40,6 +42,12 @@ struct Communicator : torch::CustomClassHolder {
   Tensor Wait(const std::vector<Tensor>& handle);
 
   // ---- utilities --------------------------------------------------------------
+  // MPI_Comm_split: ranks passing the same `color` (>= 0) form a new communicator,
+  // ordered by (`key`, old rank); a negative colour yields a self-only communicator.
+  // Collective over this communicator.  (The
+  // reference gets sub-communicators from mpi4py, src/__init__.py:247-261.)
+  c10::intrusive_ptr<Communicator> Split(int64_t color, int64_t key);
+  bool IsWorld() const { return owned_ == nullptr; }
   void Barrier();
   std::string Describe() const;
 
@@ -59,9 +67,12 @@ struct Communicator : torch::CustomClassHolder {
   Tensor raw_wait(const std::vector<Tensor>& handle);
 
   World& world() const { return *world_; }
+  CommContext& context() const { return *ctx_; }
 
  private:
   World* world_;
+  CommContext* ctx_;                        // world context (owned by World) or owned_.get()
+  std::shared_ptr<CommContext> owned_;      // non-null for communicators created by Split
   int64_t rank_, size_;
 };
 

@@ -20,7 +20,7 @@ constexpr int64_t kP2pRingOff = 1 << 20;
 constexpr int kMaxSlots = 64;
 }  // namespace
 
-CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) {
+CudaBackend::CudaBackend(Control& ctl, int device, int64_t stage_mb, int64_t symm_mb) : ctl_(ctl), device_(device) {
   const int P = ctl.size();
   M4T_CHECK(P <= kMaxGpuPeers, "the NVLink backend supports up to " << kMaxGpuPeers << " ranks (got " << P << ")");
   M4T_CUDA(cudaSetDevice(device_));
@@ -41,9 +41,9 @@ CudaBackend::CudaBackend(Control& ctl, int device) : ctl_(ctl), device_(device) 
   p2p_off_ = kP2pRingOff;
   const int64_t p2p_bytes = static_cast<int64_t>(P) * nslots_ * slot_bytes_;
   const int64_t stage_off = round_up64(p2p_off_ + p2p_bytes, 2 << 20);
-  const int64_t half = P > 1 ? round_up64(env_i64("M4T_STAGE_MB", 2176) << 20, 2 << 20) : 0;
+  const int64_t half = P > 1 ? round_up64((stage_mb >= 0 ? stage_mb : env_i64("M4T_STAGE_MB", 2176)) << 20, 2 << 20) : 0;
   symm_off_ = stage_off + 2 * half;
-  symm_bytes_ = P > 1 ? round_up64(env_i64("M4T_SYMM_MB", 512) << 20, 2 << 20) : 0;
+  symm_bytes_ = P > 1 ? round_up64((symm_mb >= 0 ? symm_mb : env_i64("M4T_SYMM_MB", 512)) << 20, 2 << 20) : 0;
   symm_cursor_ = 0;
   heap_ = std::make_unique<SymmHeap>(ctl_, device_, static_cast<size_t>(symm_off_ + symm_bytes_));
 

@@ -31,7 +31,8 @@ struct CudaTuning {
 
 class CudaBackend final : public Backend {
  public:
-  CudaBackend(Control& ctl, int device);
+  // stage_mb / symm_mb < 0: take M4T_STAGE_MB / M4T_SYMM_MB (sub-communicators pass smaller arenas)
+  CudaBackend(Control& ctl, int device, int64_t stage_mb = -1, int64_t symm_mb = -1);
   ~CudaBackend() override;
 
   const char* name() const override { return "cuda-nvlink"; }

@@ -9,16 +9,33 @@ World* g_world = nullptr;
 std::mutex g_world_mu;
 }  // namespace
 
-World::World() {
-  env_ = world_env_from_environment();
-  ctl_ = std::make_unique<Control>(env_.rank, env_.size, env_.job_id);
+CommContext::CommContext(int rank, int size, const std::string& job_id) : job_id_(job_id) {
+  ctl_ = std::make_unique<Control>(rank, size, job_id);
   cpu_ = std::make_unique<CpuBackend>(*ctl_);
 }
 
-World::~World() {
+CommContext::~CommContext() {
   cuda_.reset();
   cpu_.reset();
   ctl_.reset();
+}
+
+void CommContext::init_cuda(int device, int64_t stage_mb, int64_t symm_mb) {
+  if (cuda_) return;
+  cuda_ = std::make_unique<CudaBackend>(*ctl_, device, stage_mb, symm_mb);
+}
+
+void CommContext::shutdown_cuda() { cuda_.reset(); }
+
+World::World() {
+  env_ = world_env_from_environment();
+  ctx_ = std::make_shared<CommContext>(env_.rank, env_.size, env_.job_id);
+}
+
+World::~World() {
+  for (auto& w : children_)
+    if (auto c = w.lock()) c->shutdown_cuda();
+  ctx_.reset();
 }
 
 World& World::instance() {
@@ -42,8 +59,7 @@ void World::finalize() {
 
 void World::init_cuda(int device) {
   std::lock_guard<std::recursive_mutex> g(mu_);
-  if (cuda_) return;
-  cuda_ = std::make_unique<CudaBackend>(*ctl_, device);
+  ctx_->init_cuda(device);
 }
 
 }  // namespace m4t

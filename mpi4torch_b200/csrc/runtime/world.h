@@ -5,6 +5,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "backend.h"
 #include "control.h"
@@ -13,6 +14,36 @@
 namespace m4t {
 
 class CudaBackend;
+
+// Everything one communicator needs: its own control segment (barriers,
+// metadata exchange, p2p descriptor rings), CPU backend and - when CUDA is up -
+// its own symmetric heap + device counters.  COMM_WORLD's context is created
+// from the launcher environment; Split() creates further contexts over a subset
+// of ranks (the reference obtains such communicators through mpi4py,
+// src/__init__.py:247-261).
+class CommContext {
+ public:
+  CommContext(int rank, int size, const std::string& job_id);
+  ~CommContext();
+  int rank() const { return ctl_->rank(); }
+  int size() const { return ctl_->size(); }
+  const std::string& job_id() const { return job_id_; }
+  Control& control() { return *ctl_; }
+  CpuBackend& cpu() { return *cpu_; }
+  // Collective over the context's ranks.  stage_mb / symm_mb < 0 = environment defaults.
+  void init_cuda(int device, int64_t stage_mb = -1, int64_t symm_mb = -1);
+  void shutdown_cuda();
+  bool cuda_ready() const { return cuda_ != nullptr; }
+  CudaBackend* cuda() { return cuda_.get(); }
+  uint64_t next_split_id() { return ++split_seq_; }
+
+ private:
+  std::string job_id_;
+  std::unique_ptr<Control> ctl_;
+  std::unique_ptr<CpuBackend> cpu_;
+  std::unique_ptr<CudaBackend> cuda_;
+  uint64_t split_seq_ = 0;
+};
 
 class World {
  public:
@@ -27,14 +58,18 @@ class World {
   int local_rank() const { return env_.local_rank; }
   const std::string& job_id() const { return env_.job_id; }
 
-  Control& control() { return *ctl_; }
-  CpuBackend& cpu() { return *cpu_; }
+  // the world communicator's context
+  const std::shared_ptr<CommContext>& ctx() { return ctx_; }
+  Control& control() { return ctx_->control(); }
+  CpuBackend& cpu() { return ctx_->cpu(); }
 
   // Collective: every rank must call it (done eagerly at import when CUDA is
   // visible, or explicitly via init_cuda()).  Idempotent.
   void init_cuda(int device);
-  bool cuda_ready() const { return cuda_ != nullptr; }
-  CudaBackend* cuda() { return cuda_.get(); }
+  bool cuda_ready() const { return ctx_->cuda_ready(); }
+  CudaBackend* cuda() { return ctx_->cuda(); }
+  // sub-communicator contexts are torn down before the world at exit
+  void register_child(const std::shared_ptr<CommContext>& c) { children_.push_back(c); }
 
   // Runtime toggle mirroring deactivate_cuda_aware_mpi_support() (reference
   // csrc/extension.cpp:54-59): CUDA tensors are staged through host memory and
@@ -50,9 +85,8 @@ class World {
   World();
   ~World();
   WorldEnv env_;
-  std::unique_ptr<Control> ctl_;
-  std::unique_ptr<CpuBackend> cpu_;
-  std::unique_ptr<CudaBackend> cuda_;
+  std::shared_ptr<CommContext> ctx_;
+  std::vector<std::weak_ptr<CommContext>> children_;
   bool host_staging_ = false;
   std::recursive_mutex mu_;
 };

@@ -27,7 +27,8 @@ class DPLinearModel:
         g = torch.Generator().manual_seed(seed)  # identical initial weights on every rank
         w = torch.randn(out_features, in_features, generator=g) * (in_features ** -0.5)
         dev = torch.device(device)
-        if (dev.type == "cuda" and dtype == torch.bfloat16 and self.comm.size > 1 and m4t.cuda_backend_ready()
+        if (dev.type == "cuda" and dtype == torch.bfloat16 and self.comm.size > 1 and self.comm.is_world
+                and m4t.cuda_backend_ready()
                 and hasattr(torch.ops.mpi4torch_b200, "symmetric_empty")):
             # keep the parameter in the symmetric heap: the fused Allreduce->GEMM
             # kernel (and the NVSwitch) then read it in place, no staging copy
@@ -52,7 +53,7 @@ class DPLinearModel:
         return self.comm.Allreduce(local, m4t.MPI_SUM)
 
     def _fast_path_ok(self, x: torch.Tensor, target: torch.Tensor) -> bool:
-        return (self.fast and x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and target.dtype == torch.bfloat16
+        return (self.fast and self.comm.is_world and x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and target.dtype == torch.bfloat16
                 and self.weight.dtype == torch.bfloat16 and x.stride(1) == 1 and target.stride(1) == 1
                 and m4t.cuda_backend_ready() and hasattr(torch.ops.mpi4torch_b200, "linear_mse_forward")
                 and torch.ops.mpi4torch_b200.gemm_bf16_tn_supported(x, self.weight))

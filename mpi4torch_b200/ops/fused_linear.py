@@ -46,7 +46,7 @@ class _AllreduceLinearFused(torch.autograd.Function):
 def allreduce_linear(x: torch.Tensor, weight: torch.Tensor, comm=None, *, force_unfused: bool = False) -> torch.Tensor:
     """``x @ (Allreduce(weight, SUM) / size)^T`` (differentiable w.r.t. both)."""
     c = m4t.COMM_WORLD if comm is None else comm
-    fused_ok = (not force_unfused and has_fused_kernel() and x.is_cuda and weight.is_cuda and c.size > 1
+    fused_ok = (not force_unfused and has_fused_kernel() and c.is_world and x.is_cuda and weight.is_cuda and c.size > 1
                 and m4t.cuda_backend_ready() and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
                 and torch.ops.mpi4torch_b200.allreduce_linear_supported(x, weight))
     if fused_ok:
