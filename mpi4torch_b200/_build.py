@@ -34,6 +34,7 @@ _SOURCES = [
     "kernels/p2p.cu",
     "kernels/gemm_tcgen05.cu",
     "kernels/gemm_tcgen05_2cta.cu",
+    "kernels/wgrad_tcgen05_2cta.cu",
     "api/comm_raw.cpp",
     "api/autograd_ops.cpp",
     "api/fused_ops.cpp",

@@ -158,9 +158,55 @@ void allreduce_axpy_(Tensor param, const Tensor& grad, double scale, int64_t max
   comm->raw_allreduce_axpy_(param, grad, scale, max_blocks);
 }
 
+// G = dy^T @ x on the tcgen05 path with MN-major operands (no transposed copies).  Experimental.
+Tensor wgrad_bf16(const Tensor& dy, const Tensor& x) {
+  check_2d_bf16(dy, "dy");
+  check_2d_bf16(x, "x");
+  TORCH_CHECK(dy.size(0) == x.size(0), "mpi4torch_b200: batch dimensions differ");
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor gw = at::empty({dy.size(1), x.size(1)}, x.options());
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  launch_wgrad_bf16(dy.data_ptr(), x.data_ptr(), gw.data_ptr(), dy.size(0), dy.size(1), x.size(1), dy.stride(0),
+                    x.stride(0), gw.stride(0), backend().device_comm().sm_count,
+                    c10::cuda::getCurrentCUDAStream(x.device().index()).stream());
+  return gw;
+}
+
+bool wgrad_bf16_ok(const Tensor& dy, const Tensor& x) {
+  if (!(dy.is_cuda() && x.is_cuda() && dy.dim() == 2 && x.dim() == 2 && dy.scalar_type() == at::kBFloat16 &&
+        x.scalar_type() == at::kBFloat16 && dy.stride(1) == 1 && x.stride(1) == 1 && dy.size(0) == x.size(0)))
+    return false;
+  return World::instance().cuda_ready() &&
+         wgrad_bf16_supported(dy.size(0), dy.size(1), x.size(1), dy.data_ptr(), x.data_ptr(), x.data_ptr(), dy.stride(0),
+                              x.stride(0), x.size(1));
+}
+
+bool wgrad_allreduce_sgd_supported(const Tensor& w, const Tensor& dy, const Tensor& x) {
+  if (!World::instance().cuda_ready() || !wgrad_bf16_ok(dy, x)) return false;
+  if (!(w.is_cuda() && w.dim() == 2 && w.scalar_type() == at::kBFloat16 && w.is_contiguous() &&
+        w.size(0) == dy.size(1) && w.size(1) == x.size(1)))
+    return false;
+  return backend().fused_wgrad_available(w.data_ptr(), dy.size(0), w.size(0), w.size(1));
+}
+
+// w += scale * sum_ranks(dy^T @ x): backward GEMM, gradient all-reduce and SGD step in one kernel.
+// Collective; `w` must be a replicated symmetric_empty() tensor.  Experimental (M4T_FUSED_WGRAD=1).
+void wgrad_allreduce_sgd_(Tensor w, const Tensor& dy, const Tensor& x, double scale) {
+  TORCH_CHECK(wgrad_allreduce_sgd_supported(w, dy, x), "mpi4torch_b200: fused wgrad->Allreduce->SGD does not support these tensors");
+  c10::cuda::CUDAGuard guard(x.device());
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  backend().fused_wgrad_update(w.data_ptr(), dy.data_ptr(), x.data_ptr(), dy.size(0), w.size(0), w.size(1), dy.stride(0),
+                               x.stride(0), static_cast<float>(scale),
+                               c10::cuda::getCurrentCUDAStream(x.device().index()).stream());
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
+  m.def("wgrad_bf16(Tensor dy, Tensor x) -> Tensor", &wgrad_bf16);
+  m.def("wgrad_bf16_supported(Tensor dy, Tensor x) -> bool", &wgrad_bf16_ok);
+  m.def("wgrad_allreduce_sgd_supported(Tensor w, Tensor dy, Tensor x) -> bool", &wgrad_allreduce_sgd_supported);
+  m.def("wgrad_allreduce_sgd_(Tensor(a!) w, Tensor dy, Tensor x, float scale) -> ()", &wgrad_allreduce_sgd_);
   m.def("linear_mse_forward(Tensor x, Tensor w, Tensor target, float scale, float loss_scale, float grad_scale, "
         "bool allow_fused) -> (Tensor, Tensor, Tensor)",
         &linear_mse_forward);

@@ -115,6 +115,22 @@ void launch_fused_allreduce_gemm_2cta(const DeviceComm& dc, const void* x, void*
                                       uint32_t panel_target, float scale, cudaStream_t stream,
                                       const MseEpilogue* mse = nullptr);
 int fused_gemm_grid(const DeviceComm& dc);
+
+// ---- weight gradient (wgrad_tcgen05_2cta.cu), experimental -------------------------
+// G[N,K] = dY[Mb,N]^T * X[Mb,K]: both operands MN-major, no transposed copies.
+bool wgrad_bf16_supported(int64_t Mb, int64_t N, int64_t K, const void* dy, const void* x, const void* g, int64_t ldy,
+                          int64_t ldx, int64_t ldg);
+void launch_wgrad_bf16(const void* dy, const void* x, void* g, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
+                       int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream);
+// wgrad GEMM -> reduce-scatter through the switch -> W += scale * sum -> multicast of the new
+// weights, ONE kernel.  W (bf16 [N,K] contiguous) lives at heap offset w_off on every rank and
+// must be replicated (identical on all ranks), as it is under data-parallel SGD.
+int64_t fused_wgrad_tiles(int64_t N, int64_t K);
+int fused_wgrad_signals_per_tile(int ksplit);
+void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
+                               int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
+                               int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
+                               uint32_t done_target, float scale, cudaStream_t stream);
 // Plain device copy into the heap (used to stage the weight for the fused kernel).
 void launch_copy_bytes(void* dst, const void* src, int64_t bytes, int sm_count, cudaStream_t stream);
 

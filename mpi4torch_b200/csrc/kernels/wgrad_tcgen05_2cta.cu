@@ -1,0 +1,463 @@
+// Weight-gradient GEMM on CTA pairs, optionally fused with the gradient
+// all-reduce and the SGD update (EXPERIMENTAL: compiled and SASS-checked, not
+// yet run on hardware - enabled only by M4T_FUSED_WGRAD=1 / the explicit ops).
+//
+//   G[N,K] = dY[Mb,N]^T * X[Mb,K]          (bf16 in, fp32 accumulate in TMEM)
+//
+// The contraction runs over the batch dimension Mb, which is the STRIDED
+// dimension of both row-major operands, so both UMMA operands are MN-major:
+// TMA boxes are {64 contiguous elements (128 B swizzle span), BK batch rows} and
+// the shared-memory descriptors use the MN-major SWIZZLE_128B canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (LBO = one 64-wide chunk =
+// BK*128 B, SBO = one 8-row swizzle atom = 1024 B); instruction-descriptor bits
+// 15/16 select MN-major A and B.  No transposed copy of dY or X is ever made.
+//
+// Fused mode (the backward of the data-parallel linear layer, where the
+// reference does wgrad GEMM -> MPI_Allreduce -> optimizer step as three passes
+// over the gradient, csrc/extension.cpp:197-260 + the example's SGD loop):
+//   * the batch contraction is split in `ksplit` halves so that 2*tiles work
+//     units fill the 74 CTA pairs evenly (256 tiles alone would leave the last
+//     wave 46 % empty);
+//   * the epilogue writes each partial tile as bf16 into this rank's symmetric
+//     staging buffer and bumps the tile's counter ON THE OWNER rank (tile t is
+//     owned by rank t % P) with a release-scoped remote red;
+//   * four communication warps per CTA wait for owned tiles to be complete on
+//     all ranks, pull the sum through the NVSwitch (multimem.ld_reduce), apply
+//     W -= lr/P * sum in fp32 and multicast the new bf16 weights into every
+//     rank's copy (multimem.st) - reduce-scatter + update + all-gather, hidden
+//     under the GEMM of later tiles;
+//   * a multicast "done" counter makes kernel completion imply that every
+//     rank's weights are final.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "kernels.h"
+#include "tcgen05_ptx.cuh"
+#include "vec_ops.cuh"
+
+namespace m4t {
+
+namespace {
+
+constexpr int BMC = 128;        // rows of G (columns of dY) per CTA
+constexpr int BM2 = 2 * BMC;    // cluster tile rows (n)
+constexpr int BN = 256;         // cluster tile cols (k)
+constexpr int BNH = BN / 2;     // X columns staged per CTA
+constexpr int BK = 64;          // batch rows per pipeline stage
+constexpr int UMMA_K = 16;
+constexpr int kChunk = 64;      // elements per 128-byte swizzle span
+constexpr int kStages = 6;
+constexpr int kAccStages = 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kBoxBytes = kChunk * BK * 2;          // 8 KiB: one TMA box
+constexpr int kABytes = (BMC / kChunk) * kBoxBytes;  // 16 KiB
+constexpr int kBBytes = (BNH / kChunk) * kBoxBytes;  // 16 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kWarps = 6;
+constexpr int kCommWarps = 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kSignalsPerUnit = 8;  // 4 epilogue warps x 2 CTAs arrive on the tile counter
+
+struct WgradArgs {
+  void* out;            // plain: G [N, K]; fused: this rank's staging buffer(s)
+  int64_t out_split_stride;  // bytes between the ksplit partial buffers
+  int Mb, N, K;
+  int ldo;              // leading dimension of out (elements)
+  int ksplit;
+};
+
+struct WgradComm {
+  SyncCtx sync;
+  char* heap[kMaxGpuPeers];
+  char* mc_heap;
+  int64_t stage_off;     // partial-gradient staging (same offset on every rank)
+  int64_t stage_stride;  // bytes between the ksplit partial buffers
+  int64_t w_off;         // bf16 weights [N, K] (contiguous) inside every rank's heap
+  int64_t cnt_off;       // u32 tile counters [tiles]
+  int64_t done_off;      // u32 completion counter
+  uint32_t tile_target;
+  uint32_t done_target;
+  float scale;           // W += scale * sum_ranks G   (scale = -lr / P)
+};
+
+struct __align__(8) Bars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  return static_cast<uint32_t>(float_to_bf16_bits(lo)) | (static_cast<uint32_t>(float_to_bf16_bits(hi)) << 16);
+}
+
+// MN-major operand tile stored by TMA with SWIZZLE_128B as [chunk][BK rows][128 B].
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>(kBoxBytes >> 4) << 16;  // LBO: next 64-element chunk along M/N
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;      // SBO: next 8 rows along K
+  d |= static_cast<uint64_t>(1u) << 46;              // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2u) << 61;              // SWIZZLE_128B
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32_mn(uint32_t umma_m, uint32_t umma_n) {
+  return tc::make_idesc_bf16_f32(umma_m, umma_n) | (1u << 15) | (1u << 16);  // A and B MN-major
+}
+
+__device__ __forceinline__ void bounded_wait_ge(const uint32_t* flag, uint32_t target, const SyncCtx& c) {
+  if (static_cast<int32_t>(ld_acquire_sys_u32(flag) - target) >= 0) return;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned int spins = 0;
+  while (static_cast<int32_t>(ld_acquire_sys_u32(flag) - target) < 0) {
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > c.timeout_ns) {
+      *reinterpret_cast<volatile int*>(c.err_flag) = kErrTimeout;
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+// Owner side of the fused mode; runs on kCommWarps warps of every CTA.
+__device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int first_thread, int cluster_id,
+                                                   int num_clusters, uint32_t cta, int num_tiles, int k_tiles, int K,
+                                                   int ksplit) {
+  const SyncCtx& c = wc.sync;
+  const int P = c.size, r = c.rank;
+  const int ct = threadIdx.x - first_thread;
+  const int lane = ct & 31;
+  const int cw = ct >> 5;
+  constexpr int kCommThreads = kCommWarps * 32;
+  constexpr int kU = 4;  // rows in flight per warp (independent switch round trips)
+  const uint32_t* my_cnt = reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.cnt_off);
+  const int64_t row_bytes = static_cast<int64_t>(K) * 2;
+  // j-th owned tile (t = r + j*P) is served by cluster j % num_clusters: owned tiles finish in
+  // GEMM order, so consecutive ones land on different CTA pairs and their round trips overlap.
+  for (int j = cluster_id; r + j * P < num_tiles; j += num_clusters) {
+    const int t = r + j * P;
+    if (lane == 0) bounded_wait_ge(my_cnt + t, wc.tile_target, c);
+    __syncwarp();
+    const int n_blk = t / k_tiles;
+    const int k_blk = t - n_blk * k_tiles;
+    // this CTA's half of the tile: 128 rows x 512 bytes, one row per warp pass
+    const int64_t tile_off = (static_cast<int64_t>(n_blk) * BM2 + static_cast<int64_t>(cta) * BMC) * row_bytes +
+                             static_cast<int64_t>(k_blk) * BN * 2 + lane * 16;
+    for (int row0 = cw; row0 < BMC; row0 += kCommWarps * kU) {
+      Vec16 s0[kU], s1[kU], w[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int row = row0 + u * kCommWarps;
+        if (row < BMC) {
+          const int64_t off = tile_off + row * row_bytes;
+          s0[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
+          if (ksplit > 1) s1[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
+          w[u] = ld_vec(wc.heap[r] + wc.w_off + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int row = row0 + u * kCommWarps;
+        if (row < BMC) {
+          const int64_t off = tile_off + row * row_bytes;
+          float a[8], b[8], wv[8];
+          VecOf<DType::BF16>::unpack(s0[u], a);
+          VecOf<DType::BF16>::unpack(w[u], wv);
+          if (ksplit > 1) {
+            VecOf<DType::BF16>::unpack(s1[u], b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] += b[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) wv[e] = fmaf(wc.scale, a[e], wv[e]);
+          multimem_st_vec(wc.mc_heap + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
+        }
+      }
+    }
+  }
+  // completion: every CTA of every rank reports once; leaving the kernel means all weights are final
+  asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
+  if (ct == 0) {
+    __threadfence_system();
+    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(wc.mc_heap + wc.done_off), "r"(1u) : "memory");
+    bounded_wait_ge(reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.done_off), wc.done_target, c);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
+}
+
+template <bool FUSED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kWarps + (FUSED ? kCommWarps : 0)) * 32, 1)
+wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          const WgradArgs g, const WgradComm wc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars* bars = reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = tc::cluster_ctarank();
+  const bool leader = cta == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int n_tiles = g.N / BM2;  // tiles along the rows of G
+  const int k_tiles = g.K / BN;   // tiles along the columns of G
+  const int num_tiles = n_tiles * k_tiles;
+  const int num_units = num_tiles * g.ksplit;
+  const int kb_per_unit = g.Mb / BK / g.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&bars->full[s], 1);
+      tc::mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      tc::mbar_init(&bars->tmem_full[a], 1);
+      tc::mbar_init(&bars->tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs (collected by the leader)
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc_2sm<kTmemCols>(&bars->tmem_base);
+  tc::tcgen05_fence_before();
+  tc::cluster_sync();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const int t = u / g.ksplit;
+        const int h = u - t * g.ksplit;
+        const int n_blk = t / k_tiles;
+        const int k_blk = t - n_blk * k_tiles;
+        const int n0 = n_blk * BM2 + static_cast<int>(cta) * BMC;  // column of dY
+        const int k0 = k_blk * BN + static_cast<int>(cta) * BNH;   // column of X
+        for (int kb = 0; kb < kb_per_unit; ++kb) {
+          const int mb0 = (h * kb_per_unit + kb) * BK;
+          tc::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          if (leader) tc::mbar_arrive_expect_tx(&bars->full[stage], 2 * kStageBytes);
+#pragma unroll
+          for (int ch = 0; ch < BMC / kChunk; ++ch)
+            tc::tma_load_2d_2sm(sa + ch * kBoxBytes, &tmap_a, &bars->full[stage], n0 + ch * kChunk, mb0);
+#pragma unroll
+          for (int ch = 0; ch < BNH / kChunk; ++ch)
+            tc::tma_load_2d_2sm(sb + ch * kBoxBytes, &tmap_b, &bars->full[stage], k0 + ch * kChunk, mb0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32_mn(BM2, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc::tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kb_per_unit; ++kb) {
+          tc::mbar_wait(&bars->full[stage], phase);
+          tc::tcgen05_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t adesc = make_smem_desc_mn_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_mn_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // 16 batch rows = two 8-row swizzle atoms = 2048 bytes further into every chunk
+            const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 128) >> 4);
+            tc::umma_bf16_ss_2sm(tmem_d, adesc + koff, bdesc + koff, idesc, (kb | k) ? 1u : 0u);
+          }
+          tc::umma_commit_2sm(&bars->empty[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::umma_commit_2sm(&bars->tmem_full[acc]);
+      }
+    }
+  } else if (warp < kWarps) {
+    // ===================== epilogue (both CTAs) =========================
+    const int q = warp & 3;
+    int it = 0;
+    for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+      const int t = u / g.ksplit;
+      const int h = u - t * g.ksplit;
+      const int n_blk = t / k_tiles;
+      const int k_blk = t - n_blk * k_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      tc::mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc::tcgen05_fence_after();
+      const int row = n_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(static_cast<char*>(g.out) + h * g.out_split_stride) +
+                       static_cast<int64_t>(row) * g.ldo + k_blk * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32);
+        tc::tmem_ld_32x32b_x32(taddr, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          Vec16 o;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o.w[e] = pack2(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+          st_vec(orow + c * 32 + v * 8, o);
+        }
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) tc::mbar_arrive(&bars->tmem_empty[acc]);
+        else tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bars->tmem_empty[acc]), 0));
+        if (FUSED) {
+          // this warp's 32 rows of the partial tile are in local HBM: tell the owner
+          __threadfence_system();
+          uint32_t* cnt = reinterpret_cast<uint32_t*>(wc.heap[t % wc.sync.size] + wc.cnt_off) + t;
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+        }
+      }
+    }
+  } else if (FUSED) {
+    // ===================== reduce + update (both CTAs) ==================
+    comm_reduce_update(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, g.ksplit);
+  }
+
+  tc::tcgen05_fence_before();
+  tc::cluster_sync();
+  if (warp == 1) tc::tmem_dealloc_2sm<kTmemCols>(tmem_base);
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_w() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    M4T_CHECK(e == cudaSuccess && q == cudaDriverEntryPointSuccess && p, "cuTensorMapEncodeTiled unavailable");
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Row-major [rows, cols] bf16 tensor, boxes of {64 columns, BK rows}.
+CUtensorMap make_tmap_mn(const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunk), static_cast<cuuint32_t>(BK)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled_w()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  M4T_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " << static_cast<int>(r));
+  return m;
+}
+
+template <bool FUSED> void configure_w() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_nt_2cta_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
+  });
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+bool wgrad_bf16_supported(int64_t Mb, int64_t N, int64_t K, const void* dy, const void* x, const void* g, int64_t ldy,
+                          int64_t ldx, int64_t ldg) {
+  return Mb > 0 && N > 0 && K > 0 && N % BM2 == 0 && K % BN == 0 && Mb % BK == 0 && aligned16(dy) && aligned16(x) &&
+         aligned16(g) && ldy % 8 == 0 && ldx % 8 == 0 && ldg % 8 == 0 && ldy >= N && ldx >= K && ldg >= K &&
+         Mb < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31);
+}
+
+void launch_wgrad_bf16(const void* dy, const void* x, void* gout, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
+                       int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream) {
+  M4T_CHECK(wgrad_bf16_supported(Mb, N, K, dy, x, gout, ldy, ldx, ldg),
+            "unsupported wgrad shape/alignment for the tcgen05 path (N % 256, K % 256, batch % 64)");
+  const CUtensorMap ta = make_tmap_mn(dy, Mb, N, ldy);
+  const CUtensorMap tb = make_tmap_mn(x, Mb, K, ldx);
+  WgradArgs g{};
+  g.out = gout;
+  g.out_split_stride = 0;
+  g.Mb = static_cast<int>(Mb);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldo = static_cast<int>(ldg);
+  g.ksplit = 1;
+  const int tiles = static_cast<int>((N / BM2) * (K / BN));
+  const int clusters = std::max(1, std::min(tiles, sm_count / 2));
+  configure_w<false>();
+  wgrad_bf16_nt_2cta_kernel<false><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, WgradComm{});
+  cudaError_t e = cudaGetLastError();
+  M4T_CHECK(e == cudaSuccess, "wgrad_bf16 launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
+}
+
+int64_t fused_wgrad_tiles(int64_t N, int64_t K) { return (N / BM2) * (K / BN); }
+int fused_wgrad_signals_per_tile(int ksplit) { return kSignalsPerUnit * ksplit; }
+
+void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
+                               int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
+                               int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
+                               uint32_t done_target, float scale, cudaStream_t stream) {
+  M4T_CHECK(dc.mc_heap != nullptr, "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping");
+  M4T_CHECK(ksplit == 1 || ksplit == 2, "ksplit must be 1 or 2");
+  M4T_CHECK((Mb / BK) % ksplit == 0, "batch / 64 must be divisible by ksplit");
+  char* stage = dc.heap[dc.sync.rank] + stage_off;
+  M4T_CHECK(wgrad_bf16_supported(Mb, N, K, dy, x, stage, ldy, ldx, K), "unsupported wgrad shape/alignment for the fused path");
+  const CUtensorMap ta = make_tmap_mn(dy, Mb, N, ldy);
+  const CUtensorMap tb = make_tmap_mn(x, Mb, K, ldx);
+  WgradArgs g{};
+  g.out = stage;
+  g.out_split_stride = stage_stride;
+  g.Mb = static_cast<int>(Mb);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldo = static_cast<int>(K);
+  g.ksplit = ksplit;
+  WgradComm wc{};
+  wc.sync = dc.sync;
+  for (int p = 0; p < dc.sync.size; ++p) wc.heap[p] = dc.heap[p];
+  wc.mc_heap = dc.mc_heap;
+  wc.stage_off = stage_off;
+  wc.stage_stride = stage_stride;
+  wc.w_off = w_off;
+  wc.cnt_off = cnt_off;
+  wc.done_off = done_off;
+  wc.tile_target = tile_target;
+  wc.done_target = done_target;
+  wc.scale = scale;
+  const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
+  configure_w<true>();
+  wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, wc);
+  cudaError_t e = cudaGetLastError();
+  M4T_CHECK(e == cudaSuccess, "fused_wgrad_update launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch();
+}
+
+}  // namespace m4t

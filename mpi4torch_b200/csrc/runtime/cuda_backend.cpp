@@ -371,6 +371,48 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
   return symm_ptr(st.wavg_off[par]);
 }
 
+bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, int64_t K) const {
+  if (size() <= 1 || !has_nvls()) return false;
+  const int64_t mode = env_i64("M4T_FUSED_WGRAD", 0);  // experimental: opt-in
+  if (mode == 0) return false;
+  if (size() < tune_.nvls_min_ranks && mode != 2) return false;
+  if (N % 256 != 0 || K % 256 != 0 || Mb % 128 != 0) return false;
+  const char* wb = static_cast<const char*>(w);
+  const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
+  if (!(wb >= arena && wb + N * K * 2 <= arena + symm_bytes_)) return false;  // must be switch-visible in place
+  const int64_t need = 2 * N * K * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;
+  return wgrad_.count((N << 32) | K) > 0 || symm_cursor_ + need <= symm_bytes_;
+}
+
+void CudaBackend::fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
+                                     int64_t ldy, int64_t ldx, float scale, cudaStream_t stream) {
+  check_device_error();
+  M4T_CHECK(fused_wgrad_available(w, Mb, N, K), "fused wgrad->Allreduce->SGD unavailable for N=" << N << " K=" << K
+                                                    << " (needs NVLS, M4T_FUSED_WGRAD=1 and a symmetric weight)");
+  M4T_CUDA(cudaSetDevice(device_));
+  const int64_t key = (N << 32) | K;
+  auto it = wgrad_.find(key);
+  if (it == wgrad_.end()) {
+    FusedWgradState st;
+    // two work units per tile even out the last wave on 74 CTA pairs (M4T_WGRAD_KSPLIT=1 disables)
+    st.ksplit = (env_i64("M4T_WGRAD_KSPLIT", 2) >= 2 && (Mb / 64) % 2 == 0) ? 2 : 1;
+    st.stage_stride = round_up64(N * K * 2, 1024);
+    st.stage_off = symm_alloc(st.stage_stride * st.ksplit);
+    st.cnt_off = symm_alloc(fused_wgrad_tiles(N, K) * 4);
+    st.done_off = symm_alloc(16);
+    it = wgrad_.emplace(key, st).first;  // the arena is zero-initialised: counters start at 0
+  }
+  FusedWgradState& st = it->second;
+  chain(stream);
+  const int64_t w_off = static_cast<const char*>(w) - dc_.heap[dc_.sync.rank];
+  st.calls += 1;
+  const uint32_t tile_target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(fused_wgrad_signals_per_tile(st.ksplit)) *
+                                                     static_cast<uint64_t>(size()));
+  const uint32_t done_target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
+  launch_fused_wgrad_update(dc_, dy, x, Mb, N, K, ldy, ldx, w_off, st.stage_off, st.stage_stride, st.cnt_off,
+                            st.done_off, st.ksplit, tile_target, done_target, scale, stream);
+}
+
 // ---------------------------------------------------------------------------
 // point-to-point
 // ---------------------------------------------------------------------------

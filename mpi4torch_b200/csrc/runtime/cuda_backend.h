@@ -74,6 +74,12 @@ class CudaBackend final : public Backend {
                                      const MseEpilogue* mse = nullptr);
   void gemm_bf16_tn(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                     int64_t ldc, cudaStream_t stream, const MseEpilogue* mse = nullptr);
+  // Experimental: w[N,K] += scale * sum_ranks (dy[Mb,N]^T x[Mb,K]) in one kernel (wgrad GEMM +
+  // in-switch reduce-scatter + SGD update + multicast of the new weights).  `w` must come from
+  // symmetric_alloc() and be replicated across ranks.
+  bool fused_wgrad_available(const void* w, int64_t Mb, int64_t N, int64_t K) const;
+  void fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
+                          int64_t ldx, float scale, cudaStream_t stream);
 
   // Throws if a device-side wait timed out since the last check.
   void check_device_error();
@@ -141,6 +147,12 @@ class CudaBackend final : public Backend {
     uint64_t calls = 0;
   };
   std::unordered_map<int64_t, FusedLinearState> fused_;  // key = N << 32 | K
+  struct FusedWgradState {
+    int64_t stage_off = 0, stage_stride = 0, cnt_off = 0, done_off = 0;
+    int ksplit = 1;
+    uint64_t calls = 0;
+  };
+  std::unordered_map<int64_t, FusedWgradState> wgrad_;  // key = N << 32 | K
   int64_t symm_off_ = 0, symm_cursor_ = 0, symm_bytes_ = 0;
   bool gemm_2cta_default_ = true;  // CTA-pair kernel validated on B200: 1521 vs 1390 TFLOP/s (cuBLAS 1552)
 };

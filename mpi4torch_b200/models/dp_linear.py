@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 import mpi4torch_b200 as m4t
@@ -42,6 +44,7 @@ class DPLinearModel:
         self.fast = fast    # fully fused training step (no autograd graph) when the inputs allow it
         self.overlap_slices = overlap_slices  # wgrad/allreduce pipelining granularity (fast path)
         self.overlap_blocks = 32              # CTAs of the overlapped allreduce (small footprint under the GEMM)
+        self.fused_wgrad = os.environ.get("M4T_FUSED_WGRAD", "0") not in ("", "0")  # experimental backward fusion
         self._side = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -70,6 +73,11 @@ class DPLinearModel:
         loss = c.Allreduce(local, m4t.MPI_SUM)
         n_out = self.weight.shape[0]
         slices = self.overlap_slices if (c.size > 1 and n_out % max(self.overlap_slices, 1) == 0) else 1
+        if self.fused_wgrad and torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_supported(self.weight, dy, x):
+            # experimental (M4T_FUSED_WGRAD=1): wgrad GEMM + gradient reduce-scatter in the switch +
+            # SGD update + multicast of the new weights as ONE tcgen05 kernel
+            torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(self.weight, dy, x, -self.lr / c.size)
+            return loss[0]
         if slices <= 1:
             gw_local = dy.t() @ x
             torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight, gw_local, -self.lr / c.size)

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Brings up the kernels / paths that are compiled but have not run on hardware yet
+# (DESIGN.md section 10).  usage:  gpurun --gpus <np> --timeout 900 -- bash scripts/gpu_experimental.sh <np>
+set -u
+NP=${1:-1}
+OUT=gpurun_out; mkdir -p $OUT
+export PYTHONPATH=$PWD M4T_TIMEOUT_S=90 M4T_DEVICE_TIMEOUT_S=10 M4T_DEBUG_SEGV=1 M4T_TEST_EXPERIMENTAL=1
+echo "=== [1 GPU] MN-major wgrad GEMM numerics"
+timeout 600 python -m pytest tests/test_gpu_gemm.py -x -q -k wgrad > $OUT/exp_wgrad.log 2>&1; echo "exit=$?"; tail -5 $OUT/exp_wgrad.log | cut -c1-400
+if [ "$NP" -gt 1 ]; then
+  echo "=== sub-communicators on CUDA np=$NP"
+  M4T_TEST_DEVICE=cuda M4T_TEST_SPLIT_CUDA=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_split.py > $OUT/exp_split_np$NP.log 2>&1
+  echo "exit=$?"; grep -v "^W0" $OUT/exp_split_np$NP.log | tail -6 | cut -c1-400
+  echo "=== fused wgrad -> reduce-scatter -> SGD -> multicast np=$NP"
+  M4T_TEST_DEVICE=cuda M4T_FUSED_WGRAD=2 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_gpu.py > $OUT/exp_fwgrad_np$NP.log 2>&1
+  echo "exit=$?"; grep -v "^W0" $OUT/exp_fwgrad_np$NP.log | tail -6 | cut -c1-400
+  echo "=== bench with the fused backward np=$NP"
+  M4T_FUSED_WGRAD=2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $NP --steps 20 --warmup 5 --no-extras > $OUT/exp_bench_fwgrad_n$NP.log 2>&1
+  echo "exit=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" $OUT/exp_bench_fwgrad_n$NP.log | tail -1 | cut -c1-900
+  echo "=== multicast-push Allgather np=$NP"
+  M4T_TEST_DEVICE=cuda M4T_AG_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_collectives.py > $OUT/exp_agpush_np$NP.log 2>&1
+  echo "exit=$?"; grep -v "^W0" $OUT/exp_agpush_np$NP.log | tail -4 | cut -c1-400
+fi

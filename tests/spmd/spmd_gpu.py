@@ -221,6 +221,29 @@ class TestFusedTrainingStep(unittest.TestCase):
         # all ranks hold identical weights after the fused allreduce+SGD epilogue
         self.assertTrue(torch.equal(fast.weight.detach(), comm.Bcast_(fast.weight.detach().clone(), 0)))
 
+    @unittest.skipUnless(os.environ.get("M4T_TEST_EXPERIMENTAL", "0") == "1" and os.environ.get("M4T_FUSED_WGRAD", "0") != "0",
+                         "experimental kernel: set M4T_TEST_EXPERIMENTAL=1 M4T_FUSED_WGRAD=2")
+    def test_fused_wgrad_update_matches_composition(self):
+        if P < 2 or not m4t.has_nvls():
+            return
+        N, K, Mb = 512, 256, 384
+        g = torch.Generator().manual_seed(5)
+        w0 = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16)
+        w = m4t.symmetric_empty((N, K), torch.bfloat16)
+        w.copy_(w0)
+        gr = torch.Generator().manual_seed(100 + R)
+        for step in range(3):
+            dy = torch.randn(Mb, N, generator=gr).to(torch.bfloat16).to(DEVICE)
+            x = torch.randn(Mb, K, generator=gr).to(torch.bfloat16).to(DEVICE)
+            ref_w = w.detach().clone()
+            gw = (dy.float().t() @ x.float()).to(torch.bfloat16)
+            torch.ops.mpi4torch_b200.allreduce_axpy_(ref_w, gw, -0.01 / P)
+            self.assertTrue(torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_supported(w, dy, x))
+            torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(w, dy, x, -0.01 / P)
+            torch.cuda.synchronize()
+            self.assertLess((w.float() - ref_w.float()).abs().max().item(), 2e-2, f"step {step}")
+            self.assertTrue(torch.equal(w, comm.Bcast_(w.detach().clone(), 0)))
+
     def test_allreduce_axpy_in_place(self):
         p = torch.full((1000,), 2.0, dtype=torch.float32, device=DEVICE)
         gsrc = torch.full((1000,), float(R + 1), dtype=torch.float32, device=DEVICE)

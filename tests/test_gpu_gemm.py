@@ -2,7 +2,13 @@
 import pytest
 import torch
 
+import os
+
 pytestmark = pytest.mark.gpu
+
+# kernels that have been compiled and SASS-checked but not yet run on hardware
+experimental = pytest.mark.skipif(os.environ.get("M4T_TEST_EXPERIMENTAL", "0") != "1",
+                                  reason="experimental kernel: set M4T_TEST_EXPERIMENTAL=1")
 
 
 def _ref(x, w):
@@ -88,3 +94,28 @@ def test_gemm_2cta_speed_report():
     b.synchronize()
     ms = a.elapsed_time(b) / 10
     print(f"[gemm] tcgen05 cta_group::2: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
+@experimental
+@pytest.mark.parametrize("shape", [(64, 256, 256), (128, 256, 512), (512, 512, 256), (8192, 4096, 4096), (4096, 1024, 2048)])
+def test_wgrad_mn_major_matches_fp32_reference(shape):
+    import mpi4torch_b200 as m4t  # noqa: F401
+
+    m4t.COMM_WORLD
+    Mb, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(Mb + 3 * N + 7 * K)
+    dy = torch.randn(Mb, N, device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn(Mb, K, device="cuda", generator=g).to(torch.bfloat16)
+    assert torch.ops.mpi4torch_b200.wgrad_bf16_supported(dy, x)
+    gw = torch.ops.mpi4torch_b200.wgrad_bf16(dy, x)
+    torch.cuda.synchronize()
+    ref = dy.float().t() @ x.float()
+    err = (gw.float() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err / scale < 2e-2, f"{shape}: max abs err {err} vs scale {scale}"
+    # structured check: a one-hot dy row selects rows of x exactly
+    sel = torch.zeros(Mb, N, device="cuda", dtype=torch.bfloat16)
+    idx = torch.arange(min(Mb, N), device="cuda")
+    sel[idx, idx] = 1
+    out = torch.ops.mpi4torch_b200.wgrad_bf16(sel, x)
+    assert torch.equal(out[: idx.numel()], x[: idx.numel()])
