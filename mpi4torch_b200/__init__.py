@@ -287,6 +287,12 @@ class MPI_Communicator:
         ``src/__init__.py:247-261``)."""
         return MPI_Communicator(self._comm.Split(color, key))
 
+    def Free(self) -> None:
+        """``MPI_Comm_free``: collective release of a sub-communicator's segments
+        and symmetric heap (otherwise they live until the process exits).  The
+        communicator must not be used afterwards."""
+        self._comm.Free()
+
     @property
     def is_world(self) -> bool:
         """True for :data:`COMM_WORLD` (fused GEMM ops and pickling need it)."""

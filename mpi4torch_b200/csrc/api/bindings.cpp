@@ -67,6 +67,7 @@ TORCH_LIBRARY(mpi4torch_b200, m) {
       .def("Wait", &Communicator::Wait)
       .def("Split", &Communicator::Split)
       .def("IsWorld", &Communicator::IsWorld)
+      .def("Free", &Communicator::Free)
       .def("Barrier", &Communicator::Barrier)
       .def("Describe", &Communicator::Describe)
       // Only the world communicator exists, so pickling round-trips it by name

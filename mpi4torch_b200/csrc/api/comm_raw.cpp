@@ -110,6 +110,7 @@ Communicator::Communicator() : world_(&World::instance()) {
 }
 
 Communicator::Communicator(std::shared_ptr<CommContext> owned) : world_(&World::instance()), owned_(std::move(owned)) {
+  is_world_ = false;
   ctx_ = owned_.get();
   rank_ = ctx_->rank();
   size_ = ctx_->size();
@@ -120,7 +121,7 @@ c10::intrusive_ptr<Communicator> Communicator::Split(int64_t color, int64_t key)
   // one metadata round: everybody learns everybody's (color, key)
   int64_t mine[2] = {color, key};
   std::vector<int64_t> all(static_cast<size_t>(size_) * 2);
-  ctx_->control().allgather_i64(mine, 2, all.data());
+  cx().control().allgather_i64(mine, 2, all.data());
   std::vector<std::pair<int64_t, int64_t>> members;  // (key, old rank)
   // a negative colour (MPI_UNDEFINED) still takes part in the exchange and gets
   // a communicator that contains only itself (MPI_COMM_SELF)
@@ -130,29 +131,38 @@ c10::intrusive_ptr<Communicator> Communicator::Split(int64_t color, int64_t key)
   int new_rank = -1;
   for (size_t i = 0; i < members.size(); ++i)
     if (members[i].second == rank_) new_rank = static_cast<int>(i);
-  const uint64_t split_id = ctx_->next_split_id();  // identical on all ranks: Split is collective
-  const std::string job = ctx_->job_id() + "_s" + std::to_string(split_id) +
+  const uint64_t split_id = cx().next_split_id();  // identical on all ranks: Split is collective
+  const std::string job = cx().job_id() + "_s" + std::to_string(split_id) +
                           (color >= 0 ? "c" + std::to_string(color) : "r" + std::to_string(rank_));
   auto child = std::make_shared<CommContext>(new_rank, static_cast<int>(members.size()), job);
-  if (ctx_->cuda_ready()) {
+  if (cx().cuda_ready()) {
     // same device, smaller arenas than the world communicator's
-    child->init_cuda(ctx_->cuda()->device(), env_i64("M4T_SUB_STAGE_MB", 256), env_i64("M4T_SUB_SYMM_MB", 0));
+    child->init_cuda(cx().cuda()->device(), env_i64("M4T_SUB_STAGE_MB", 256), env_i64("M4T_SUB_SYMM_MB", 0));
   }
   world_->register_child(child);
   return c10::make_intrusive<Communicator>(std::move(child));
+}
+
+void Communicator::Free() {
+  TORCH_CHECK(!IsWorld(), "mpi4torch_b200: the world communicator cannot be freed");
+  std::lock_guard<std::recursive_mutex> g(world_->mutex());
+  if (!ctx_) return;
+  world_->release_child(ctx_);
+  ctx_ = nullptr;
+  owned_.reset();  // the context's destructor performs the collective handshake
 }
 
 c10::intrusive_ptr<Communicator> comm_world() { return c10::make_intrusive<Communicator>(); }
 
 void Communicator::Barrier() {
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  ctx_->control().barrier();
+  cx().control().barrier();
 }
 
 std::string Communicator::Describe() const {
   std::ostringstream o;
-  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << ctx_->job_id() << " | cpu: posix-shm";
-  if (ctx_->cuda_ready()) o << " | " << ctx_->cuda()->describe();
+  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << cx().job_id() << " | cpu: posix-shm";
+  if (cx().cuda_ready()) o << " | " << cx().cuda()->describe();
   if (world_->host_staging()) o << " | host staging forced";
   return o.str();
 }
@@ -164,7 +174,7 @@ Tensor Communicator::raw_allreduce(const Tensor& input, int64_t op_, double scal
   const DType dt = to_dtype(input.scalar_type());
   check_op_dtype(op, dt);
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   Tensor in = r.to_comm(input);
   Tensor acc;
   Epilogue epi;
@@ -189,7 +199,7 @@ void Communicator::raw_allreduce_axpy_(Tensor& param, const Tensor& grad, double
               "mpi4torch_b200: allreduce_axpy_ needs a contiguous parameter and a gradient of the same shape/dtype/device");
   const DType dt = to_dtype(param.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, param);
+  Route r(*world_, cx(), param);
   Tensor gin = r.to_comm(grad);
   Epilogue epi;
   epi.scale = scale;
@@ -226,7 +236,7 @@ void Communicator::raw_bcast_(Tensor& work, int64_t root) {
   TORCH_CHECK(root >= 0 && root < size_, "mpi4torch_b200: Bcast_ root ", root, " out of range");
   const DType dt = to_dtype(work.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, work);
+  Route r(*world_, cx(), work);
   if (r.staged) {
     Tensor h = work.cpu();
     r.be->bcast(h.data_ptr(), h.numel(), dt, static_cast<int>(root), nullptr);
@@ -243,7 +253,7 @@ void Communicator::raw_reduce_(Tensor& work, int64_t op_, int64_t root) {
   const DType dt = to_dtype(work.scalar_type());
   check_op_dtype(op, dt);
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, work);
+  Route r(*world_, cx(), work);
   if (r.staged) {
     Tensor h = work.cpu();
     r.be->reduce(h.data_ptr(), h.numel(), dt, op, static_cast<int>(root), nullptr);
@@ -259,14 +269,14 @@ Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root
   const DType dt = to_dtype(input.scalar_type());
   const int64_t axis = wrap_axis(axis_, input.dim(), all ? "Allgather" : "Gather");
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   Tensor in = r.to_comm(input);
   const auto shape = in.sizes().vec();
   const Axis3 a3 = split_axis(shape, axis);
   // one metadata round: [axis length, before, after]
   int64_t mine[3] = {a3.axis, a3.before, a3.after};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
-  ctx_->control().allgather_i64(mine, 3, allmeta.data());
+  cx().control().allgather_i64(mine, 3, allmeta.data());
   std::vector<int64_t> lens(static_cast<size_t>(size_));
   for (int64_t p = 0; p < size_; ++p) {
     lens[p] = allmeta[p * 3];
@@ -291,7 +301,7 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
   TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Scatter numelem must be non-negative");
   const DType dt = to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   Tensor in = r.to_comm(input);
   // one metadata round: [numelem, ndim, sizes...]; only root's shape matters
   // (off-root tensors are placeholders, reference :786-796).
@@ -302,7 +312,7 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
   mine[1] = nd;
   for (int64_t i = 0; i < nd; ++i) mine[2 + i] = in.size(i);
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * kMetaWords);
-  ctx_->control().allgather_i64(mine.data(), kMetaWords, allmeta.data());
+  cx().control().allgather_i64(mine.data(), kMetaWords, allmeta.data());
   const int64_t* rootmeta = allmeta.data() + root * kMetaWords;
   const int64_t rnd = rootmeta[1];
   std::vector<int64_t> rshape(rootmeta + 2, rootmeta + 2 + rnd);
@@ -336,12 +346,12 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
   const int64_t gaxis = wrap_axis(gatheraxis_, nd, "Alltoall");
   const int64_t saxis = wrap_axis(scatteraxis_, nd, "Alltoall");
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   Tensor in = r.to_comm(input);
   const auto shape = in.sizes().vec();
   int64_t mine[2] = {numelem, shape[gaxis]};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 2);
-  ctx_->control().allgather_i64(mine, 2, allmeta.data());
+  cx().control().allgather_i64(mine, 2, allmeta.data());
   std::vector<int64_t> counts(static_cast<size_t>(size_)), glen(static_cast<size_t>(size_));
   for (int64_t p = 0; p < size_; ++p) {
     counts[p] = allmeta[p * 2];
@@ -375,13 +385,13 @@ Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_
   check_op_dtype(op, dt);
   const int64_t axis = wrap_axis(axis_, input.dim(), "Reduce_scatter");
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   Tensor in = r.to_comm(input);
   const auto shape = in.sizes().vec();
   const Axis3 a3 = split_axis(shape, axis);
   int64_t mine[3] = {numelem, a3.before * a3.after, a3.axis};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
-  ctx_->control().allgather_i64(mine, 3, allmeta.data());
+  cx().control().allgather_i64(mine, 3, allmeta.data());
   std::vector<int64_t> counts(static_cast<size_t>(size_));
   int64_t total = 0;
   for (int64_t p = 0; p < size_; ++p) {
@@ -427,7 +437,7 @@ std::vector<Tensor> Communicator::raw_isend(const Tensor& input, int64_t dest, i
   TORCH_CHECK(dest >= 0 && dest < size_, "mpi4torch_b200: Isend destination ", dest, " out of range");
   to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   Tensor buf = r.to_comm(input);
   if (buf.is_same(input)) buf = input.detach();  // own TensorImpl: the handle is an autograd output
   const int64_t req = r.be->isend(buf.data_ptr(), static_cast<int64_t>(buf.nbytes()), static_cast<int>(dest), tag, r.stream);
@@ -439,7 +449,7 @@ std::vector<Tensor> Communicator::raw_irecv(const Tensor& input, int64_t source,
   TORCH_CHECK(source >= 0 && source < size_, "mpi4torch_b200: Irecv source ", source, " out of range");
   to_dtype(input.scalar_type());
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  Route r(*world_, *ctx_, input);
+  Route r(*world_, cx(), input);
   // A non-contiguous (or host-staged) receive lands in a fresh buffer; callers
   // must use Wait's return value (same contract as the reference, :1256-1259).
   Tensor buf;
@@ -472,12 +482,12 @@ Tensor Communicator::raw_wait(const std::vector<Tensor>& handle) {
   void* stream = nullptr;
   c10::optional<c10::cuda::CUDAGuard> guard;
   if (buf.is_cuda()) {
-    TORCH_CHECK(ctx_->cuda_ready(), "mpi4torch_b200: CUDA wait handle without a CUDA backend");
+    TORCH_CHECK(cx().cuda_ready(), "mpi4torch_b200: CUDA wait handle without a CUDA backend");
     guard.emplace(buf.device());
     stream = c10::cuda::getCurrentCUDAStream(buf.device().index()).stream();
-    be = ctx_->cuda();
+    be = cx().cuda();
   } else {
-    be = &ctx_->cpu();
+    be = &cx().cpu();
   }
   be->wait(req, stream);
   if (kind == 0) return handle[2];

@@ -47,7 +47,10 @@ struct Communicator : torch::CustomClassHolder {
   // Collective over this communicator.  (The
   // reference gets sub-communicators from mpi4py, src/__init__.py:247-261.)
   c10::intrusive_ptr<Communicator> Split(int64_t color, int64_t key);
-  bool IsWorld() const { return owned_ == nullptr; }
+  bool IsWorld() const { return is_world_; }
+  // MPI_Comm_free: collective over the communicator; releases its segments and symmetric heap.
+  // Without it a sub-communicator's resources live until the process finalizes.
+  void Free();
   void Barrier();
   std::string Describe() const;
 
@@ -67,10 +70,15 @@ struct Communicator : torch::CustomClassHolder {
   Tensor raw_wait(const std::vector<Tensor>& handle);
 
   World& world() const { return *world_; }
-  CommContext& context() const { return *ctx_; }
+  CommContext& context() const { return cx(); }
 
  private:
+  CommContext& cx() const {
+    TORCH_CHECK(ctx_ != nullptr, "mpi4torch_b200: this communicator has been freed");
+    return *ctx_;
+  }
   World* world_;
+  bool is_world_ = true;
   CommContext* ctx_;                        // world context (owned by World) or owned_.get()
   std::shared_ptr<CommContext> owned_;      // non-null for communicators created by Split
   int64_t rank_, size_;

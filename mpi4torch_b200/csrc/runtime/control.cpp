@@ -1,5 +1,7 @@
 #include "control.h"
 
+#include <signal.h>
+
 #include <fcntl.h>
 #include <sched.h>
 #include <sys/mman.h>
@@ -162,6 +164,26 @@ void Control::barrier() {
     if (a.load(std::memory_order_acquire) >= my) continue;
     wait_until([&] { return a.load(std::memory_order_acquire) >= my; }, "host barrier");
   }
+}
+
+bool Control::quiesce(double timeout_s) noexcept {
+  if (!cb_ || size_ <= 1) return true;
+  cb_->departing.fetch_add(1, std::memory_order_acq_rel);
+  const uint64_t start = now_ns();
+  uint64_t spins = 0;
+  while (cb_->departing.load(std::memory_order_acquire) < static_cast<uint32_t>(size_)) {
+    if (cb_->abort_flag.load(std::memory_order_acquire)) return false;
+    if ((now_ns() - start) * 1e-9 > timeout_s) return false;
+    if ((spins & 0xfff) == 0xfff) {
+      // a peer that died without detaching will never arrive
+      for (int p = 0; p < size_; ++p) {
+        const int32_t pid = cb_->slots[p].pid.load(std::memory_order_relaxed);
+        if (p != rank_ && pid > 0 && kill(pid, 0) != 0 && errno == ESRCH) return false;
+      }
+    }
+    backoff(spins);
+  }
+  return true;
 }
 
 void Control::allgather_i64(const int64_t* mine, int k, int64_t* all) {

@@ -57,7 +57,8 @@ struct ControlBlock {
   std::atomic<uint32_t> attached;
   std::atomic<uint32_t> abort_flag;  // set by any rank on a fatal error
   std::atomic<uint32_t> abort_rank;
-  char pad[64 - 24];
+  std::atomic<uint32_t> departing;   // ranks that reached quiesce() (teardown handshake)
+  char pad[64 - 28];
   RankSlot slots[kMaxRanks];
   PairRing rings[kMaxRanks][kMaxRanks];  // [src][dst]
 };
@@ -78,6 +79,10 @@ class Control {
 
   // Host barrier over all ranks.  Throws on peer abort / timeout.
   void barrier();
+  // Teardown handshake (call at most once): waits until every rank has also reached its
+  // quiesce(), so nobody unlinks a shared segment a slower peer has not opened yet.  Never
+  // throws; gives up (false) on abort, on a dead peer or after `timeout_s`.
+  bool quiesce(double timeout_s) noexcept;
 
   // All-gather `k` int64 words per rank; `all` is [size][k] row-major.
   // One barrier; double-buffered so consecutive calls need no trailing barrier.

@@ -15,6 +15,8 @@ CommContext::CommContext(int rank, int size, const std::string& job_id) : job_id
 }
 
 CommContext::~CommContext() {
+  // every member reaches this point before anybody unmaps / unlinks shared segments
+  ctl_->quiesce(static_cast<double>(env_i64("M4T_EXIT_TIMEOUT_S", 10)));
   cuda_.reset();
   cpu_.reset();
   ctl_.reset();
@@ -33,9 +35,17 @@ World::World() {
 }
 
 World::~World() {
-  for (auto& w : children_)
-    if (auto c = w.lock()) c->shutdown_cuda();
+  for (auto& c : children_) c.reset();  // creation order
+  children_.clear();
   ctx_.reset();
+}
+
+void World::release_child(const CommContext* c) {
+  for (auto it = children_.begin(); it != children_.end(); ++it)
+    if (it->get() == c) {
+      children_.erase(it);
+      return;
+    }
 }
 
 World& World::instance() {

@@ -68,8 +68,12 @@ class World {
   void init_cuda(int device);
   bool cuda_ready() const { return ctx_->cuda_ready(); }
   CudaBackend* cuda() { return ctx_->cuda(); }
-  // sub-communicator contexts are torn down before the world at exit
+  // Sub-communicator contexts live until Free() or finalize(): like MPI_Comm_free, releasing
+  // a communicator is collective, so dropping the last Python reference must not tear down
+  // segments that slower members of the group are still reading.  Torn down in creation
+  // order (identical on all members), before the world.
   void register_child(const std::shared_ptr<CommContext>& c) { children_.push_back(c); }
+  void release_child(const CommContext* c);
 
   // Runtime toggle mirroring deactivate_cuda_aware_mpi_support() (reference
   // csrc/extension.cpp:54-59): CUDA tensors are staged through host memory and
@@ -86,7 +90,7 @@ class World {
   ~World();
   WorldEnv env_;
   std::shared_ptr<CommContext> ctx_;
-  std::vector<std::weak_ptr<CommContext>> children_;
+  std::vector<std::shared_ptr<CommContext>> children_;
   bool host_staging_ = false;
   std::recursive_mutex mu_;
 };

@@ -112,7 +112,9 @@ class TestSplit(unittest.TestCase):
             s = comm.Split(i % 2 if R % 2 else 0, R)
             t = s.Allreduce(torch.ones(1, dtype=torch.double, device=DEVICE), m4t.MPI_SUM)
             self.assertEqual(float(t[0]), float(s.size))
-            del s
+            s.Free()  # collective release (MPI_Comm_free)
+            with self.assertRaises(Exception):
+                s.Barrier()
 
 
 if __name__ == "__main__":
