@@ -74,10 +74,12 @@ def main() -> int:
 
     import mpi4torch_b200 as m4t
     from mpi4torch_b200.models import DPLinearModel
-    from mpi4torch_b200.utils import ClockSampler
+    from mpi4torch_b200.utils import ClockSampler, bind_to_gpu_numa
 
     comm = m4t.COMM_WORLD
     rank, size = comm.rank, comm.size
+    # pinned staging buffers must live on the GPU's own NUMA node (H2D is the e2e bound)
+    numa = bind_to_gpu_numa(torch.cuda.current_device())
     if size != args.gpus and rank == 0:
         sys.stderr.write(f"[bench] warning: --gpus {args.gpus} but world size is {size}\n")
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -187,6 +189,7 @@ def main() -> int:
             "fused_forward": bool(model.fused and size > 1),
             "heap_mode": m4t.heap_mode(),
             "nvls": m4t.has_nvls(),
+            "numa_bind": numa,
         },
         "tflops_per_gpu": flops_per_step * args.steps / (dev_ms * 1e-3) / 1e12,
         "gpu_launches": int(launches),
