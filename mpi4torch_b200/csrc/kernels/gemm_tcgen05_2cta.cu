@@ -54,6 +54,7 @@ struct Gemm2Args {
   float loss_scale, grad_scale;
   const uint32_t* panel_flags;  // fused mode: per-panel counters (local HBM, written through multicast)
   uint32_t panel_target;
+  int prefetch_target;          // M4T_EPI_PREFETCH=1 (experimental): pull the MSE target tile into L2 while the MMA runs
 };
 
 struct __align__(8) Bars {
@@ -189,9 +190,17 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int m_blk = t - n_blk * m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
+      if (EPI == 1 && g.prefetch_target && row < g.M) {
+        // the epilogue warps idle until the accumulator is complete: use the time to bring this
+        // lane's 512 bytes of the target into L2, so the loads below do not pay HBM latency
+        const char* tp = static_cast<const char*>(g.T) + (static_cast<int64_t>(row) * g.ldt + n_blk * BN) * 2;
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i)
+          if (n_blk * BN + (i + 1) * 64 <= g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + i * 128));
+      }
       tc::mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
-      const int row = m_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
       uint16_t* crow = static_cast<uint16_t*>(g.C) + static_cast<int64_t>(row) * g.ldc + n_blk * BN;
       const uint16_t* trow = nullptr;
       float loss_part = 0.f;
@@ -304,6 +313,8 @@ void launch_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int64_t M, 
   g.ldc = static_cast<int>(ldc);
   const int tiles = static_cast<int>(((M + BM2 - 1) / BM2) * ((N + BN - 1) / BN));
   const int clusters = std::max(1, std::min(tiles, sm_count / 2));
+  static const int epi_prefetch = static_cast<int>(env_i64("M4T_EPI_PREFETCH", 0));
+  g.prefetch_target = epi_prefetch;
   if (mse) {
     g.T = mse->target;
     g.ldt = static_cast<int>(mse->ldt);
@@ -340,6 +351,8 @@ void launch_fused_allreduce_gemm_2cta(const DeviceComm& dc, const void* x, void*
   g.ldc = static_cast<int>(ldy);
   g.panel_flags = reinterpret_cast<const uint32_t*>(dc.heap[dc.sync.rank] + flags_off);
   g.panel_target = panel_target;
+  static const int epi_prefetch = static_cast<int>(env_i64("M4T_EPI_PREFETCH", 0));
+  g.prefetch_target = epi_prefetch;
   CommArgs cm{};
   cm.sync = dc.sync;
   cm.mc_heap = dc.mc_heap;
