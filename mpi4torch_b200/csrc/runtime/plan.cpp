@@ -71,6 +71,16 @@ std::vector<int64_t> exclusive_scan(const std::vector<int64_t>& v) {
 }
 }  // namespace
 
+// Every rank walks its jobs in the same item order, so with jobs sorted by peer all ranks
+// would pull from peer 0 at the same time, then from peer 1, ... and share ONE GPU's NVLink
+// egress.  Start each rank at itself and continue with rank+1, rank+2, ...: at any moment the
+// (reader -> source) pairs form a permutation and every link is busy.
+static void rotate_jobs(PullPlan& plan, int rank, int size) {
+  std::stable_sort(plan.jobs.begin(), plan.jobs.end(), [&](const SlabJob& a, const SlabJob& b) {
+    return (a.peer - rank + size) % size < (b.peer - rank + size) % size;
+  });
+}
+
 PullPlan plan_gather(int rank, int size, int root, int64_t before, int64_t after,
                      const std::vector<int64_t>& axis_len, bool all) {
   PullPlan plan;
@@ -102,6 +112,7 @@ PullPlan plan_gather(int rank, int size, int root, int64_t before, int64_t after
       plan.jobs.push_back(j);
     }
   }
+  rotate_jobs(plan, rank, size);
   return plan;
 }
 
@@ -178,6 +189,7 @@ PullPlan plan_alltoall(int rank, int size, const std::vector<int64_t>& shape, in
     normalize_job(j);
     plan.jobs.push_back(j);
   }
+  rotate_jobs(plan, rank, size);
   return plan;
 }
 
@@ -209,6 +221,7 @@ PullPlan plan_repartition(int rank, int size, int64_t before, int64_t after,
     normalize_job(j);
     plan.jobs.push_back(j);
   }
+  rotate_jobs(plan, rank, size);
   return plan;
 }
 
