@@ -193,13 +193,21 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
           v[u] = ld_vec_sys(src + (base + idx[u]) * 16);
         }
       }
+      // the accumulate operand is requested for the whole batch before any of it is used, so
+      // its HBM latency is paid once per batch instead of once per vector
+      Vec16 av[kUnroll];
+      if (a.epi.acc) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (idx[u] >= 0) av[u] = load_private<DT>(a.epi.acc, base + idx[u], a.n, al);
+      }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         if (idx[u] < 0) continue;
         if (a.epi.acc) {
           typename V::A acc[V::N];
           V::unpack(v[u], acc);
-          apply_accumulate<DT>(acc, a.epi, base + idx[u], a.n, al);
+          add_vec<DT>(acc, av[u]);
           v[u] = V::pack(acc);
         }
         store_private<DT>(a.out, base + idx[u], a.n, al, v[u]);

@@ -200,21 +200,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32);
+        const int col0 = n_blk * BN + c * 32;
+        // all four target vectors of this chunk are requested up front (and before the TMEM
+        // load): one HBM round trip per chunk instead of four dependent ones
+        Vec16 tv[4];
+        if (EPI == 1 && row < g.M) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (col0 + v * 8 + 8 <= g.N) tv[v] = ld_vec_stream(trow + c * 32 + v * 8);
+        }
         tc::tmem_ld_32x32b_x32(taddr, r);
         tc::tmem_ld_wait();
         if (row < g.M) {
-          const int col0 = n_blk * BN + c * 32;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             if (col0 + v * 8 + 8 <= g.N) {
               Vec16 o;
               if (EPI == 1) {
-                // dL/dy = grad_scale * (y - t); loss += (y - t)^2
-                const Vec16 tv = ld_vec_stream(trow + c * 32 + v * 8);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float d0 = __uint_as_float(r[v * 8 + 2 * e]) - bf16_bits_to_float(static_cast<uint16_t>(tv.w[e] & 0xffffu));
-                  const float d1 = __uint_as_float(r[v * 8 + 2 * e + 1]) - bf16_bits_to_float(static_cast<uint16_t>(tv.w[e] >> 16));
+                  const float d0 = __uint_as_float(r[v * 8 + 2 * e]) - bf16_bits_to_float(static_cast<uint16_t>(tv[v].w[e] & 0xffffu));
+                  const float d1 = __uint_as_float(r[v * 8 + 2 * e + 1]) - bf16_bits_to_float(static_cast<uint16_t>(tv[v].w[e] >> 16));
                   loss_part = fmaf(d0, d0, loss_part);
                   loss_part = fmaf(d1, d1, loss_part);
                   o.w[e] = pack_bf16x2(d0 * g.grad_scale, d1 * g.grad_scale);

@@ -120,6 +120,16 @@ __device__ __forceinline__ void apply_accumulate(typename VecOf<DT>::A (&acc)[Ve
   }
 }
 
+// acc[] += unpack(v)   (the accumulate tensor's vector, loaded by the caller ahead of use)
+template <DType DT>
+__device__ __forceinline__ void add_vec(typename VecOf<DT>::A (&acc)[VecOf<DT>::N], const Vec16& v) {
+  using V = VecOf<DT>;
+  typename V::A b[V::N];
+  V::unpack(v, b);
+#pragma unroll
+  for (int k = 0; k < V::N; ++k) acc[k] = acc[k] + b[k];
+}
+
 __host__ inline DevEpilogue make_dev_epilogue(const Epilogue& e) {
   DevEpilogue d;
   d.scale_d = e.scale;
