@@ -87,16 +87,25 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const RootedArgs a) {
     }
     block_barrier_all(c, fb, bar++);
     if (is_root) {
-      for (int64_t i = base + first; i < end; i += stride) {
-        typename V::A acc[V::N];
-        if constexpr (NK != NvlsKind::NONE) {
-          V::unpack(multimem_ld_reduce_vec<NK>(a.mc_heap + half + i * 16), acc);
-        } else {
+      if constexpr (NK != NvlsKind::NONE) {
+        // four in-switch reductions in flight per thread (one NVSwitch round trip each)
+        for (int64_t i0 = base + first; i0 < end; i0 += 4 * stride) {
+          Vec16 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u * stride < end) x[u] = multimem_ld_reduce_vec<NK>(a.mc_heap + half + (i0 + u * stride) * 16);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u * stride < end) store_private<DT>(a.buf, i0 + u * stride, a.n, al, x[u]);
+        }
+      } else {
+        for (int64_t i = base + first; i < end; i += stride) {
+          typename V::A acc[V::N];
           init_from<DT, OP>(acc, ld_vec_sys(a.heap[0] + half + i * 16));
 #pragma unroll 1
           for (int p = 1; p < P; ++p) combine_into<DT, OP>(acc, ld_vec_sys(a.heap[p] + half + i * 16));
+          store_private<DT>(a.buf, i, a.n, al, V::pack(acc));
         }
-        store_private<DT>(a.buf, i, a.n, al, V::pack(acc));
       }
     }
   }

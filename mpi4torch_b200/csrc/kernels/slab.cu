@@ -87,6 +87,7 @@ __device__ __forceinline__ void item_to_offsets(const DevJob& j, int64_t local, 
 // Loads kPullUnroll items before storing any: peer loads take ~2 us, so the
 // achievable NVLink bandwidth is proportional to the requests in flight.
 constexpr int kPullUnroll = 4;
+constexpr int kReduceUnroll = 4;  // slab_reduce_vec: switch / peer reductions in flight per thread
 
 template <int VB> struct MoverReg;
 template <> struct MoverReg<16> {
@@ -209,36 +210,52 @@ __global__ void __launch_bounds__(kThreads) slab_reduce_vec_kernel(const ReduceA
   const int P = a.do_barrier ? c.size : 1;
   const int64_t half = a.stage_off + static_cast<int64_t>(par) * a.half_bytes;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
-  for (int64_t it = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; it < a.total_items; it += stride) {
-    int64_t so, d_o;
-    item_to_offsets(a.job, it, 16, so, d_o);
-    typename V::A acc[V::N];
-    if constexpr (NK != NvlsKind::NONE) {
-      V::unpack(multimem_ld_reduce_vec<NK>(a.mc_heap + half + so), acc);
-    } else {
-      // peers in batches of four: four NVLink loads in flight, combined in rank order
-      const char* s0 = (c.rank == 0 || !a.do_barrier) ? a.in : (a.heap[0] + half);
-      init_from<DT, OP>(acc, ld_vec_sys(s0 + so));
-#pragma unroll 1
-      for (int p0 = 1; p0 < P; p0 += 4) {
-        Vec16 v[4];
+  // kReduceUnroll items per thread and trip: the in-switch reductions (one ~3 us NVSwitch round
+  // trip each) are all requested before the first result is consumed
+  for (int64_t it0 = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; it0 < a.total_items;
+       it0 += kReduceUnroll * stride) {
+    int64_t so[kReduceUnroll], d_o[kReduceUnroll];
+    Vec16 x[kReduceUnroll];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int p = p0 + u;
-          if (p < P) {
-            const char* sp = (p == c.rank) ? a.in : (a.heap[p] + half);
-            v[u] = ld_vec_sys(sp + so);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (p0 + u < P) combine_into<DT, OP>(acc, v[u]);
+    for (int u = 0; u < kReduceUnroll; ++u) {
+      const int64_t it = it0 + u * stride;
+      d_o[u] = -1;
+      if (it < a.total_items) {
+        item_to_offsets(a.job, it, 16, so[u], d_o[u]);
+        if constexpr (NK != NvlsKind::NONE) x[u] = multimem_ld_reduce_vec<NK>(a.mc_heap + half + so[u]);
       }
     }
-    apply_scale<DT>(acc, a.epi);
-    // the box is 16-byte aligned in the output, so vector index = byte offset / 16
-    apply_accumulate<DT>(acc, a.epi, d_o / 16, a.out_elems, true);
-    st_vec(a.out + d_o, V::pack(acc));
+#pragma unroll
+    for (int u = 0; u < kReduceUnroll; ++u) {
+      if (d_o[u] < 0) continue;
+      typename V::A acc[V::N];
+      if constexpr (NK != NvlsKind::NONE) {
+        V::unpack(x[u], acc);
+      } else {
+        // peers in batches of four: four NVLink loads in flight, combined in rank order
+        const char* s0 = (c.rank == 0 || !a.do_barrier) ? a.in : (a.heap[0] + half);
+        init_from<DT, OP>(acc, ld_vec_sys(s0 + so[u]));
+#pragma unroll 1
+        for (int p0 = 1; p0 < P; p0 += 4) {
+          Vec16 v[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int p = p0 + w;
+            if (p < P) {
+              const char* sp = (p == c.rank) ? a.in : (a.heap[p] + half);
+              v[w] = ld_vec_sys(sp + so[u]);
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (p0 + w < P) combine_into<DT, OP>(acc, v[w]);
+        }
+      }
+      apply_scale<DT>(acc, a.epi);
+      // the box is 16-byte aligned in the output, so vector index = byte offset / 16
+      apply_accumulate<DT>(acc, a.epi, d_o[u] / 16, a.out_elems, true);
+      st_vec(a.out + d_o[u], V::pack(acc));
+    }
   }
   if (a.do_barrier) finish_op(c, 1);
 }
