@@ -17,6 +17,13 @@ if [ "$NP" -gt 1 ]; then
   echo "=== bench with the fused backward np=$NP"
   M4T_FUSED_WGRAD=2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $NP --steps 20 --warmup 5 --no-extras > $OUT/exp_bench_fwgrad_n$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" $OUT/exp_bench_fwgrad_n$NP.log | tail -1 | cut -c1-900
+  echo "=== fused forward diagnosis np=$NP (full / comm skipped / GEMM skipped / target prefetch)"
+  for v in "full:" "nocomm:M4T_FUSED_DEBUG=1" "nogemm:M4T_FUSED_DEBUG=2" "prefetch:M4T_EPI_PREFETCH=1"; do
+    name=${v%%:*}; kv=${v#*:}
+    env VARIANT=$name $kv timeout 300 python -m mpi4torch_b200.launch -np $NP scripts/fused_diag.py 2>&1 | grep -v "^W0" | tail -1 | tee -a $OUT/exp_fused_diag_np$NP.jsonl
+  done
+  echo "=== step breakdown np=$NP"; timeout 200 python -m mpi4torch_b200.launch -np $NP scripts/step_breakdown.py 2>&1 | grep -v "^W0" | tail -6 | tee $OUT/exp_step_breakdown_np$NP.jsonl
+  echo "=== collectives np=$NP (rotated pull plans)"; timeout 600 python -m mpi4torch_b200.launch -np $NP benchmarks/collectives_bench.py --max-mb 64 --out $OUT/exp_collectives_np$NP.json 2>&1 | grep -v "^W0" | tail -8 | cut -c1-700
   echo "=== multicast-push Allgather np=$NP"
   M4T_TEST_DEVICE=cuda M4T_AG_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_collectives.py > $OUT/exp_agpush_np$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0" $OUT/exp_agpush_np$NP.log | tail -4 | cut -c1-400
