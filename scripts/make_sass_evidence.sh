@@ -18,16 +18,22 @@ want = {
   'allreduce_pipelined_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_pipelined_bf16_sum',
   'allreduce_twoshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_bf16_sum',
   'allreduce_oneshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2E': 'allreduce_oneshot_bf16_sum',
+  'wgrad_bf16_nt_2cta_kernelILb1E': 'fused_wgrad_reduce_scatter_sgd_cta_pair',
+  'wgrad_bf16_nt_2cta_kernelILb0E': 'wgrad_mn_major_cta_pair',
+  'gemm_bf16_tn_2cta_kernelILb0ELi1E': 'gemm_mse_epilogue_cta_pair',
+  'slab_reduce_vec_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'reduce_scatter_nvls_bf16_sum',
   'p2p_recv_kernel': 'p2p_recv',
   'slab_pull_kernelILi16E': 'slab_pull_16B',
   'bcast_kernel': 'bcast',
 }
-pat = re.compile(r'\b(UTCHMMA[.\w]*|UTCQMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|LDTM[.\w]*|STTM[.\w]*|UTCBAR[.\w]*|LDGMC[.\w]*|STG\.[\w.]*MC[\w.]*|REDG?[.\w]*MC[.\w]*|MULTIMEM[.\w]*|LDG\.E\.128[.\w]*|STG\.E\.128[.\w]*|SYNCS[.\w]*|HMMA[.\w]*|MEMBAR[.\w]*|ST\.E[.\w]*STRONG\.SYS|LD\.E[.\w]*STRONG\.SYS)\b')
+pat = re.compile(r'\b(UTCHMMA[.\w]*|UTCQMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|LDTM[.\w]*|STTM[.\w]*|UTCBAR[.\w]*|LDGMC[.\w]*|STG\.[\w.]*MC[\w.]*|REDG?[.\w]*MC[.\w]*|MULTIMEM[.\w]*|LDG\.E\.128[.\w]*|LDG\.E\.NA\.128[.\w]*|STG\.E\.128[.\w]*|SYNCS[.\w]*|HMMA[.\w]*|MEMBAR[.\w]*|ST\.E[.\w]*STRONG\.SYS|LD\.E[.\w]*STRONG\.SYS)\b')
 summary = []
+seen = set()
 for f in funcs[1:]:
     name = f.split('\n', 1)[0].strip()
     for key, label in want.items():
-        if key in name:
+        if key in name and label not in seen:
+            seen.add(label)
             ops = collections.Counter(m.group(1) for m in pat.finditer(f))
             open(f'profiles/sass/{label}.sass', 'w').write('Function : ' + f)
             summary.append((label, name, ops))
