@@ -2,8 +2,8 @@
 parallel (the only strategy the reference ships, as an example), plus the ring
 (pipeline-style p2p) and sequence<->head (Ulysses-style) exchanges the
 reference's primitives enable."""
-from .data_parallel import DataParallel, sync_gradients_
+from .data_parallel import DataParallel, OverlappedGradSync, sync_gradients_
 from .ring import ring_exchange
 from .sequence import heads_to_sequence, sequence_to_heads
 
-__all__ = ["DataParallel", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence"]
+__all__ = ["DataParallel", "OverlappedGradSync", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence"]

@@ -14,6 +14,9 @@ if [ "$NP" -gt 1 ]; then
   echo "=== fused wgrad -> reduce-scatter -> SGD -> multicast np=$NP"
   M4T_TEST_DEVICE=cuda M4T_FUSED_WGRAD=2 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_gpu.py > $OUT/exp_fwgrad_np$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0" $OUT/exp_fwgrad_np$NP.log | tail -6 | cut -c1-400
+  echo "=== side-stream bucketed gradient sync np=$NP"
+  M4T_TEST_DEVICE=cuda timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_parallel.py > $OUT/exp_parallel_np$NP.log 2>&1
+  echo "exit=$?"; grep -v "^W0" $OUT/exp_parallel_np$NP.log | tail -4 | cut -c1-400
   echo "=== bench with the fused backward np=$NP"
   M4T_FUSED_WGRAD=2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $NP --steps 20 --warmup 5 --no-extras > $OUT/exp_bench_fwgrad_n$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" $OUT/exp_bench_fwgrad_n$NP.log | tail -1 | cut -c1-900

@@ -1,12 +1,14 @@
 """Parallelism helpers built on the primitives: DataParallel wrapper, in-place
 gradient sync, ring exchange, sequence<->head exchange, fused-epilogue ops."""
+import os
 import unittest
 
 import torch
 
 import mpi4torch_b200 as m4t
 from mpi4torch_b200 import ops
-from mpi4torch_b200.parallel import DataParallel, heads_to_sequence, ring_exchange, sequence_to_heads, sync_gradients_
+from mpi4torch_b200.parallel import (DataParallel, OverlappedGradSync, heads_to_sequence, ring_exchange,
+                                     sequence_to_heads, sync_gradients_)
 from common import DEVICE, comm
 
 P, R = comm.size, comm.rank
@@ -51,6 +53,50 @@ class TestDataParallel(unittest.TestCase):
         w.grad = torch.full((5,), float(R + 1), dtype=DT, device=DEVICE)
         sync_gradients_([w], comm)
         self.assertTrue(torch.equal(w.grad, torch.full_like(w.grad, (P + 1) / 2)))
+
+
+class TestOverlappedGradSync(unittest.TestCase):
+    # the side-stream variant has not run on hardware yet
+    @unittest.skipIf(DEVICE.type == "cuda" and os.environ.get("M4T_TEST_EXPERIMENTAL", "0") != "1",
+                     "CUDA side-stream gradient sync: set M4T_TEST_EXPERIMENTAL=1")
+    def test_matches_blocking_gradient_sync(self):
+        def make():
+            torch.manual_seed(3)
+            return torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                       torch.nn.Linear(16, 4)).to(DT).to(DEVICE)
+
+        a, b = make(), make()
+        sync = OverlappedGradSync(a.parameters(), comm, bucket_mb=1e-3)  # ~1 KB buckets: several of them
+        self.assertGreater(sync.num_buckets, 1)
+        g = torch.Generator().manual_seed(40 + R)
+        for step in range(3):
+            x = torch.randn(12, 8, generator=g, dtype=DT).to(DEVICE)
+            sync.zero_grad()
+            a(x).square().sum().backward()
+            sync.wait()
+            for p in b.parameters():
+                p.grad = None
+            b(x).square().sum().backward()
+            sync_gradients_(b.parameters(), comm)
+            for pa, pb in zip(a.parameters(), b.parameters()):
+                self.assertTrue(torch.allclose(pa.grad, pb.grad, rtol=1e-12, atol=1e-12), f"step {step}")
+            with torch.no_grad():
+                for pa, pb in zip(a.parameters(), b.parameters()):
+                    pa.add_(pa.grad, alpha=-0.01)
+                    pb.add_(pb.grad, alpha=-0.01)
+        sync.remove()
+
+    def test_unused_parameter_and_sum_mode(self):
+        if DEVICE.type == "cuda" and os.environ.get("M4T_TEST_EXPERIMENTAL", "0") != "1":
+            return
+        w1 = torch.nn.Parameter(torch.ones(3, dtype=DT, device=DEVICE))
+        w2 = torch.nn.Parameter(torch.ones(2, dtype=DT, device=DEVICE))  # never used in the loss
+        sync = OverlappedGradSync([w1, w2], comm, average=False)
+        (w1 * float(R + 1)).sum().backward()
+        sync.wait()
+        self.assertTrue(torch.equal(w1.grad, torch.full_like(w1, P * (P + 1) / 2)))
+        self.assertTrue(torch.equal(w2.grad, torch.zeros_like(w2)))
+        sync.remove()
 
 
 class TestRingAndSequence(unittest.TestCase):
