@@ -5,5 +5,7 @@ reference's primitives enable."""
 from .data_parallel import DataParallel, OverlappedGradSync, sync_gradients_
 from .ring import ring_exchange
 from .sequence import heads_to_sequence, sequence_to_heads
+from .tensor_parallel import ColumnParallelLinear, RowParallelLinear, TensorParallelMLP, replicated_input
 
-__all__ = ["DataParallel", "OverlappedGradSync", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence"]
+__all__ = ["DataParallel", "OverlappedGradSync", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence",
+           "ColumnParallelLinear", "RowParallelLinear", "TensorParallelMLP", "replicated_input"]

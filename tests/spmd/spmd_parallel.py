@@ -120,6 +120,49 @@ class TestRingAndSequence(unittest.TestCase):
         self.assertTrue(torch.equal(heads_to_sequence(y, 1, 2, comm), x))
 
 
+class TestTensorParallel(unittest.TestCase):
+    def _reference(self, x, feat, hid, seed):
+        from mpi4torch_b200.parallel.tensor_parallel import _full_weight
+
+        w1 = _full_weight(hid, feat, seed, DT, DEVICE).requires_grad_()
+        w2 = _full_weight(feat, hid, seed + 1, DT, DEVICE).requires_grad_()
+        xr = x.detach().clone().requires_grad_()
+        y = torch.tanh(xr @ w1.t()) @ w2.t()
+        y.square().sum().backward()
+        return y.detach(), w1.grad, w2.grad, xr.grad
+
+    def test_mlp_matches_unsharded_model(self):
+        from mpi4torch_b200.parallel import TensorParallelMLP
+
+        feat, hid = 6, 4 * P
+        mlp = TensorParallelMLP(feat, hid, comm, dtype=DT, device=DEVICE, seed=21)
+        x = torch.randn(5, feat, generator=torch.Generator().manual_seed(9), dtype=DT).to(DEVICE).requires_grad_()
+        y = mlp(x)
+        (y.square().sum() / P).backward()  # every rank holds the same loss: objective = sum over ranks
+        y_ref, g1, g2, gx = self._reference(x, feat, hid, 21)
+        rows = hid // P
+        self.assertTrue(torch.allclose(y.detach(), y_ref, rtol=1e-11, atol=1e-11))
+        self.assertTrue(torch.allclose(mlp.up.weight.grad, g1[R * rows:(R + 1) * rows], rtol=1e-10, atol=1e-10))
+        self.assertTrue(torch.allclose(mlp.down.weight.grad, g2[:, R * rows:(R + 1) * rows], rtol=1e-10, atol=1e-10))
+        self.assertTrue(torch.allclose(x.grad, gx, rtol=1e-10, atol=1e-10))
+        # replicated bias of the row-parallel layer: d/db sum(y^2) = 2 * sum_batch y
+        self.assertTrue(torch.allclose(mlp.down.bias.grad, 2 * y_ref.sum(dim=0), rtol=1e-10, atol=1e-10))
+
+    def test_column_parallel_gathers_and_reduce_scatters(self):
+        from mpi4torch_b200.parallel import ColumnParallelLinear
+        from mpi4torch_b200.parallel.tensor_parallel import _full_weight
+
+        lin = ColumnParallelLinear(3, 2 * P, comm, bias=False, dtype=DT, device=DEVICE, seed=4)
+        x = torch.randn(4, 3, generator=torch.Generator().manual_seed(2), dtype=DT).to(DEVICE)
+        y = lin(x)
+        w = _full_weight(2 * P, 3, 4, DT, DEVICE)
+        self.assertTrue(torch.allclose(y.detach(), x @ w.t(), rtol=1e-12, atol=1e-12))
+        coef = torch.arange(1, 2 * P + 1, dtype=DT, device=DEVICE)
+        ((y * coef).sum() / P).backward()
+        expect = coef[2 * R:2 * R + 2, None] * x.sum(dim=0)[None, :]
+        self.assertTrue(torch.allclose(lin.weight.grad, expect, rtol=1e-11, atol=1e-11))
+
+
 class TestFunctionalOps(unittest.TestCase):
     def test_allreduce_mean_and_sgd_step(self):
         x = torch.full((7,), float(R), dtype=DT, device=DEVICE)
