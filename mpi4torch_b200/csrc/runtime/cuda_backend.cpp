@@ -36,6 +36,7 @@ CudaBackend::CudaBackend(Control& ctl, int device, int64_t stage_mb, int64_t sym
 
   nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", 16))));
   slot_bytes_ = round_up64(std::max<int64_t>(4096, env_i64("M4T_P2P_SLOT_KB", 1024) * 1024), 128);
+  p2p_push_ = env_i64("M4T_P2P_PUSH", 0) != 0;
   p2p_head_off_ = kP2pHeadOff;
   p2p_tail_off_ = kP2pTailOff;
   p2p_off_ = kP2pRingOff;
@@ -428,7 +429,12 @@ cudaStream_t CudaBackend::recv_stream(int peer) {
 P2pChannel CudaBackend::send_channel(int dest) const {
   P2pChannel ch;
   const int r = rank();
-  ch.slots = heap_->peer(r) + p2p_off_ + static_cast<int64_t>(dest) * nslots_ * slot_bytes_;
+  // default: ring in the SENDER's heap (local copy-in, receiver pulls over NVLink).  With
+  // M4T_P2P_PUSH=1 (experimental, every rank must agree) the ring for the pair lives in the
+  // RECEIVER's heap, indexed by the source: the sender's stores cross NVLink as posted
+  // writes (no round trip) and the receiver's copy-out is local.
+  ch.slots = p2p_push_ ? heap_->peer(dest) + p2p_off_ + static_cast<int64_t>(r) * nslots_ * slot_bytes_
+                       : heap_->peer(r) + p2p_off_ + static_cast<int64_t>(dest) * nslots_ * slot_bytes_;
   // head flags live in the receiver's pad, indexed by the source rank (me)
   ch.head_flags = reinterpret_cast<uint32_t*>(heap_->peer(dest) + p2p_head_off_) + static_cast<int64_t>(r) * kMaxSlots;
   // tail flags live in my pad, indexed by the destination
@@ -441,7 +447,8 @@ P2pChannel CudaBackend::send_channel(int dest) const {
 P2pChannel CudaBackend::recv_channel(int source) const {
   P2pChannel ch;
   const int r = rank();
-  ch.slots = heap_->peer(source) + p2p_off_ + static_cast<int64_t>(r) * nslots_ * slot_bytes_;
+  ch.slots = p2p_push_ ? heap_->peer(r) + p2p_off_ + static_cast<int64_t>(source) * nslots_ * slot_bytes_
+                       : heap_->peer(source) + p2p_off_ + static_cast<int64_t>(r) * nslots_ * slot_bytes_;
   ch.head_flags = reinterpret_cast<uint32_t*>(heap_->peer(r) + p2p_head_off_) + static_cast<int64_t>(source) * kMaxSlots;
   ch.tail_flags = reinterpret_cast<uint32_t*>(heap_->peer(source) + p2p_tail_off_) + static_cast<int64_t>(r) * kMaxSlots;
   ch.slot_bytes = slot_bytes_;

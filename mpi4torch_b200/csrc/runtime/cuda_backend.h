@@ -133,6 +133,7 @@ class CudaBackend final : public Backend {
   int64_t p2p_off_ = 0, p2p_head_off_ = 0, p2p_tail_off_ = 0;
   int64_t slot_bytes_ = 0;
   int nslots_ = 0;
+  bool p2p_push_ = false;  // ring in the receiver's heap (sender pushes) instead of the sender's (receiver pulls)
   std::vector<cudaStream_t> send_streams_, recv_streams_;
   std::vector<unsigned long long> send_chunks_, recv_chunks_;
   std::vector<uint64_t> send_seq_;

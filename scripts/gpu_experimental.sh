@@ -27,6 +27,11 @@ if [ "$NP" -gt 1 ]; then
   done
   echo "=== step breakdown np=$NP"; timeout 200 python -m mpi4torch_b200.launch -np $NP scripts/step_breakdown.py 2>&1 | grep -v "^W0" | tail -6 | tee $OUT/exp_step_breakdown_np$NP.jsonl
   echo "=== collectives np=$NP (rotated pull plans)"; timeout 600 python -m mpi4torch_b200.launch -np $NP benchmarks/collectives_bench.py --max-mb 64 --out $OUT/exp_collectives_np$NP.json 2>&1 | grep -v "^W0" | tail -8 | cut -c1-700
+  echo "=== p2p ring: pull (default) vs push np=$NP"
+  for push in 0 1; do
+    M4T_P2P_PUSH=$push timeout 300 python -m mpi4torch_b200.launch -np $NP benchmarks/ring_overlap.py --mb 64 --out $OUT/exp_ring_push${push}_np$NP.json 2>&1 | grep -v "^W0" | tail -2
+  done
+  M4T_TEST_DEVICE=cuda M4T_P2P_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_nonblocking.py 2>&1 | grep -v "^W0" | tail -3
   echo "=== multicast-push Allgather np=$NP"
   M4T_TEST_DEVICE=cuda M4T_AG_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_collectives.py > $OUT/exp_agpush_np$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0" $OUT/exp_agpush_np$NP.log | tail -4 | cut -c1-400
