@@ -31,6 +31,13 @@ if [ "$NP" -gt 1 ]; then
   for push in 0 1; do
     M4T_P2P_PUSH=$push timeout 300 python -m mpi4torch_b200.launch -np $NP benchmarks/ring_overlap.py --mb 64 --out $OUT/exp_ring_push${push}_np$NP.json 2>&1 | grep -v "^W0" | tail -2
   done
+  for cfg in "64 256 64" "32 512 64"; do
+    set -- $cfg
+    for push in 0 1; do
+      echo "slots=$1 slot_kb=$2 blocks=$3 push=$push"
+      M4T_P2P_SLOTS=$1 M4T_P2P_SLOT_KB=$2 M4T_P2P_BLOCKS=$3 M4T_P2P_PUSH=$push timeout 300 python -m mpi4torch_b200.launch -np $NP benchmarks/ring_overlap.py --mb 64 2>&1 | grep -v "^W0" | tail -1
+    done
+  done
   M4T_TEST_DEVICE=cuda M4T_P2P_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_nonblocking.py 2>&1 | grep -v "^W0" | tail -3
   echo "=== multicast-push Allgather np=$NP"
   M4T_TEST_DEVICE=cuda M4T_AG_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_collectives.py > $OUT/exp_agpush_np$NP.log 2>&1
