@@ -74,7 +74,7 @@ struct Communicator : torch::CustomClassHolder {
 
  private:
   CommContext& cx() const {
-    TORCH_CHECK(ctx_ != nullptr, "mpi4torch_b200: this communicator has been freed");
+    TORCH_CHECK(ctx_ != nullptr && (is_world_ || ctx_->alive()), "mpi4torch_b200: this communicator has been freed");
     return *ctx_;
   }
   World* world_;

@@ -14,7 +14,10 @@ CommContext::CommContext(int rank, int size, const std::string& job_id) : job_id
   cpu_ = std::make_unique<CpuBackend>(*ctl_);
 }
 
-CommContext::~CommContext() {
+CommContext::~CommContext() { shutdown(); }
+
+void CommContext::shutdown() {
+  if (!ctl_) return;
   // every member reaches this point before anybody unmaps / unlinks shared segments
   ctl_->quiesce(static_cast<double>(env_i64("M4T_EXIT_TIMEOUT_S", 10)));
   cuda_.reset();
@@ -35,8 +38,9 @@ World::World() {
 }
 
 World::~World() {
-  for (auto& c : children_) c.reset();  // creation order
+  for (auto& c : children_) c->shutdown();  // creation order (identical on all members)
   children_.clear();
+  ctx_->shutdown();
   ctx_.reset();
 }
 

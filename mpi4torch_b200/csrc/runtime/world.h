@@ -33,6 +33,11 @@ class CommContext {
   // Collective over the context's ranks.  stage_mb / symm_mb < 0 = environment defaults.
   void init_cuda(int device, int64_t stage_mb = -1, int64_t symm_mb = -1);
   void shutdown_cuda();
+  // Collective teardown (handshake, then backends, then the control segment).  Idempotent;
+  // also run by the destructor.  World::finalize() calls it on every context that is still
+  // registered, even if Python objects keep the context object itself alive.
+  void shutdown();
+  bool alive() const { return ctl_ != nullptr; }
   bool cuda_ready() const { return cuda_ != nullptr; }
   CudaBackend* cuda() { return cuda_.get(); }
   uint64_t next_split_id() { return ++split_seq_; }
