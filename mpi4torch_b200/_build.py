@@ -17,7 +17,9 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
-_LIB = _PKG / "_lib"
+# M4T_LIB_DIR / M4T_EXTRA_CXXFLAGS / M4T_EXTRA_LDFLAGS: out-of-tree instrumented builds
+# (scripts/asan_cpu.sh); the default is the in-tree release build.
+_LIB = Path(os.environ["M4T_LIB_DIR"]) if os.environ.get("M4T_LIB_DIR") else _PKG / "_lib"
 _NAME = "_m4t_C"
 
 _SOURCES = [
@@ -42,6 +44,7 @@ _SOURCES = [
 ]
 
 CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-Wno-sign-compare"]
+CXX_FLAGS += os.environ.get("M4T_EXTRA_CXXFLAGS", "").split()
 NVCC_FLAGS = [
     "-O3",
     "-std=c++17",
@@ -52,7 +55,7 @@ NVCC_FLAGS = [
     "-diag-suppress",
     "177",
 ]
-LD_FLAGS = ["-lrt", "-lpthread"]
+LD_FLAGS = ["-lrt", "-lpthread"] + os.environ.get("M4T_EXTRA_LDFLAGS", "").split()
 
 
 def _existing_sources() -> list[str]:
