@@ -43,7 +43,7 @@ _SOURCES = [
     "api/bindings.cpp",
 ]
 
-CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-Wno-sign-compare"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-fopenmp", "-Wall", "-Wno-unused-function", "-Wno-sign-compare"]
 CXX_FLAGS += os.environ.get("M4T_EXTRA_CXXFLAGS", "").split()
 NVCC_FLAGS = [
     "-O3",
@@ -55,7 +55,7 @@ NVCC_FLAGS = [
     "-diag-suppress",
     "177",
 ]
-LD_FLAGS = ["-lrt", "-lpthread"] + os.environ.get("M4T_EXTRA_LDFLAGS", "").split()
+LD_FLAGS = ["-lrt", "-lpthread", "-fopenmp"] + os.environ.get("M4T_EXTRA_LDFLAGS", "").split()
 
 
 def _existing_sources() -> list[str]:

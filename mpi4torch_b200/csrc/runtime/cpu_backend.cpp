@@ -9,11 +9,31 @@
 #include <cerrno>
 #include <cstring>
 
+#include <omp.h>
+
 #include "reduce_ops.h"
 
 namespace m4t {
 
 namespace {
+
+// Large copies / reductions are memory-bound; a rank may use the OpenMP threads the launcher
+// left it (OMP_NUM_THREADS = cores / ranks).  Below the threshold one thread is faster.
+constexpr size_t kParallelBytes = 1u << 20;
+
+inline void par_memcpy(void* dst, const void* src, size_t bytes) {
+  if (bytes < kParallelBytes || omp_get_max_threads() <= 1 || omp_in_parallel()) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  constexpr size_t kChunk = 256u << 10;
+  const int64_t chunks = static_cast<int64_t>((bytes + kChunk - 1) / kChunk);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < chunks; ++c) {
+    const size_t off = static_cast<size_t>(c) * kChunk;
+    std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(kChunk, bytes - off));
+  }
+}
 
 constexpr size_t kMinArena = 1u << 20;
 constexpr int64_t kTwoPhaseBytes = 256 * 1024;
@@ -25,24 +45,54 @@ template <typename A> inline A scale_acc(A v, double s) {
 }
 template <> inline float scale_acc<float>(float v, double s) { return v * static_cast<float>(s); }
 
-// out[i] = epi(combine_k srcs[k][i]) for i in [lo, hi)
+// out[i] = epi(combine_k srcs[k][i]) for i in [lo, hi).  Sources are combined in index order
+// k = 0..nsrc-1 per element (identical result on every rank); the loops are blocked so that
+// the inner ones run over contiguous elements of ONE source and vectorise.
 template <DType DT, ReduceOp OP> struct CpuReduceRange {
+  using E = Elem<DT>;
+  using S = typename E::storage;
+  using A = typename E::acc;
+  using C = Combine<OP, A, E::is_float>;
+
+  static void run_serial(const void* const* srcs, int nsrc, S* o, const S* accp, bool scaled, double s, int64_t lo,
+                         int64_t hi) {
+    constexpr int kBlock = 512;
+    A buf[kBlock];
+    for (int64_t b0 = lo; b0 < hi; b0 += kBlock) {
+      const int n = static_cast<int>(std::min<int64_t>(kBlock, hi - b0));
+      const S* s0 = static_cast<const S*>(srcs[0]) + b0;
+      for (int j = 0; j < n; ++j) buf[j] = normalise_single<OP, A>(E::load(s0[j]));
+      for (int k = 1; k < nsrc; ++k) {
+        const S* sk = static_cast<const S*>(srcs[k]) + b0;
+        for (int j = 0; j < n; ++j) buf[j] = C::apply(buf[j], E::load(sk[j]));
+      }
+      if (scaled)
+        for (int j = 0; j < n; ++j) buf[j] = scale_acc<A>(buf[j], s);
+      if (accp)
+        for (int j = 0; j < n; ++j) buf[j] = buf[j] + E::load(accp[b0 + j]);
+      for (int j = 0; j < n; ++j) o[b0 + j] = E::store(buf[j]);
+    }
+  }
+
   static void run(const void* const* srcs, int nsrc, void* out, int64_t lo, int64_t hi,
                   const Epilogue* epi) {
-    using E = Elem<DT>;
-    using S = typename E::storage;
-    using A = typename E::acc;
-    using C = Combine<OP, A, E::is_float>;
     S* o = static_cast<S*>(out);
     const S* accp = (epi && epi->accumulate) ? static_cast<const S*>(epi->accumulate) : nullptr;
     const bool scaled = epi && epi->has_scale;
     const double s = epi ? epi->scale : 1.0;
-    for (int64_t i = lo; i < hi; ++i) {
-      A v = normalise_single<OP, A>(E::load(static_cast<const S*>(srcs[0])[i]));
-      for (int k = 1; k < nsrc; ++k) v = C::apply(v, E::load(static_cast<const S*>(srcs[k])[i]));
-      if (scaled) v = scale_acc<A>(v, s);
-      if (accp) v = v + E::load(accp[i]);
-      o[i] = E::store(v);
+    const int64_t n = hi - lo;
+    const int threads = omp_get_max_threads();
+    if (n <= 0) return;
+    if (static_cast<size_t>(n) * sizeof(S) < kParallelBytes || threads <= 1 || omp_in_parallel()) {
+      run_serial(srcs, nsrc, o, accp, scaled, s, lo, hi);
+      return;
+    }
+    const int64_t per = ((n + threads - 1) / threads + 511) / 512 * 512;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < threads; ++t) {
+      const int64_t a = lo + static_cast<int64_t>(t) * per;
+      const int64_t b = std::min(hi, a + per);
+      if (a < b) run_serial(srcs, nsrc, o, accp, scaled, s, a, b);
     }
   }
 };
@@ -162,7 +212,7 @@ void CpuBackend::allreduce(const void* in, void* out, int64_t n, DType dt, Reduc
   const int par = static_cast<int>(op_seq_++ & 1);
   const bool two_phase = static_cast<int64_t>(bytes) >= kTwoPhaseBytes;
   char* mine = stage(par, two_phase ? 2 * bytes : bytes);
-  if (bytes) std::memcpy(mine, in, bytes);
+  if (bytes) par_memcpy(mine, in, bytes);
   ctl_.barrier();
   const void* srcs[kMaxRanks];
   for (int p = 0; p < P; ++p) srcs[p] = peer_arena(p, par);
@@ -184,7 +234,7 @@ void CpuBackend::allreduce(const void* in, void* out, int64_t n, DType dt, Reduc
     if (epi.accumulate) {
       M4T_DISPATCH_DTYPE_OP(dt, ReduceOp::SUM, CpuAccumulateCopy, res, epi.accumulate, out, plo, phi);
     } else {
-      std::memcpy(static_cast<char*>(out) + plo * es, res + plo * es, static_cast<size_t>((phi - plo) * es));
+      par_memcpy(static_cast<char*>(out) + plo * es, res + plo * es, static_cast<size_t>((phi - plo) * es));
     }
   }
 }
@@ -197,10 +247,10 @@ void CpuBackend::bcast(void* buf, int64_t n, DType dt, int root, void*) {
   const int par = static_cast<int>(op_seq_++ & 1);
   if (r == root) {
     char* mine = stage(par, bytes);
-    if (bytes) std::memcpy(mine, buf, bytes);
+    if (bytes) par_memcpy(mine, buf, bytes);
   }
   ctl_.barrier();
-  if (r != root && bytes) std::memcpy(buf, peer_arena(root, par), bytes);
+  if (r != root && bytes) par_memcpy(buf, peer_arena(root, par), bytes);
 }
 
 void CpuBackend::reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void*) {
@@ -215,7 +265,7 @@ void CpuBackend::reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, v
   }
   const int par = static_cast<int>(op_seq_++ & 1);
   char* mine = stage(par, bytes);
-  if (bytes) std::memcpy(mine, buf, bytes);
+  if (bytes) par_memcpy(mine, buf, bytes);
   ctl_.barrier();
   if (r == root) {
     const void* srcs[kMaxRanks];
@@ -237,7 +287,7 @@ void CpuBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt,
   if (plan.stage_elems > 0) {
     const size_t bytes = static_cast<size_t>(plan.stage_elems * es);
     char* mine = stage(par, bytes);
-    std::memcpy(mine, in, bytes);
+    par_memcpy(mine, in, bytes);
   }
   ctl_.barrier();
   for (const auto& j : plan.jobs) {
@@ -284,7 +334,7 @@ void CpuBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out, 
   const int par = static_cast<int>(op_seq_++ & 1);
   const size_t bytes = static_cast<size_t>(plan.stage_elems * es);
   char* mine = stage(par, bytes);
-  if (bytes) std::memcpy(mine, in, bytes);
+  if (bytes) par_memcpy(mine, in, bytes);
   ctl_.barrier();
   if (plan.out_elems == 0) return;
   for (int p = 0; p < P; ++p) srcs[p] = (p == r) ? static_cast<const char*>(in) : peer_arena(p, par);
@@ -316,7 +366,7 @@ int64_t CpuBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag,
     void* p = mmap(nullptr, static_cast<size_t>(bytes), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     M4T_CHECK(p != MAP_FAILED, "mmap of message segment failed: " << std::strerror(errno));
-    std::memcpy(p, buf, static_cast<size_t>(bytes));
+    par_memcpy(p, buf, static_cast<size_t>(bytes));
     munmap(p, static_cast<size_t>(bytes));
   }
   const uint64_t head = ring.head.load(std::memory_order_relaxed);
@@ -362,7 +412,7 @@ void CpuBackend::deliver(const MsgDesc& d, int source, Request& rq) {
   void* p = mmap(nullptr, d.bytes, PROT_READ, MAP_SHARED, fd, 0);
   close(fd);
   M4T_CHECK(p != MAP_FAILED, "mmap of message segment failed: " << std::strerror(errno));
-  std::memcpy(rq.buf, p, d.bytes);
+  par_memcpy(rq.buf, p, d.bytes);
   munmap(p, d.bytes);
   shm_unlink(name.c_str());
 }
