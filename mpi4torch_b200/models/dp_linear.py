@@ -78,6 +78,11 @@ class DPLinearModel:
             # SGD update + multicast of the new weights as ONE tcgen05 kernel
             torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(self.weight, dy, x, -self.lr / c.size)
             return loss[0]
+        if c.size == 1:
+            # single rank: nothing to reduce - the SGD update is the GEMM's own epilogue
+            # (W = 1*W + (-lr) * dy^T x, one library GEMM, no gradient tensor)
+            self.weight.addmm_(dy.t(), x, alpha=-self.lr)
+            return loss[0]
         if slices <= 1:
             gw_local = dy.t() @ x
             torch.ops.mpi4torch_b200.allreduce_axpy_(self.weight, gw_local, -self.lr / c.size)
