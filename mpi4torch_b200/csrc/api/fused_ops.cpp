@@ -197,12 +197,52 @@ void wgrad_allreduce_sgd_(Tensor w, const Tensor& dy, const Tensor& x, double sc
   std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
   backend().fused_wgrad_update(w.data_ptr(), dy.data_ptr(), x.data_ptr(), dy.size(0), w.size(0), w.size(1), dy.stride(0),
                                x.stride(0), static_cast<float>(scale),
-                               c10::cuda::getCurrentCUDAStream(x.device().index()).stream());
+                               c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), false);
+}
+
+// Same kernel, and additionally the parameter all-reduce of the NEXT forward: returns
+// W_avg = (1/size) * sum_ranks w_new (symmetric-heap memory, valid until the next call).
+Tensor wgrad_allreduce_sgd_prefetch_(Tensor w, const Tensor& dy, const Tensor& x, double scale) {
+  TORCH_CHECK(wgrad_allreduce_sgd_supported(w, dy, x), "mpi4torch_b200: fused wgrad->Allreduce->SGD does not support these tensors");
+  c10::cuda::CUDAGuard guard(x.device());
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  const void* wavg = backend().fused_wgrad_update(w.data_ptr(), dy.data_ptr(), x.data_ptr(), dy.size(0), w.size(0), w.size(1),
+                                                  dy.stride(0), x.stride(0), static_cast<float>(scale),
+                                                  c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), true);
+  return torch::from_blob(const_cast<void*>(wavg), {w.size(0), w.size(1)}, w.options().requires_grad(false));
+}
+
+// Forward + fused MSE epilogue against weights that are ALREADY averaged (no collective):
+// (dL/dy, loss[1]).  Pairs with wgrad_allreduce_sgd_prefetch_.
+std::tuple<Tensor, Tensor> linear_mse_forward_local(const Tensor& x, const Tensor& w_avg, const Tensor& target,
+                                                    double loss_scale, double grad_scale) {
+  check_2d_bf16(x, "x");
+  check_2d_bf16(w_avg, "w_avg");
+  check_2d_bf16(target, "target");
+  TORCH_CHECK(x.size(1) == w_avg.size(1) && target.size(0) == x.size(0) && target.size(1) == w_avg.size(0),
+              "mpi4torch_b200: linear_mse_forward_local shape mismatch");
+  c10::cuda::CUDAGuard guard(x.device());
+  cudaStream_t stream = c10::cuda::getCurrentCUDAStream(x.device().index()).stream();
+  Tensor dy = at::empty({x.size(0), w_avg.size(0)}, x.options());
+  Tensor loss = at::zeros({1}, x.options().dtype(at::kFloat));
+  MseEpilogue mse;
+  mse.target = target.data_ptr();
+  mse.ldt = target.stride(0);
+  mse.loss_acc = loss.data_ptr<float>();
+  mse.loss_scale = static_cast<float>(loss_scale);
+  mse.grad_scale = static_cast<float>(grad_scale);
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  backend().gemm_bf16_tn(x.data_ptr(), w_avg.data_ptr(), dy.data_ptr(), x.size(0), w_avg.size(0), x.size(1), x.stride(0),
+                         w_avg.stride(0), dy.stride(0), stream, &mse);
+  return {dy, loss};
 }
 
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
+  m.def("wgrad_allreduce_sgd_prefetch_(Tensor(a!) w, Tensor dy, Tensor x, float scale) -> Tensor", &wgrad_allreduce_sgd_prefetch_);
+  m.def("linear_mse_forward_local(Tensor x, Tensor w_avg, Tensor target, float loss_scale, float grad_scale) -> (Tensor, Tensor)",
+        &linear_mse_forward_local);
   m.def("wgrad_bf16(Tensor dy, Tensor x) -> Tensor", &wgrad_bf16);
   m.def("wgrad_bf16_supported(Tensor dy, Tensor x) -> bool", &wgrad_bf16_ok);
   m.def("wgrad_allreduce_sgd_supported(Tensor w, Tensor dy, Tensor x) -> bool", &wgrad_allreduce_sgd_supported);

@@ -130,7 +130,9 @@ int fused_wgrad_signals_per_tile(int ksplit);
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
-                               uint32_t done_target, float scale, cudaStream_t stream);
+                               uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream);
+// wavg_off >= 0: additionally leaves (1/P) * sum_ranks W_new in the bf16 [N,K] buffer at that heap
+// offset on every rank (the parameter all-reduce of the NEXT forward, run under this GEMM).
 // Plain device copy into the heap (used to stage the weight for the fused kernel).
 void launch_copy_bytes(void* dst, const void* src, int64_t bytes, int sm_count, cudaStream_t stream);
 

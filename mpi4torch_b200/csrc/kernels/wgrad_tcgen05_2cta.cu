@@ -80,6 +80,10 @@ struct WgradComm {
   uint32_t tile_target;
   uint32_t done_target;
   float scale;           // W += scale * sum_ranks G   (scale = -lr / P)
+  // optional: all-reduce the UPDATED weights for the next forward while the GEMM is still running
+  int prefetch;          // 1: W_avg[tile] = avg_scale * sum_ranks W[tile] after the update of the tile
+  int64_t wavg_off;      // bf16 [N, K] buffer receiving the averaged weights on every rank
+  float avg_scale;       // 1 / P
 };
 
 struct __align__(8) Bars {
@@ -174,6 +178,32 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 #pragma unroll
           for (int e = 0; e < 8; ++e) wv[e] = fmaf(wc.scale, a[e], wv[e]);
           multimem_st_vec(wc.mc_heap + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
+        }
+      }
+    }
+    if (wc.prefetch) {
+      // Next step's forward needs Allreduce(W) / P.  The rows this lane just multicast are final on
+      // every rank once its stores are performed system-wide, so the parameter all-reduce of the
+      // NEXT step can run here, under the GEMM of later tiles: same rows, same lane -> a per-thread
+      // fence orders the multimem.st above before the multimem.ld_reduce below.
+      __threadfence_system();
+      for (int row0 = cw; row0 < BMC; row0 += kCommWarps * kU) {
+        Vec16 x[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int row = row0 + u * kCommWarps;
+          if (row < BMC) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + tile_off + row * row_bytes);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int row = row0 + u * kCommWarps;
+          if (row < BMC) {
+            float a[8];
+            VecOf<DType::BF16>::unpack(x[u], a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] *= wc.avg_scale;
+            multimem_st_vec(wc.mc_heap + wc.wavg_off + tile_off + row * row_bytes, VecOf<DType::BF16>::pack(a));
+          }
         }
       }
     }
@@ -424,7 +454,7 @@ int fused_wgrad_signals_per_tile(int ksplit) { return kSignalsPerUnit * ksplit; 
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
-                               uint32_t done_target, float scale, cudaStream_t stream) {
+                               uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream) {
   M4T_CHECK(dc.mc_heap != nullptr, "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping");
   M4T_CHECK(ksplit == 1 || ksplit == 2, "ksplit must be 1 or 2");
   M4T_CHECK((Mb / BK) % ksplit == 0, "batch / 64 must be divisible by ksplit");
@@ -452,6 +482,9 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.tile_target = tile_target;
   wc.done_target = done_target;
   wc.scale = scale;
+  wc.prefetch = wavg_off >= 0 ? 1 : 0;
+  wc.wavg_off = wavg_off >= 0 ? wavg_off : 0;
+  wc.avg_scale = 1.0f / static_cast<float>(dc.sync.size);
   const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
   configure_w<true>();
   wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, wc);

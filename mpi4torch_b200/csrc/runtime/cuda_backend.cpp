@@ -381,12 +381,13 @@ bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, in
   const char* wb = static_cast<const char*>(w);
   const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
   if (!(wb >= arena && wb + N * K * 2 <= arena + symm_bytes_)) return false;  // must be switch-visible in place
-  const int64_t need = 2 * N * K * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;
+  const int64_t need = 3 * N * K * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;  // 2 partial buffers + W_avg prefetch
   return wgrad_.count((N << 32) | K) > 0 || symm_cursor_ + need <= symm_bytes_;
 }
 
-void CudaBackend::fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
-                                     int64_t ldy, int64_t ldx, float scale, cudaStream_t stream) {
+const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
+                                            int64_t ldy, int64_t ldx, float scale, cudaStream_t stream,
+                                            bool prefetch_avg) {
   check_device_error();
   M4T_CHECK(fused_wgrad_available(w, Mb, N, K), "fused wgrad->Allreduce->SGD unavailable for N=" << N << " K=" << K
                                                     << " (needs NVLS, M4T_FUSED_WGRAD=1 and a symmetric weight)");
@@ -404,6 +405,7 @@ void CudaBackend::fused_wgrad_update(void* w, const void* dy, const void* x, int
     it = wgrad_.emplace(key, st).first;  // the arena is zero-initialised: counters start at 0
   }
   FusedWgradState& st = it->second;
+  if (prefetch_avg && st.wavg_off < 0) st.wavg_off = symm_alloc(N * K * 2);  // same call sequence on every rank
   chain(stream);
   const int64_t w_off = static_cast<const char*>(w) - dc_.heap[dc_.sync.rank];
   st.calls += 1;
@@ -411,7 +413,9 @@ void CudaBackend::fused_wgrad_update(void* w, const void* dy, const void* x, int
                                                      static_cast<uint64_t>(size()));
   const uint32_t done_target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
   launch_fused_wgrad_update(dc_, dy, x, Mb, N, K, ldy, ldx, w_off, st.stage_off, st.stage_stride, st.cnt_off,
-                            st.done_off, st.ksplit, tile_target, done_target, scale, stream);
+                            st.done_off, st.ksplit, tile_target, done_target, scale, prefetch_avg ? st.wavg_off : -1,
+                            stream);
+  return prefetch_avg ? symm_ptr(st.wavg_off) : nullptr;
 }
 
 // ---------------------------------------------------------------------------

@@ -78,8 +78,10 @@ class CudaBackend final : public Backend {
   // in-switch reduce-scatter + SGD update + multicast of the new weights).  `w` must come from
   // symmetric_alloc() and be replicated across ranks.
   bool fused_wgrad_available(const void* w, int64_t Mb, int64_t N, int64_t K) const;
-  void fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
-                          int64_t ldx, float scale, cudaStream_t stream);
+  // prefetch_avg: also all-reduce the updated weights (x 1/size) into a symmetric buffer whose
+  // address is returned - the next forward can then run as a plain local GEMM.
+  const void* fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
+                                 int64_t ldx, float scale, cudaStream_t stream, bool prefetch_avg = false);
 
   // Throws if a device-side wait timed out since the last check.
   void check_device_error();
@@ -149,7 +151,7 @@ class CudaBackend final : public Backend {
   };
   std::unordered_map<int64_t, FusedLinearState> fused_;  // key = N << 32 | K
   struct FusedWgradState {
-    int64_t stage_off = 0, stage_stride = 0, cnt_off = 0, done_off = 0;
+    int64_t stage_off = 0, stage_stride = 0, cnt_off = 0, done_off = 0, wavg_off = -1;
     int ksplit = 1;
     uint64_t calls = 0;
   };

@@ -45,6 +45,10 @@ class DPLinearModel:
         self.overlap_slices = overlap_slices  # wgrad/allreduce pipelining granularity (fast path)
         self.overlap_blocks = 32              # CTAs of the overlapped allreduce (small footprint under the GEMM)
         self.fused_wgrad = os.environ.get("M4T_FUSED_WGRAD", "0") not in ("", "0")  # experimental backward fusion
+        # experimental, needs fused_wgrad: the backward kernel also all-reduces the UPDATED weights, so the
+        # next forward starts as a plain local GEMM (its parameter Allreduce already ran under the wgrad GEMM)
+        self.wavg_prefetch = os.environ.get("M4T_WAVG_PREFETCH", "0") not in ("", "0")
+        self._wavg_next = None  # Allreduce(weight)/size produced by the previous fused backward, if any
         self._side = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -68,15 +72,23 @@ class DPLinearModel:
         scalar loss Allreduce, wgrad GEMM, gradient Allreduce with SGD epilogue."""
         c = self.comm
         B = x.shape[0]
-        dy, local, _w_avg = torch.ops.mpi4torch_b200.linear_mse_forward(
-            x, self.weight, target, 1.0 / c.size, 1.0 / (B * c.size), 2.0 / B, self.fused)
+        if self._wavg_next is not None:
+            w_avg, self._wavg_next = self._wavg_next, None
+            dy, local = torch.ops.mpi4torch_b200.linear_mse_forward_local(x, w_avg, target, 1.0 / (B * c.size), 2.0 / B)
+        else:
+            dy, local, _w_avg = torch.ops.mpi4torch_b200.linear_mse_forward(
+                x, self.weight, target, 1.0 / c.size, 1.0 / (B * c.size), 2.0 / B, self.fused)
         loss = c.Allreduce(local, m4t.MPI_SUM)
         n_out = self.weight.shape[0]
         slices = self.overlap_slices if (c.size > 1 and n_out % max(self.overlap_slices, 1) == 0) else 1
         if self.fused_wgrad and torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_supported(self.weight, dy, x):
             # experimental (M4T_FUSED_WGRAD=1): wgrad GEMM + gradient reduce-scatter in the switch +
             # SGD update + multicast of the new weights as ONE tcgen05 kernel
-            torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(self.weight, dy, x, -self.lr / c.size)
+            if self.wavg_prefetch:
+                self._wavg_next = torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_prefetch_(self.weight, dy, x,
+                                                                                      -self.lr / c.size)
+            else:
+                torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(self.weight, dy, x, -self.lr / c.size)
             return loss[0]
         if c.size == 1:
             # single rank: nothing to reduce - the SGD update is the GEMM's own epilogue
@@ -107,10 +119,15 @@ class DPLinearModel:
         main.wait_stream(side)
         return loss[0]
 
+    def invalidate_prefetch(self) -> None:
+        """Call after modifying ``weight`` by hand: drops the prefetched parameter average."""
+        self._wavg_next = None
+
     def train_step(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """forward + backward + SGD update; returns the (global) loss tensor."""
         if self._fast_path_ok(x, target):
             return self._train_step_fast(x, target)
+        self._wavg_next = None  # the weights are about to change outside the fused backward
         self.weight.grad = None
         value = self.loss(x, target)
         value.backward()

@@ -243,6 +243,17 @@ class TestFusedTrainingStep(unittest.TestCase):
             torch.cuda.synchronize()
             self.assertLess((w.float() - ref_w.float()).abs().max().item(), 2e-2, f"step {step}")
             self.assertTrue(torch.equal(w, comm.Bcast_(w.detach().clone(), 0)))
+        # prefetch variant: also returns Allreduce(w_new) / P
+        dy = torch.randn(Mb, N, generator=gr).to(torch.bfloat16).to(DEVICE)
+        x = torch.randn(Mb, K, generator=gr).to(torch.bfloat16).to(DEVICE)
+        w_avg = torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_prefetch_(w, dy, x, -0.01 / P)
+        torch.cuda.synchronize()
+        expect = comm.AllreduceFused(w.detach().clone(), m4t.MPI_SUM, 1.0 / P, None)
+        self.assertLess((w_avg.float() - expect.float()).abs().max().item(), 1e-2)
+        t = torch.randn(Mb, N, generator=gr).to(torch.bfloat16).to(DEVICE)
+        dy2, loss2 = torch.ops.mpi4torch_b200.linear_mse_forward_local(x, w_avg, t, 1.0, 1.0)
+        ref = (x.float() @ w_avg.float().t() - t.float())
+        self.assertLess(abs(float(loss2) - float(ref.square().sum())) / float(ref.square().sum()), 2e-2)
 
     def test_allreduce_axpy_in_place(self):
         p = torch.full((1000,), 2.0, dtype=torch.float32, device=DEVICE)
