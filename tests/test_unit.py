@@ -73,3 +73,47 @@ def test_host_staging_toggle_exists():
     x = torch.rand(4)
     assert torch.equal(m4t.COMM_WORLD.Allreduce(x, m4t.MPI_SUM), x)
     m4t.activate_nvlink_transport()
+
+
+def test_numa_binding_is_a_noop_without_cuda():
+    from mpi4torch_b200.utils import bind_to_gpu_numa
+
+    if torch.cuda.is_available():
+        return
+    report = bind_to_gpu_numa(0)
+    assert report["bound"] is False and "reason" in report
+
+
+def test_launcher_shares_cores_between_ranks(tmp_path):
+    import os
+    import subprocess
+    import sys
+
+    script = tmp_path / "omp.py"
+    script.write_text("import os\nprint('OMP', os.environ.get('OMP_NUM_THREADS'), flush=True)\n")
+    env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+    out = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", str(script)], env=env,
+                         capture_output=True, text=True, timeout=120, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert out.returncode == 0, out.stderr
+    cores = len(os.sched_getaffinity(0))
+    assert out.stdout.count(f"OMP {max(1, cores // 2)}") == 2, out.stdout
+    env["OMP_NUM_THREADS"] = "3"  # an explicit setting wins
+    out = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", str(script)], env=env,
+                         capture_output=True, text=True, timeout=120, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert out.stdout.count("OMP 3") == 2, out.stdout
+
+
+def test_single_rank_split_and_free():
+    comm = m4t.COMM_WORLD
+    sub = comm.Split(0, 0)
+    assert sub.size == 1 and sub.rank == 0 and not sub.is_world and comm.is_world
+    x = torch.rand(3, dtype=torch.double, requires_grad=True)
+    sub.Allreduce(x, m4t.MPI_SUM).sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    sub.Free()
+    try:
+        sub.Barrier()
+    except RuntimeError as exc:
+        assert "freed" in str(exc)
+    else:
+        raise AssertionError("a freed communicator must raise")
