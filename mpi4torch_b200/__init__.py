@@ -332,20 +332,32 @@ def symmetric_empty(shape, dtype=torch.float32) -> torch.Tensor:
 
 
 def comm_from_mpi4py(comm) -> MPI_Communicator:
-    """Interop shim for code written against ``mpi4torch.comm_from_mpi4py``.
+    """Interop for code written against ``mpi4torch.comm_from_mpi4py``
+    (reference ``src/__init__.py:247-261``).
 
-    There is no MPI underneath this library, so only a communicator that is
-    congruent with the launcher's world (same size and rank) can be converted
-    (reference ``src/__init__.py:247-261`` converts any mpi4py communicator).
+    There is no MPI underneath this library; the mpi4py communicator is only
+    used to learn the group.  A communicator congruent with the launcher's
+    world maps to :data:`COMM_WORLD`.  Any other communicator is rebuilt with
+    :meth:`MPI_Communicator.Split` (colour = smallest world rank of the group,
+    key = rank inside ``comm``) - which is collective over the WORLD, so every
+    world rank must call ``comm_from_mpi4py`` at the same point with its own
+    group, exactly as they all took part in the ``comm.Split`` that created
+    these groups.
     """
     try:
         size, rank = comm.Get_size(), comm.Get_rank()
     except AttributeError as exc:  # pragma: no cover
         raise RuntimeError("mpi4py is not available!") from exc
     world = __getattr__("COMM_WORLD") if "COMM_WORLD" not in globals() else globals()["COMM_WORLD"]
-    if size != world.size or rank != world.rank:
+    if size == world.size and rank == world.rank:
+        return world
+    if not hasattr(comm, "allgather"):
         raise RuntimeError(
-            "mpi4torch_b200 only supports the world communicator: the mpi4py communicator has "
-            f"rank {rank}/{size} but this process is rank {world.rank}/{world.size}"
-        )
-    return world
+            "mpi4torch_b200: the communicator has "
+            f"rank {rank}/{size} but this process is rank {world.rank}/{world.size}, and it offers no "
+            "allgather() to discover its members")
+    members = [int(r) for r in comm.allgather(world.rank)]
+    sub = world.Split(min(members), rank)
+    if sub.size != size or sub.rank != rank:
+        raise RuntimeError(f"mpi4torch_b200: rebuilt communicator is {sub.rank}/{sub.size}, expected {rank}/{size}")
+    return sub

@@ -81,6 +81,9 @@ TORCH_LIBRARY(mpi4torch_b200, m) {
                     return comm_world();
                   });
   m.def("COMM_WORLD", &comm_world);
+  // The reference converts an MPI Fortran handle (csrc/extension.cpp:165-172).  There is no MPI
+  // here, hence no handle space: the op exists for API parity and returns the world communicator.
+  m.def("comm_from_fortran", [](int64_t) { return comm_world(); });
   m.def("JoinDummies(Tensor loopthrough, Tensor[] dummies) -> Tensor",
         [](const Tensor& loopthrough, std::vector<Tensor> dummies) { return JoinDummies(loopthrough, dummies); });
 }

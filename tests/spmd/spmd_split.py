@@ -99,6 +99,28 @@ class TestSplit(unittest.TestCase):
         rs = sub.Reduce_scatter(torch.ones(S, 2, dtype=torch.double, device=DEVICE), m4t.MPI_SUM, 0, 1)
         self.assertTrue(torch.equal(rs, torch.full((1, 2), float(S), dtype=torch.double, device=DEVICE)))
 
+    def test_comm_from_mpi4py_rebuilds_groups(self):
+        members = [p for p in range(P) if p % 2 == R % 2]
+
+        class FakeSubComm:  # what an mpi4py communicator from COMM_WORLD.Split(rank % 2) offers
+            def Get_size(self):
+                return len(members)
+
+            def Get_rank(self):
+                return members.index(R)
+
+            def allgather(self, value):
+                assert value == R
+                return list(members)
+
+        sub = m4t.comm_from_mpi4py(FakeSubComm())
+        self.assertEqual((sub.rank, sub.size), (members.index(R), len(members)))
+        if P > 1:
+            self.assertFalse(sub.is_world)
+        y = sub.Allreduce(torch.full((2,), float(R), dtype=torch.double, device=DEVICE), m4t.MPI_SUM)
+        self.assertEqual(float(y[0]), float(sum(members)))
+        self.assertEqual(torch.ops.mpi4torch_b200.comm_from_fortran(0).GetSize(), P)
+
     def test_errors(self):
         lone = comm.Split(-1 if R == 0 else 0, 0)  # MPI_UNDEFINED: rank 0 stays alone
         self.assertEqual(lone.size, 1 if R == 0 else P - 1)
