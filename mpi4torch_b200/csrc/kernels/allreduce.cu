@@ -44,6 +44,8 @@ struct ArArgs {
   int64_t slot_bytes;  // ONESHOT: bytes per rank slot
   int aligned;         // in/out/acc 16-byte aligned
   int skip_mask;       // debug only (M4T_AR_DEBUG_SKIP): bit0 skip phase A, bit1 B, bit2 C
+  int64_t sym_in_off;  // >= 0: the input already lives at this heap offset on every rank (zero copy:
+                       // phase A is skipped and peers / the switch read the tensor in place)
 };
 
 template <DType DT, ReduceOp OP>
@@ -100,8 +102,10 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
   const int P = c.size, r = c.rank;
   const bool al = a.aligned != 0;
   // staging half: [ in copy : nvec*16 ][ reduced out : nvec*16 ]
-  const int64_t in_off = a.stage_off + static_cast<int64_t>(par) * a.half_bytes;
-  const int64_t out_off = in_off + ((a.nvec * 16 + 127) / 128) * 128;
+  const int64_t stage_in = a.stage_off + static_cast<int64_t>(par) * a.half_bytes;
+  const bool zero_copy = a.sym_in_off >= 0;
+  const int64_t in_off = zero_copy ? a.sym_in_off : stage_in;
+  const int64_t out_off = stage_in + ((a.nvec * 16 + 127) / 128) * 128;
   char* my_in = a.heap[r] + in_off;
   char* my_out = a.heap[r] + out_off;
   const int64_t gstride = static_cast<int64_t>(gridDim.x) * kThreads;
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ArArg
     const int64_t nw = first < L ? (L - first + gstride - 1) / gstride : 0;
     const int64_t nitems = nw * P;
     // ---- phase A: stage my part of every shard (block b owns pattern b of each shard)
-    for (int64_t j0 = (a.skip_mask & 1) ? nitems : 0; j0 < nitems; j0 += kUnroll) {
+    for (int64_t j0 = ((a.skip_mask & 1) || zero_copy) ? nitems : 0; j0 < nitems; j0 += kUnroll) {
       Vec16 v[kUnroll];
       int64_t idx[kUnroll];
 #pragma unroll
@@ -522,7 +526,8 @@ void launch_local_epilogue(const void* in, void* out, int64_t n, DType dt, Reduc
 }
 
 void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n, DType dt, ReduceOp op,
-                      const Epilogue& epi, ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream) {
+                      const Epilogue& epi, ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream,
+                      int64_t sym_in_off) {
   check_op_dtype(op, dt);
   M4T_CHECK(algo == ArAlgo::ONESHOT || algo == ArAlgo::TWOSHOT || algo == ArAlgo::NVLS,
             "launch_allreduce needs a concrete algorithm");
@@ -540,6 +545,7 @@ void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n
   a.slot_bytes = ((a.nvec * 16 + 127) / 128) * 128;
   a.aligned = is_aligned16(in) && is_aligned16(out) && (!epi.accumulate || is_aligned16(epi.accumulate));
   a.skip_mask = static_cast<int>(env_i64("M4T_AR_DEBUG_SKIP", 0));
+  a.sym_in_off = -1;
   M4T_CHECK(allreduce_stage_bytes(n, dt, algo, dc.sync.size) <= dc.half_bytes,
             "allreduce of " << n << " elements does not fit the staging half (" << dc.half_bytes << " B)");
   blocks = std::max(1, std::min(blocks, kMaxChannels));
@@ -560,6 +566,8 @@ void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n
   // Pipelined role-split kernels: one 1024-thread CTA per SM, >= 2 chunks to overlap.
   const bool pipelined = env_i64("M4T_AR_PIPE", 1) != 0 && a.nvec > a.chunk_vecs;
   if (pipelined) blocks = std::min(blocks, dc.sm_count);
+  // zero copy: single-chunk kernels only (the chunk loop of the two-shot kernel indexes one buffer)
+  if (!pipelined && a.nvec <= a.chunk_vecs && sym_in_off >= 0 && (sym_in_off & 15) == 0) a.sym_in_off = sym_in_off;
   if (algo == ArAlgo::NVLS) {
     M4T_CHECK(dc.mc_heap != nullptr, "NVLS allreduce requested but no multicast mapping exists");
     if (pipelined) launch_nvls_pipelined(nvls_kind(dt, op), a, blocks, stream);

@@ -38,8 +38,11 @@ bool nvls_supported(DType dt, ReduceOp op);
 int64_t allreduce_stage_bytes(int64_t n, DType dt, ArAlgo algo, int size);
 
 // out = epilogue(reduce over ranks of in).  One launch.
+// sym_in_off >= 0: `in` is this rank's instance of a symmetric tensor at that heap offset (the
+// same on every rank); two-shot / NVLS kernels then read it in place instead of staging it.
 void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n, DType dt, ReduceOp op,
-                      const Epilogue& epi, ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream);
+                      const Epilogue& epi, ArAlgo algo, int blocks, int64_t chunk_bytes, cudaStream_t stream,
+                      int64_t sym_in_off = -1);
 
 // World-size-1 / local form: out = epilogue(normalise(in)); also the copy kernel.
 void launch_local_epilogue(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,

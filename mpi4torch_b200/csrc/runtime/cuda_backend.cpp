@@ -196,8 +196,17 @@ void CudaBackend::allreduce_algo(const void* in, void* out, int64_t n, DType dt,
     const int64_t cnt = std::min(max_elems, n - off);
     Epilogue e = epi;
     if (e.accumulate) e.accumulate = static_cast<const char*>(e.accumulate) + off * es;
+    // experimental (M4T_ZERO_COPY_IN=1): an input inside the symmetric user arena is read in place.
+    // Contract: if one rank passes a symmetric tensor, every rank passes its instance of the same one.
+    static const bool zero_copy = env_i64("M4T_ZERO_COPY_IN", 0) != 0;
+    int64_t sym_off = -1;
+    if (zero_copy) {
+      const char* ib = static_cast<const char*>(in) + off * es;
+      const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
+      if (ib >= arena && ib + round_up64(cnt * es, 16) <= arena + symm_bytes_) sym_off = ib - dc_.heap[dc_.sync.rank];
+    }
     launch_allreduce(dc_, static_cast<const char*>(in) + off * es, static_cast<char*>(out) + off * es, cnt, dt, op, e,
-                     algo, blocks, chunk_bytes, stream);
+                     algo, blocks, chunk_bytes, stream, sym_off);
   }
 }
 

@@ -42,6 +42,8 @@ if [ "$NP" -gt 1 ]; then
   echo "=== bench with fused backward + prefetched parameter average np=$NP"
   M4T_FUSED_WGRAD=2 M4T_WAVG_PREFETCH=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus $NP --steps 20 --warmup 5 --no-extras > $OUT/exp_bench_prefetch_n$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" $OUT/exp_bench_prefetch_n$NP.log | tail -1 | cut -c1-900
+  echo "=== zero-copy symmetric allreduce inputs np=$NP"
+  M4T_TEST_DEVICE=cuda M4T_ZERO_COPY_IN=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_gpu.py 2>&1 | grep -v "^W0" | tail -3
   echo "=== multicast-push Allgather np=$NP"
   M4T_TEST_DEVICE=cuda M4T_AG_PUSH=1 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_collectives.py > $OUT/exp_agpush_np$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0" $OUT/exp_agpush_np$NP.log | tail -4 | cut -c1-400

@@ -255,6 +255,19 @@ class TestFusedTrainingStep(unittest.TestCase):
         ref = (x.float() @ w_avg.float().t() - t.float())
         self.assertLess(abs(float(loss2) - float(ref.square().sum())) / float(ref.square().sum()), 2e-2)
 
+    @unittest.skipUnless(os.environ.get("M4T_ZERO_COPY_IN", "0") == "1", "zero-copy symmetric inputs: set M4T_ZERO_COPY_IN=1")
+    def test_zero_copy_symmetric_input(self):
+        if P < 2:
+            return
+        for dt, n in ((torch.bfloat16, 3 * 1024 * 1024 + 8), (torch.float32, 1 << 20), (torch.float64, 70001)):
+            x = m4t.symmetric_empty((n,), dt)
+            src = make(R, n, dt, seed=9).to(DEVICE)
+            x.copy_(src)
+            y = comm.Allreduce(x, m4t.MPI_SUM)
+            ref = comm.Allreduce(src, m4t.MPI_SUM)  # staged path, same kernels otherwise
+            self.assertTrue(torch.equal(y, ref), str(dt))
+            self.assertTrue(torch.equal(x, src), "input must be untouched")
+
     def test_allreduce_axpy_in_place(self):
         p = torch.full((1000,), 2.0, dtype=torch.float32, device=DEVICE)
         gsrc = torch.full((1000,), float(R + 1), dtype=torch.float32, device=DEVICE)
