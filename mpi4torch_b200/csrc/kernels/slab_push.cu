@@ -94,9 +94,7 @@ bool launch_allgather_push(const DeviceComm& dc, const PullPlan& plan, const voi
     if (j.peer == dc.sync.rank) mine = &j;
   auto al16 = [](int64_t v) { return (v & 15) == 0; };
   const int64_t out_bytes = plan.out_elems * es;
-  if (!al16(reinterpret_cast<intptr_t>(in)) || !al16(reinterpret_cast<intptr_t>(out)) || !al16(out_bytes) ||
-      out_bytes > dc.half_bytes)
-    return false;
+  if (!al16(out_bytes) || out_bytes > dc.half_bytes) return false;  // rank-independent (replicated output)
   // eligibility must be decided identically on every rank: all slabs share the
   // same `after` stride pattern, so checking the global quantities suffices
   for (const auto& j : plan.jobs) {
@@ -104,6 +102,11 @@ bool launch_allgather_push(const DeviceComm& dc, const PullPlan& plan, const voi
     for (int k = 0; k < 3; ++k)
       if (j.n[k] > 1 && (!al16(j.ss[k] * es) || !al16(j.ds[k] * es))) return false;
   }
+  // Everything above is identical on every rank, so all ranks take the same path.  Pointer
+  // alignment is rank-local: it cannot select a different algorithm without desynchronising
+  // the ranks, so it is a hard requirement of the opt-in path.
+  M4T_CHECK(al16(reinterpret_cast<intptr_t>(in)) && al16(reinterpret_cast<intptr_t>(out)),
+            "M4T_AG_PUSH needs 16-byte aligned input and output tensors");
   PushArgs a{};
   a.sync = dc.sync;
   a.mc_heap = dc.mc_heap;
