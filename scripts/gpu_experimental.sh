@@ -14,6 +14,8 @@ if [ "$NP" -gt 1 ]; then
   echo "=== fused wgrad -> reduce-scatter -> SGD -> multicast np=$NP"
   M4T_TEST_DEVICE=cuda M4T_FUSED_WGRAD=2 timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_gpu.py > $OUT/exp_fwgrad_np$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0" $OUT/exp_fwgrad_np$NP.log | tail -6 | cut -c1-400
+  echo "=== randomised traffic patterns np=$NP"
+  M4T_TEST_DEVICE=cuda timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_stress.py 2>&1 | grep -v "^W0" | tail -3
   echo "=== side-stream bucketed gradient sync np=$NP"
   M4T_TEST_DEVICE=cuda timeout 600 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py spmd_parallel.py > $OUT/exp_parallel_np$NP.log 2>&1
   echo "exit=$?"; grep -v "^W0" $OUT/exp_parallel_np$NP.log | tail -4 | cut -c1-400
