@@ -187,6 +187,8 @@ def main() -> int:
             "per_gpu_batch": B,
             "cold_cache": f"inputs rotate over {POOL} batches (>= {POOL * 2 * B * IN_F * 2 >> 20} MiB) > 126 MB L2",
             "fused_forward": bool(model.fused and size > 1),
+            "fused_backward": bool(model.fused_wgrad and size > 1),
+            "prefetched_param_allreduce": bool(model.wavg_prefetch and model.fused_wgrad and size > 1),
             "heap_mode": m4t.heap_mode(),
             "nvls": m4t.has_nvls(),
             "numa_bind": numa,
