@@ -28,3 +28,12 @@ def test_dp_linear_example_loss_decreases_cpu():
     assert res.returncode == 0, res.stderr[-4000:]
     losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
     assert len(losses) == 8 and losses[-1] < losses[0]
+
+
+def test_tensor_parallel_mlp_example_2d_parallelism_cpu():
+    res = run_spmd(4, ["examples/tensor_parallel_mlp.py", "--tp", "2", "--device", "cpu", "--steps", "30"], device="cpu",
+                   timeout=300)
+    assert res.returncode == 0, res.stderr[-4000:]
+    losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
+    assert len(losses) >= 3 and losses[-1] < 0.7 * losses[0], losses
+    assert "(tp=2, dp=2)" in res.stdout
