@@ -85,3 +85,18 @@ def test_jobs_are_coalesced_for_contiguous_cases():
     # Gather of whole leading slabs (before == 1) must collapse to ONE contiguous run per peer
     jobs, _s, _n = _C.plan_gather(0, 4, 0, 1, 8, [5, 5, 5, 5], True)
     assert all(j["n"] == (1, 1, 1) and j["run"] == 40 for j in jobs)
+
+
+@pytest.mark.parametrize("size", [2, 4, 8])
+def test_pull_plans_never_aim_two_readers_at_one_source(size):
+    """All ranks walk their job lists in lock step (same item order in the kernel): at every
+    position the sources must be pairwise distinct, and every rank starts with its own slab."""
+    gather = [_C.plan_gather(r, size, 0, 2, 3, [4] * size, True)[0] for r in range(size)]
+    shape = [2 * size, 3 * size]
+    a2a = [_C.plan_alltoall(r, size, shape, 0, 1, [2 * size] * size, [3] * size)[0] for r in range(size)]
+    for plans in (gather, a2a):
+        assert all(len(p) == size for p in plans)
+        for k in range(size):
+            peers = [plans[r][k]["peer"] for r in range(size)]
+            assert sorted(peers) == list(range(size)), (k, peers)
+        assert [plans[r][0]["peer"] for r in range(size)] == list(range(size))
