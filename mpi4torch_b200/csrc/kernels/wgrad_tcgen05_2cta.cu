@@ -136,26 +136,33 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   const int lane = ct & 31;
   const int cw = ct >> 5;
   constexpr int kCommThreads = kCommWarps * 32;
-  constexpr int kU = 4;  // rows in flight per warp (independent switch round trips)
+  constexpr int kU = 8;         // rows in flight per warp (independent switch round trips)
+  constexpr int kRowSplit = 2;  // CTA pairs sharing one owned tile: shortens the tail after the last GEMM wave
+  constexpr int kRows = BMC / kRowSplit;  // rows of this CTA's half handled per work item
   const uint32_t* my_cnt = reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.cnt_off);
   const int64_t row_bytes = static_cast<int64_t>(K) * 2;
-  // j-th owned tile (t = r + j*P) is served by cluster j % num_clusters: owned tiles finish in
-  // GEMM order, so consecutive ones land on different CTA pairs and their round trips overlap.
-  for (int j = cluster_id; r + j * P < num_tiles; j += num_clusters) {
+  // Work item w = (j-th owned tile, row slice s); item w is served by cluster w % num_clusters.
+  // Owned tiles (t = r + j*P) finish in GEMM order, so consecutive items land on different CTA
+  // pairs and their switch round trips overlap; with 256 tiles / 8 ranks x 2 slices = 64 items
+  // almost every pair of the 74 has at most one.
+  const int owned = r < num_tiles ? (num_tiles - r + P - 1) / P : 0;
+  for (int w_item = cluster_id; w_item < owned * kRowSplit; w_item += num_clusters) {
+    const int j = w_item / kRowSplit;
+    const int slice = w_item - j * kRowSplit;
     const int t = r + j * P;
     if (lane == 0) bounded_wait_ge(my_cnt + t, wc.tile_target, c);
     __syncwarp();
     const int n_blk = t / k_tiles;
     const int k_blk = t - n_blk * k_tiles;
-    // this CTA's half of the tile: 128 rows x 512 bytes, one row per warp pass
-    const int64_t tile_off = (static_cast<int64_t>(n_blk) * BM2 + static_cast<int64_t>(cta) * BMC) * row_bytes +
+    // this CTA's rows of the item: kRows rows x 512 bytes, one row per warp pass
+    const int64_t tile_off = (static_cast<int64_t>(n_blk) * BM2 + static_cast<int64_t>(cta) * BMC + slice * kRows) * row_bytes +
                              static_cast<int64_t>(k_blk) * BN * 2 + lane * 16;
-    for (int row0 = cw; row0 < BMC; row0 += kCommWarps * kU) {
+    for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
       Vec16 s0[kU], s1[kU], w[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int row = row0 + u * kCommWarps;
-        if (row < BMC) {
+        if (row < kRows) {
           const int64_t off = tile_off + row * row_bytes;
           s0[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
           if (ksplit > 1) s1[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
@@ -165,7 +172,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int row = row0 + u * kCommWarps;
-        if (row < BMC) {
+        if (row < kRows) {
           const int64_t off = tile_off + row * row_bytes;
           float a[8], b[8], wv[8];
           VecOf<DType::BF16>::unpack(s0[u], a);
@@ -187,17 +194,17 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
       // NEXT step can run here, under the GEMM of later tiles: same rows, same lane -> a per-thread
       // fence orders the multimem.st above before the multimem.ld_reduce below.
       __threadfence_system();
-      for (int row0 = cw; row0 < BMC; row0 += kCommWarps * kU) {
+      for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
         Vec16 x[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int row = row0 + u * kCommWarps;
-          if (row < BMC) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + tile_off + row * row_bytes);
+          if (row < kRows) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + tile_off + row * row_bytes);
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int row = row0 + u * kCommWarps;
-          if (row < BMC) {
+          if (row < kRows) {
             float a[8];
             VecOf<DType::BF16>::unpack(x[u], a);
 #pragma unroll
