@@ -90,17 +90,23 @@ def test_launcher_shares_cores_between_ranks(tmp_path):
     import sys
 
     script = tmp_path / "omp.py"
-    script.write_text("import os\nprint('OMP', os.environ.get('OMP_NUM_THREADS'), flush=True)\n")
+    # one file per rank: nothing to interleave on a shared pipe
+    script.write_text("import os, sys\n"
+                      "open(os.path.join(sys.argv[1], 'rank' + os.environ['RANK']), 'w').write(os.environ.get('OMP_NUM_THREADS', 'unset'))\n")
+    root = os.path.dirname(os.path.dirname(__file__))
+
+    def run(env, out_dir):
+        os.makedirs(out_dir, exist_ok=True)
+        res = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", str(script), str(out_dir)], env=env,
+                             capture_output=True, text=True, timeout=300, cwd=root)
+        assert res.returncode == 0, f"stdout:\n{res.stdout}\nstderr:\n{res.stderr}"
+        return [open(os.path.join(out_dir, f"rank{r}")).read() for r in range(2)]
+
     env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
-    out = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", str(script)], env=env,
-                         capture_output=True, text=True, timeout=120, cwd=os.path.dirname(os.path.dirname(__file__)))
-    assert out.returncode == 0, out.stderr
     cores = len(os.sched_getaffinity(0))
-    assert out.stdout.count(f"OMP {max(1, cores // 2)}") == 2, out.stdout
+    assert run(env, tmp_path / "auto") == [str(max(1, cores // 2))] * 2
     env["OMP_NUM_THREADS"] = "3"  # an explicit setting wins
-    out = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", str(script)], env=env,
-                         capture_output=True, text=True, timeout=120, cwd=os.path.dirname(os.path.dirname(__file__)))
-    assert out.stdout.count("OMP 3") == 2, out.stdout
+    assert run(env, tmp_path / "explicit") == ["3", "3"]
 
 
 def test_single_rank_split_and_free():
