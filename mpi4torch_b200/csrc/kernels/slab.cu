@@ -446,7 +446,7 @@ void launch_zero(void* p, int64_t bytes, int sm_count, cudaStream_t stream) {
 void launch_stage_in(const DeviceComm& dc, const void* in, int64_t bytes, int sm_count, cudaStream_t stream) {
   if (bytes <= 0) return;
   M4T_CHECK(bytes <= dc.half_bytes, "staging " << bytes << " B exceeds the staging half (" << dc.half_bytes
-                                               << " B); raise M4T_STAGE_MB");
+                                               << " B); raise M4T_STAGE_MB (M4T_SUB_STAGE_MB for communicators created by Split)");
   const int aligned = (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (dc.stage_off & 15) == 0;
   const int blocks = static_cast<int>(std::min<int64_t>((bytes / 16 + kThreads) / kThreads, 4LL * sm_count));
   stage_in_kernel<<<blocks, kThreads, 0, stream>>>(dc.sync, dc.heap[dc.sync.rank], dc.stage_off, dc.half_bytes,

@@ -273,7 +273,7 @@ void CudaBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt
   const int64_t es = dtype_size(dt);
   M4T_CHECK(plan.max_stage_elems * es <= dc_.half_bytes,
             "collective stages " << plan.max_stage_elems * es << " B per rank but the staging half is "
-                                 << dc_.half_bytes << " B; raise M4T_STAGE_MB");
+                                 << dc_.half_bytes << " B; raise M4T_STAGE_MB (M4T_SUB_STAGE_MB for communicators created by Split)");
   chain(s);
   // experimental (M4T_AG_PUSH=1): Allgather as an NVSwitch multicast push; the
   // eligibility test only looks at rank-independent quantities
@@ -295,7 +295,7 @@ void CudaBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out,
   if (size() > 1) {
     M4T_CHECK(plan.stage_elems * es <= dc_.half_bytes,
               "Reduce_scatter stages " << plan.stage_elems * es << " B but the staging half is " << dc_.half_bytes
-                                       << " B; raise M4T_STAGE_MB");
+                                       << " B; raise M4T_STAGE_MB (M4T_SUB_STAGE_MB for communicators created by Split)");
     chain(s);
     if (plan.stage_elems > 0) launch_stage_in(dc_, in, plan.stage_elems * es, dc_.sm_count, s);
   }
