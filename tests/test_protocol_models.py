@@ -84,3 +84,58 @@ def test_unit_schedule_keeps_both_halves_of_a_tile_adjacent():
             wave_of[u] = it
     late = [t for t in range(num_tiles) if wave_of[2 * t] != wave_of[2 * t + 1]]
     assert len(late) == 0, late[:5]
+
+
+def _swizzle128(byte_off: int) -> int:
+    """TMA SWIZZLE_128B == cute Swizzle<3,4,3>: XOR address bits [4,7) with bits [7,10)."""
+    return byte_off ^ (((byte_off >> 7) & 7) << 4)
+
+
+def test_mn_major_descriptor_addresses_what_tma_wrote():
+    """wgrad operand tile: TMA boxes of {64 contiguous elements, BK rows} with SWIZZLE_128B, read by
+    tcgen05.mma through an MN-major SWIZZLE_128B descriptor with LBO = one box, SBO = 1024 B and a
+    start-address advance of 2048 B per UMMA_K = 16 (make_smem_desc_mn_sw128, MMA issue loop).
+    The canonical MN-major layout (cute/atom/mma_traits_sm100.hpp): in 16-byte units
+    ((8,n),(8,k)) : ((1,LBO),(8,SBO)), then Swizzle<3,4,3> on the byte address."""
+    BK, CHUNK, ES = 64, 64, 2
+    box_bytes = CHUNK * BK * ES            # 8192
+    lbo, sbo = box_bytes, 1024
+    mn_extent = 128                        # rows of the operand held by one CTA
+    # where TMA puts element (mn, k): box c = mn // 64 starts at c * box_bytes; inside a box row k is
+    # 128 bytes long and the whole box is swizzled relative to its 1024-aligned base
+    def tma_addr(mn, k):
+        c, j = divmod(mn, CHUNK)
+        return c * box_bytes + _swizzle128(k * 128 + j * ES)
+
+    # where the MMA with descriptor start address `start` looks for element (mn, k_local) of its
+    # 16-deep slice: canonical layout + swizzle of the absolute (1024-aligned) address
+    def umma_addr(start, mn, k_local):
+        e, a, nn = mn % 8, (mn // 8) % 8, mn // 64
+        off = e * ES + a * 16 + nn * lbo + (k_local % 8) * 128 + (k_local // 8) * sbo
+        return _swizzle128(start + off)
+
+    for kstep in range(BK // 16):
+        start = kstep * 2048               # koff in the issue loop: (k * UMMA_K * 128) >> 4 descriptor units
+        for mn in range(mn_extent):
+            for k_local in range(16):
+                assert umma_addr(start, mn, k_local) == tma_addr(mn, kstep * 16 + k_local), (kstep, mn, k_local)
+
+
+def test_k_major_descriptor_addresses_what_tma_wrote():
+    """Same check for the validated K-major GEMM (make_smem_desc_k_sw128): TMA box {64 k, rows},
+    descriptor SBO = 1024 B (8 rows), start-address advance of 32 B per UMMA_K = 16 inside the
+    128-byte swizzle span.  Canonical K-major layout: ((8,m),(T,2)) : ((8T,SBO),(1,T)) elements."""
+    ES, rows = 2, 128
+
+    def tma_addr(r, k):
+        return _swizzle128(r * 128 + k * ES)
+
+    def umma_addr(start, r, k_local):
+        off = (r % 8) * 128 + (r // 8) * 1024 + k_local * ES
+        return _swizzle128(start + off)  # the hardware swizzles the final address (validated on B200 for this kernel)
+
+    for kstep in range(4):
+        start = kstep * 32
+        for r in range(rows):
+            for k_local in range(16):
+                assert umma_addr(start, r, k_local) == tma_addr(r, kstep * 16 + k_local)
