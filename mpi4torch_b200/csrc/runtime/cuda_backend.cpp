@@ -134,6 +134,15 @@ void CudaBackend::check_device_error() {
 }
 
 void CudaBackend::chain(cudaStream_t s) {
+  // Inside a CUDA-graph capture the graph orders its own nodes, and a capturing stream must not
+  // wait on events recorded outside the capture.  The collective kernels themselves are
+  // capturable: flag values and staging parity come from device-resident counters.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) {
+    cudaGetLastError();  // e.g. legacy stream while another stream captures: treat as "not capturing"
+  } else if (cap != cudaStreamCaptureStatusNone) {
+    return;
+  }
   if (have_last_ && last_stream_ != s) {
     M4T_CUDA(cudaEventRecord(chain_event_, last_stream_));
     M4T_CUDA(cudaStreamWaitEvent(s, chain_event_, 0));

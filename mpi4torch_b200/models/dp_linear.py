@@ -119,6 +119,34 @@ class DPLinearModel:
         main.wait_stream(side)
         return loss[0]
 
+    def make_graphed_step(self, x: torch.Tensor, target: torch.Tensor, warmup: int = 3):
+        """Capture the fused training step into a CUDA graph (experimental).
+
+        Returns ``(replay, static_x, static_target, loss)``: copy a batch into the static
+        tensors, call ``replay()``, read ``loss`` (a device tensor the graph overwrites).  The
+        collective kernels are capturable because their flag epochs and staging parity live
+        in device memory; every rank must capture and replay the same sequence.  Not
+        available while a fused kernel with host-side step counters is in use (fused
+        forward on >= 4 ranks, fused backward) - construct the model with ``fused=False``.
+        """
+        if not self._fast_path_ok(x, target):
+            raise RuntimeError("make_graphed_step needs inputs the fused step accepts (bf16, CUDA, supported shapes)")
+        if self.comm.size > 1 and (self.fused or self.fused_wgrad):
+            raise RuntimeError("graph capture needs fused=False (the fused kernels take host-side step counters)")
+        static_x, static_t = x.clone(), target.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):  # allocator warm-up, lazy module loading, cuBLAS workspaces
+                self._train_step_fast(static_x, static_t)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.comm.Barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._train_step_fast(static_x, static_t)
+        return graph.replay, static_x, static_t, loss
+
     def invalidate_prefetch(self) -> None:
         """Call after modifying ``weight`` by hand: drops the prefetched parameter average."""
         self._wavg_next = None

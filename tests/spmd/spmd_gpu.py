@@ -268,6 +268,29 @@ class TestFusedTrainingStep(unittest.TestCase):
             self.assertTrue(torch.equal(y, ref), str(dt))
             self.assertTrue(torch.equal(x, src), "input must be untouched")
 
+    @unittest.skipUnless(os.environ.get("M4T_TEST_EXPERIMENTAL", "0") == "1", "CUDA-graph capture of the step: set M4T_TEST_EXPERIMENTAL=1")
+    def test_graphed_step_matches_eager_step(self):
+        from mpi4torch_b200.models import DPLinearModel
+
+        eager = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False)
+        graphed = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False)
+        g = torch.Generator().manual_seed(300 + R)
+        x = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
+        t = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)
+        w0 = graphed.weight.detach().clone()
+        replay, sx, st, loss = graphed.make_graphed_step(x, t)
+        with torch.no_grad():
+            graphed.weight.copy_(w0)  # undo the warm-up / capture steps
+        for step in range(3):
+            xb = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
+            tb = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)
+            le = float(eager.train_step(xb, tb))
+            sx.copy_(xb)
+            st.copy_(tb)
+            replay()
+            self.assertLess(abs(float(loss) - le) / (abs(le) + 1e-6), 1e-3, f"step {step}")
+        self.assertLess((graphed.weight.float() - eager.weight.float()).abs().max().item(), 1e-3)
+
     def test_allreduce_axpy_in_place(self):
         p = torch.full((1000,), 2.0, dtype=torch.float32, device=DEVICE)
         gsrc = torch.full((1000,), float(R + 1), dtype=torch.float32, device=DEVICE)
