@@ -274,6 +274,7 @@ class TestFusedTrainingStep(unittest.TestCase):
 
         eager = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False)
         graphed = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False)
+        eager.fused_wgrad = graphed.fused_wgrad = False  # independent of the M4T_FUSED_WGRAD environment
         g = torch.Generator().manual_seed(300 + R)
         x = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
         t = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)
