@@ -119,3 +119,32 @@ def test_wgrad_mn_major_matches_fp32_reference(shape):
     sel[idx, idx] = 1
     out = torch.ops.mpi4torch_b200.wgrad_bf16(sel, x)
     assert torch.equal(out[: idx.numel()], x[: idx.numel()])
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (384, 512, 256), (8192, 4096, 4096), (300, 520, 200), (1000, 1000, 1000),
+                                   (130, 264, 72)])
+def test_linear_mse_epilogue_matches_fp32_reference(shape):
+    """GEMM with the fused loss epilogue (dL/dy = g * (x W^T - t), loss = s * sum((x W^T - t)^2)); both the
+    CTA-pair kernel (large shapes) and the single-CTA kernel (small ones), including ragged tiles."""
+    import mpi4torch_b200 as m4t  # noqa: F401
+
+    m4t.COMM_WORLD
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + 5 * N + 11 * K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    t = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    grad_scale, loss_scale = 2.0 / M, 1.0 / M
+    dy, loss, w_avg = torch.ops.mpi4torch_b200.linear_mse_forward(x, w, t, 1.0, loss_scale, grad_scale, True)
+    torch.cuda.synchronize()
+    d = x.float() @ w.float().t() - t.float()
+    ref_dy = grad_scale * d
+    err = (dy.float() - ref_dy).abs().max().item()
+    assert err <= 2e-2 * ref_dy.abs().max().item() + 1e-6, f"{shape}: dL/dy max abs err {err}"
+    ref_loss = loss_scale * d.square().sum().item()
+    assert abs(float(loss) - ref_loss) <= 2e-3 * abs(ref_loss), f"{shape}: loss {float(loss)} vs {ref_loss}"
+    assert w_avg.data_ptr() == w.data_ptr()  # single rank: nothing to average
+    # exact structure: target equal to the bf16 product -> loss and gradient are (almost) zero
+    y = torch.ops.mpi4torch_b200.gemm_bf16_tn(x, w)
+    dy0, loss0, _ = torch.ops.mpi4torch_b200.linear_mse_forward(x, w, y, 1.0, 1.0, 1.0, True)
+    assert dy0.float().abs().max().item() <= 2 ** -7 * y.float().abs().max().item() + 1e-6
