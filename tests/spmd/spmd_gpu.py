@@ -100,6 +100,20 @@ class TestAllreduceAlgorithms(unittest.TestCase):
         ref = reference_sum(n, torch.bfloat16) / P + make(R, n, torch.bfloat16, seed=5).double()
         self.assertTrue(torch.allclose(y.double().cpu(), ref, rtol=2 ** -6, atol=2 ** -5))
 
+    def test_accumulate_epilogue_large_and_in_place(self):
+        # two-shot / NVLS kernels at every world size (the one-shot path ends at 2 MiB x (P-1))
+        for dt, n in ((torch.bfloat16, 4 * 1024 * 1024 + 3), (torch.float32, 3 * 1024 * 1024 + 1)):
+            x = make(R, n, dt, seed=2).to(DEVICE)
+            acc = make(R, n, dt, seed=7).to(DEVICE)
+            y = comm.AllreduceFused(x, m4t.MPI_SUM, 0.5, acc)
+            ref = 0.5 * reference_sum(n, dt, seed=2) + make(R, n, dt, seed=7).double()
+            tol = dict(rtol=2 ** -6, atol=2 ** -4) if dt == torch.bfloat16 else dict(rtol=1e-5, atol=1e-4)
+            self.assertTrue(torch.allclose(y.double().cpu(), ref, **tol), str(dt))
+            # in place: param += scale * Allreduce(grad), accumulate operand == output
+            p = acc.clone()
+            torch.ops.mpi4torch_b200.allreduce_axpy_(p, x, 0.5)
+            self.assertTrue(torch.allclose(p.double().cpu(), ref, **tol), f"in-place epilogue ({dt})")
+
     def test_large_message(self):
         n = int(os.environ.get("M4T_TEST_BIG_ELEMS", str(32 * 1024 * 1024 + 5)))
         x = torch.full((n,), float(R + 1), dtype=torch.bfloat16, device=DEVICE)
