@@ -114,6 +114,20 @@ class TestAllreduceAlgorithms(unittest.TestCase):
             torch.ops.mpi4torch_b200.allreduce_axpy_(p, x, 0.5)
             self.assertTrue(torch.allclose(p.double().cpu(), ref, **tol), f"in-place epilogue ({dt})")
 
+    def test_reduce_scatter_and_allgather_backward_large(self):
+        rows = 3000 + R  # rank-dependent extents, several loop trips per thread
+        total = sum(3000 + p for p in range(P))
+        for dt in (torch.bfloat16, torch.float32, torch.float64):
+            x = torch.full((total, 1024), float(R + 1), dtype=dt, device=DEVICE)
+            y = comm.Reduce_scatter(x, m4t.MPI_SUM, 0, rows)
+            self.assertEqual(list(y.shape), [rows, 1024])
+            self.assertTrue(bool((y == P * (P + 1) / 2).all()), str(dt))
+        a = torch.full((rows, 1024), 1.0, dtype=torch.float32, device=DEVICE, requires_grad=True)
+        g = comm.Allgather(a, 0)
+        self.assertEqual(g.shape[0], total)
+        (g * float(R + 1)).sum().backward()  # adjoint = reduce-scatter of every rank's upstream gradient
+        self.assertTrue(bool((a.grad == P * (P + 1) / 2).all()))
+
     def test_large_message(self):
         n = int(os.environ.get("M4T_TEST_BIG_ELEMS", str(32 * 1024 * 1024 + 5)))
         x = torch.full((n,), float(R + 1), dtype=torch.bfloat16, device=DEVICE)
