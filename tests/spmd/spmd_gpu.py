@@ -128,6 +128,17 @@ class TestAllreduceAlgorithms(unittest.TestCase):
         (g * float(R + 1)).sum().backward()  # adjoint = reduce-scatter of every rank's upstream gradient
         self.assertTrue(bool((a.grad == P * (P + 1) / 2).all()))
 
+    def test_rooted_reduce_and_bcast_large(self):
+        root = (P - 1) // 2
+        for dt in (torch.bfloat16, torch.float32, torch.int32):
+            n = 5 * 1024 * 1024 + 3
+            x = torch.full((n,), R + 1, dtype=dt, device=DEVICE)
+            y = comm.Reduce_(x, m4t.MPI_SUM, root)
+            expect = P * (P + 1) // 2 if R == root else 0
+            self.assertTrue(bool((y == expect).all()), f"Reduce_ {dt}")
+            z = comm.Bcast_(torch.full((n,), R + 7, dtype=dt, device=DEVICE), root)
+            self.assertTrue(bool((z == root + 7).all()), f"Bcast_ {dt}")
+
     def test_large_message(self):
         n = int(os.environ.get("M4T_TEST_BIG_ELEMS", str(32 * 1024 * 1024 + 5)))
         x = torch.full((n,), float(R + 1), dtype=torch.bfloat16, device=DEVICE)
