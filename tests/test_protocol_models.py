@@ -139,3 +139,64 @@ def test_k_major_descriptor_addresses_what_tma_wrote():
         for r in range(rows):
             for k_local in range(16):
                 assert umma_addr(start, r, k_local) == tma_addr(r, kstep * 16 + k_local)
+
+
+@pytest.mark.parametrize("nslots,send_blocks,recv_blocks,messages", [(4, 3, 2, [5, 1, 9]), (16, 32, 32, [64, 3]), (2, 1, 5, [7])])
+def test_p2p_slot_ring_protocol_never_overwrites_unread_data(nslots, send_blocks, recv_blocks, messages):
+    """csrc/kernels/p2p.cu: block b of the send kernel takes chunks b, b+G, ... of a message; chunk c
+    (global index) lives in slot c % nslots; head[slot] = c+1 publishes it, tail[slot] = c+1 frees it.
+    Random interleaving of all blocks of both kernels (several back-to-back messages): no slot is
+    overwritten before it was read, every chunk is read exactly once with the right content."""
+    import random
+
+    rng = random.Random(nslots * 1000 + send_blocks * 10 + recv_blocks)
+    head, tail = [0] * nslots, [0] * nslots
+    slot_content = [None] * nslots
+    received = {}
+    first = 0
+    agents = []  # [kind, message-local chunk list iterator state...]
+    for n in messages:  # kernels of consecutive messages are stream-ordered per side, modelled by per-side queues
+        agents.append(("msg", first, n))
+        first += n
+    send_queue = [(f, n) for _, f, n in agents]
+    recv_queue = list(send_queue)
+
+    def make_blocks(first_chunk, n, nblocks):
+        g = min(nblocks, n)
+        return [[first_chunk + k for k in range(b, n, g)] for b in range(g)]
+
+    send_active, recv_active = [], []
+    steps = 0
+    while send_queue or recv_queue or send_active or recv_active:
+        steps += 1
+        assert steps < 200000, "protocol model deadlocked"
+        if not send_active and send_queue:
+            f, n = send_queue.pop(0)
+            send_active = make_blocks(f, n, send_blocks)
+        if not recv_active and recv_queue:
+            f, n = recv_queue.pop(0)
+            recv_active = make_blocks(f, n, recv_blocks)
+        side = rng.choice(["s", "r"])
+        blocks = send_active if side == "s" else recv_active
+        blocks[:] = [b for b in blocks if b]
+        if not blocks:
+            continue
+        b = rng.choice(blocks)
+        c = b[0]
+        s = c % nslots
+        if side == "s":
+            if c >= nslots and tail[s] < c - nslots + 1:
+                continue  # wait_flag_ge(tail[s], c - nslots + 1)
+            assert slot_content[s] is None or slot_content[s] in received, f"chunk {slot_content[s]} overwritten unread"
+            slot_content[s] = c
+            head[s] = c + 1  # st.release after the copy
+            b.pop(0)
+        else:
+            if head[s] < c + 1:
+                continue  # wait_flag_ge(head[s], c + 1)
+            assert slot_content[s] == c, f"slot {s} holds {slot_content[s]}, expected {c}"
+            assert c not in received
+            received[c] = True
+            tail[s] = c + 1
+            b.pop(0)
+    assert sorted(received) == list(range(sum(messages)))
