@@ -163,6 +163,38 @@ class TestTensorParallel(unittest.TestCase):
         self.assertTrue(torch.allclose(lin.weight.grad, expect, rtol=1e-11, atol=1e-11))
 
 
+class TestPipelineParallel(unittest.TestCase):
+    def _stage(self, r):
+        torch.manual_seed(100 + r)  # stage r has the same weights wherever it is built
+        return torch.nn.Sequential(torch.nn.Linear(6, 6), torch.nn.Tanh()).to(DT).to(DEVICE)
+
+    @unittest.skipIf(DEVICE.type == "cuda" and os.environ.get("M4T_TEST_EXPERIMENTAL", "0") != "1",
+                     "new p2p traffic pattern: run on CUDA with M4T_TEST_EXPERIMENTAL=1 first")
+    def test_matches_the_sequential_model(self):
+        from mpi4torch_b200.parallel import pipeline_forward, split_microbatches
+
+        nmb = 3
+        x = torch.randn(12, 6, generator=torch.Generator().manual_seed(4), dtype=DT).to(DEVICE)
+        mine = self._stage(R)
+        loss = pipeline_forward(mine, split_microbatches(x, nmb) if R == 0 else None, [12 // nmb, 6],
+                                lambda y, m: y.square().sum() * (m + 1), comm, num_microbatches=nmb, dtype=DT,
+                                device=DEVICE)
+        loss.backward()
+        # reference: all stages in one process
+        stages = [self._stage(p) for p in range(P)]
+        total = 0
+        for m, xb in enumerate(split_microbatches(x, nmb)):
+            h = xb
+            for st in stages:
+                h = st(h)
+            total = total + h.square().sum() * (m + 1)
+        total.backward()
+        if R == P - 1:
+            self.assertTrue(torch.allclose(loss.detach(), total.detach(), rtol=1e-12, atol=1e-12))
+        for pm, pr in zip(mine.parameters(), stages[R].parameters()):
+            self.assertTrue(torch.allclose(pm.grad, pr.grad, rtol=1e-10, atol=1e-12), f"stage {R}")
+
+
 class TestFunctionalOps(unittest.TestCase):
     def test_allreduce_mean_and_sgd_step(self):
         x = torch.full((7,), float(R), dtype=DT, device=DEVICE)
