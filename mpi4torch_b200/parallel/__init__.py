@@ -3,10 +3,11 @@ parallel (the only strategy the reference ships, as an example), plus the ring
 (pipeline-style p2p) and sequence<->head (Ulysses-style) exchanges the
 reference's primitives enable."""
 from .data_parallel import DataParallel, OverlappedGradSync, sync_gradients_
+from .expert import DispatchInfo, combine_tokens, dispatch_tokens
 from .pipeline import pipeline_forward, split_microbatches
 from .ring import ring_exchange
 from .sequence import heads_to_sequence, sequence_to_heads
 from .tensor_parallel import ColumnParallelLinear, RowParallelLinear, TensorParallelMLP, replicated_input
 
 __all__ = ["DataParallel", "OverlappedGradSync", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence",
-           "pipeline_forward", "split_microbatches", "ColumnParallelLinear", "RowParallelLinear", "TensorParallelMLP", "replicated_input"]
+           "dispatch_tokens", "combine_tokens", "DispatchInfo", "pipeline_forward", "split_microbatches", "ColumnParallelLinear", "RowParallelLinear", "TensorParallelMLP", "replicated_input"]

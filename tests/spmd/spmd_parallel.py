@@ -195,6 +195,47 @@ class TestPipelineParallel(unittest.TestCase):
             self.assertTrue(torch.allclose(pm.grad, pr.grad, rtol=1e-10, atol=1e-12), f"stage {R}")
 
 
+class TestExpertParallel(unittest.TestCase):
+    def test_dispatch_expert_combine_round_trip_and_gradients(self):
+        from mpi4torch_b200.parallel import combine_tokens, dispatch_tokens
+
+        T, d = 7, 3
+        tokens = (torch.arange(T * d, dtype=DT).reshape(T, d) + 100 * R).to(DEVICE).requires_grad_()
+        dest = torch.tensor([(R + 2 * i) % P for i in range(T)], device=DEVICE)
+        received, info = dispatch_tokens(tokens, dest, capacity=T, comm=comm)  # capacity T: nothing is dropped
+        self.assertEqual(list(received.shape), [P, T, d])
+        # what arrived from rank p: its tokens with dest == R, in order
+        for p in range(P):
+            src = torch.arange(T * d, dtype=DT).reshape(T, d) + 100 * p
+            mine = [i for i in range(T) if (p + 2 * i) % P == R]
+            self.assertEqual(int(info.valid[p].sum()), len(mine))
+            if mine:
+                self.assertTrue(torch.equal(received[p, :len(mine)].detach().cpu(), src[mine]))
+        out = combine_tokens(received * float(R + 1), info, comm)  # "expert" of rank R multiplies by R+1
+        expect = tokens.detach() * (dest.to(DT) + 1)[:, None]
+        self.assertTrue(torch.equal(out.detach(), expect))
+        w = torch.arange(1, T + 1, dtype=DT, device=DEVICE)[:, None]
+        (out * w).sum().backward()
+        self.assertTrue(torch.equal(tokens.grad, ((dest.to(DT) + 1)[:, None] * w).expand(T, d)))
+
+    def test_tokens_over_capacity_are_dropped(self):
+        from mpi4torch_b200.parallel import combine_tokens, dispatch_tokens
+
+        tokens = torch.ones(5, 2, dtype=DT, device=DEVICE) * (R + 1)
+        dest = torch.zeros(5, dtype=torch.int64, device=DEVICE)  # everybody floods rank 0
+        received, info = dispatch_tokens(tokens, dest, capacity=2, comm=comm)
+        self.assertEqual(info.slot.tolist(), [0, 1, -1, -1, -1])
+        if R == 0:
+            self.assertEqual(int(info.valid.sum()), 2 * P)
+            for p in range(P):
+                self.assertTrue(bool((received[p] == p + 1).all()))
+        else:
+            self.assertEqual(int(info.valid.sum()), 0)
+        out = combine_tokens(received + 10.0, info, comm)
+        self.assertTrue(torch.equal(out[:2], torch.full((2, 2), R + 11.0, dtype=DT, device=DEVICE)))
+        self.assertTrue(torch.equal(out[2:], torch.zeros(3, 2, dtype=DT, device=DEVICE)))
+
+
 class TestFunctionalOps(unittest.TestCase):
     def test_allreduce_mean_and_sgd_step(self):
         x = torch.full((7,), float(R), dtype=DT, device=DEVICE)
