@@ -37,3 +37,11 @@ def test_tensor_parallel_mlp_example_2d_parallelism_cpu():
     losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
     assert len(losses) >= 3 and losses[-1] < 0.7 * losses[0], losses
     assert "(tp=2, dp=2)" in res.stdout
+
+
+def test_pipeline_example_trains_across_three_stages_cpu():
+    res = run_spmd(3, ["examples/pipeline_mlp.py", "--device", "cpu", "--steps", "40"], device="cpu", timeout=300)
+    assert res.returncode == 0, res.stderr[-4000:]
+    losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
+    assert len(losses) >= 3 and losses[-1] < 0.6 * losses[0], losses
+    assert "(3 stages, 4 micro-batches)" in res.stdout
