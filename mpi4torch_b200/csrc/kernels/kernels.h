@@ -133,7 +133,10 @@ int fused_wgrad_signals_per_tile(int ksplit);
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
-                               uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream);
+                               uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
+                               int64_t epoch_off = -1);
+// epoch_off >= 0: tile_target / done_target are PER-CALL increments and the call index lives in the local
+// device word at that heap offset (advanced by the kernel): no host-side step state, graph-capturable.
 // wavg_off >= 0: additionally leaves (1/P) * sum_ranks W_new in the bf16 [N,K] buffer at that heap
 // offset on every rank (the parameter all-reduce of the NEXT forward, run under this GEMM).
 // Plain device copy into the heap (used to stage the weight for the fused kernel).

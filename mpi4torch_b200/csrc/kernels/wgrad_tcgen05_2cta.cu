@@ -78,8 +78,10 @@ struct WgradComm {
   int64_t w_off;         // bf16 weights [N, K] (contiguous) inside every rank's heap
   int64_t cnt_off;       // u32 tile counters [tiles]
   int64_t done_off;      // u32 completion counter
-  uint32_t tile_target;
+  uint32_t tile_target;  // counters are monotonic: targets of THIS call when epoch_off < 0 ...
   uint32_t done_target;
+  int64_t epoch_off;     // ... otherwise per-call increments; the call index is read from this local
+                         // device word (and advanced by the kernel), which makes the launch graph-capturable
   float scale;           // W += scale * sum_ranks G   (scale = -lr / P)
   // optional: all-reduce the UPDATED weights for the next forward while the GEMM is still running
   int prefetch;          // 1: W_avg[tile] = avg_scale * sum_ranks W[tile] after the update of the tile
@@ -142,6 +144,12 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   constexpr int kRows = BMC / kRowSplit;  // rows of this CTA's half handled per work item
   const uint32_t* my_cnt = reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.cnt_off);
   const int64_t row_bytes = static_cast<int64_t>(K) * 2;
+  // device-resident call counter: every communication thread reads it before any CTA can pass the
+  // completion barrier below, and only CTA 0 advances it after that barrier
+  uint32_t* epoch_ptr = wc.epoch_off >= 0 ? reinterpret_cast<uint32_t*>(wc.heap[r] + wc.epoch_off) : nullptr;
+  const uint32_t epoch = epoch_ptr ? *reinterpret_cast<volatile uint32_t*>(epoch_ptr) : 0u;
+  const uint32_t tile_target = epoch_ptr ? (epoch + 1u) * wc.tile_target : wc.tile_target;
+  const uint32_t done_target = epoch_ptr ? (epoch + 1u) * wc.done_target : wc.done_target;
   // Work item w = (j-th owned tile, row slice s); item w is served by cluster w % num_clusters.
   // Owned tiles (t = r + j*P) finish in GEMM order, so consecutive items land on different CTA
   // pairs and their switch round trips overlap; with 256 tiles / 8 ranks x 2 slices = 64 items
@@ -151,7 +159,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
     const int j = w_item / kRowSplit;
     const int slice = w_item - j * kRowSplit;
     const int t = r + j * P;
-    if (lane == 0) bounded_wait_ge(my_cnt + t, wc.tile_target, c);
+    if (lane == 0) bounded_wait_ge(my_cnt + t, tile_target, c);
     __syncwarp();
     const int n_blk = t / k_tiles;
     const int k_blk = t - n_blk * k_tiles;
@@ -221,7 +229,8 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   if (ct == 0) {
     __threadfence_system();
     asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(wc.mc_heap + wc.done_off), "r"(1u) : "memory");
-    bounded_wait_ge(reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.done_off), wc.done_target, c);
+    bounded_wait_ge(reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.done_off), done_target, c);
+    if (epoch_ptr && blockIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = epoch + 1u;
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
 }
@@ -438,7 +447,8 @@ int fused_wgrad_signals_per_tile(int ksplit) { return kSignalsPerUnit * ksplit; 
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
-                               uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream) {
+                               uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
+                               int64_t epoch_off) {
   M4T_CHECK(dc.mc_heap != nullptr, "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping");
   M4T_CHECK(ksplit == 1 || ksplit == 2, "ksplit must be 1 or 2");
   M4T_CHECK((Mb / BK) % ksplit == 0, "batch / 64 must be divisible by ksplit");
@@ -465,6 +475,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.done_off = done_off;
   wc.tile_target = tile_target;
   wc.done_target = done_target;
+  wc.epoch_off = epoch_off;
   wc.scale = scale;
   wc.prefetch = wavg_off >= 0 ? 1 : 0;
   wc.wavg_off = wavg_off >= 0 ? wavg_off : 0;

@@ -420,6 +420,7 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
     st.stage_off = symm_alloc(st.stage_stride * st.ksplit);
     st.cnt_off = symm_alloc(fused_wgrad_tiles(N, K) * 4);
     st.done_off = symm_alloc(16);
+    st.epoch_off = symm_alloc(16);  // call index, kept on the device (graph-capturable launches)
     it = wgrad_.emplace(key, st).first;  // the arena is zero-initialised: counters start at 0
   }
   FusedWgradState& st = it->second;
@@ -427,12 +428,12 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
   chain(stream);
   const int64_t w_off = static_cast<const char*>(w) - dc_.heap[dc_.sync.rank];
   st.calls += 1;
-  const uint32_t tile_target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(fused_wgrad_signals_per_tile(st.ksplit)) *
-                                                     static_cast<uint64_t>(size()));
-  const uint32_t done_target = static_cast<uint32_t>(st.calls * static_cast<uint64_t>(size()) * fused_gemm_grid(dc_));
+  // per-call increments of the monotonic counters; the kernel multiplies by (device call index + 1)
+  const uint32_t tile_target = static_cast<uint32_t>(fused_wgrad_signals_per_tile(st.ksplit) * size());
+  const uint32_t done_target = static_cast<uint32_t>(size() * fused_gemm_grid(dc_));
   launch_fused_wgrad_update(dc_, dy, x, Mb, N, K, ldy, ldx, w_off, st.stage_off, st.stage_stride, st.cnt_off,
                             st.done_off, st.ksplit, tile_target, done_target, scale, prefetch_avg ? st.wavg_off : -1,
-                            stream);
+                            stream, st.epoch_off);
   return prefetch_avg ? symm_ptr(st.wavg_off) : nullptr;
 }
 
