@@ -125,14 +125,17 @@ class DPLinearModel:
         Returns ``(replay, static_x, static_target, loss)``: copy a batch into the static
         tensors, call ``replay()``, read ``loss`` (a device tensor the graph overwrites).  The
         collective kernels are capturable because their flag epochs and staging parity live
-        in device memory; every rank must capture and replay the same sequence.  Not
-        available while a fused kernel with host-side step counters is in use (fused
-        forward on >= 4 ranks, fused backward) - construct the model with ``fused=False``.
+        in device memory; every rank must capture and replay the same sequence.  The fused
+        forward kernel still takes a host-side step counter: capture needs ``fused=False``, or
+        the prefetching fused backward (``M4T_FUSED_WGRAD`` + ``M4T_WAVG_PREFETCH``), whose
+        steady-state step contains no fused forward.
         """
         if not self._fast_path_ok(x, target):
             raise RuntimeError("make_graphed_step needs inputs the fused step accepts (bf16, CUDA, supported shapes)")
-        if self.comm.size > 1 and (self.fused or self.fused_wgrad):
-            raise RuntimeError("graph capture needs fused=False (the fused kernels take host-side step counters)")
+        prefetching = self.fused_wgrad and self.wavg_prefetch
+        if self.comm.size > 1 and self.fused and not prefetching:
+            raise RuntimeError("graph capture needs fused=False or the prefetching fused backward "
+                               "(the fused forward kernel takes a host-side step counter)")
         static_x, static_t = x.clone(), target.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -142,6 +145,9 @@ class DPLinearModel:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.comm.Barrier()
+        if self.comm.size > 1 and self.fused and self._wavg_next is None:
+            raise RuntimeError("the fused backward did not take over (see wgrad_allreduce_sgd_supported): "
+                               "the step to capture would still contain the fused forward kernel")
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = self._train_step_fast(static_x, static_t)
