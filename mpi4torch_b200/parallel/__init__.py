@@ -6,8 +6,8 @@ from .data_parallel import DataParallel, OverlappedGradSync, sync_gradients_
 from .expert import DispatchInfo, combine_tokens, dispatch_tokens
 from .pipeline import pipeline_forward, split_microbatches
 from .ring import ring_exchange
-from .sequence import heads_to_sequence, sequence_to_heads
+from .sequence import heads_to_sequence, sequence_to_heads, ulysses_attention
 from .tensor_parallel import ColumnParallelLinear, RowParallelLinear, TensorParallelMLP, replicated_input
 
-__all__ = ["DataParallel", "OverlappedGradSync", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence",
+__all__ = ["DataParallel", "OverlappedGradSync", "sync_gradients_", "ring_exchange", "sequence_to_heads", "heads_to_sequence", "ulysses_attention",
            "dispatch_tokens", "combine_tokens", "DispatchInfo", "pipeline_forward", "split_microbatches", "ColumnParallelLinear", "RowParallelLinear", "TensorParallelMLP", "replicated_input"]

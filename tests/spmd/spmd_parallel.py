@@ -195,6 +195,30 @@ class TestPipelineParallel(unittest.TestCase):
             self.assertTrue(torch.allclose(pm.grad, pr.grad, rtol=1e-10, atol=1e-12), f"stage {R}")
 
 
+class TestSequenceParallelAttention(unittest.TestCase):
+    def test_ulysses_attention_matches_full_attention(self):
+        from mpi4torch_b200.parallel import ulysses_attention
+
+        B, S_local, H, D = 2, 3, 2 * P, 4
+        gen = torch.Generator().manual_seed(17)
+        full = [torch.randn(B, S_local * P, H, D, generator=gen, dtype=DT) for _ in range(3)]  # same on every rank
+        mine = [t[:, R * S_local:(R + 1) * S_local].to(DEVICE).requires_grad_() for t in full]
+        for causal in (False, True):
+            out = ulysses_attention(*mine, comm=comm, causal=causal)
+            ref_in = [t.clone().requires_grad_() for t in full]
+            ref = torch.nn.functional.scaled_dot_product_attention(
+                *(t.transpose(1, 2) for t in ref_in), is_causal=causal).transpose(1, 2)
+            self.assertTrue(torch.allclose(out.detach().cpu(), ref[:, R * S_local:(R + 1) * S_local].detach(),
+                                           rtol=1e-10, atol=1e-12), f"causal={causal}")
+            for t in mine:
+                t.grad = None
+            # objective = sum over ranks of each rank's output slice = sum of the full output
+            out.sum().backward()
+            ref.sum().backward()
+            for a, b in zip(mine, ref_in):
+                self.assertTrue(torch.allclose(a.grad.cpu(), b.grad[:, R * S_local:(R + 1) * S_local], rtol=1e-9, atol=1e-11))
+
+
 class TestExpertParallel(unittest.TestCase):
     def test_dispatch_expert_combine_round_trip_and_gradients(self):
         from mpi4torch_b200.parallel import combine_tokens, dispatch_tokens
