@@ -232,7 +232,11 @@ struct JoinDummiesBackward : public Function<JoinDummiesBackward> {
     ctx->saved_data["dtypes"] = dtypes;
     ctx->saved_data["devtypes"] = devtypes;
     ctx->saved_data["devidx"] = devidx;
-    return loopthrough.detach();  // shallow copy sharing storage (:1037)
+    Tensor out = loopthrough.detach();  // shallow copy sharing storage (:1037)
+    // the forward result is re-joined to every gradient in backward so that communication encoded
+    // through this node stays on higher-order graphs (reference :1002-1022 keeps `loopthrough`)
+    ctx->save_for_backward({out});
+    return out;
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     const auto sizes = ctx->saved_data["sizes"].toIntVector();
@@ -240,9 +244,14 @@ struct JoinDummiesBackward : public Function<JoinDummiesBackward> {
     const auto dtypes = ctx->saved_data["dtypes"].toIntVector();
     const auto devtypes = ctx->saved_data["devtypes"].toIntVector();
     const auto devidx = ctx->saved_data["devidx"].toIntVector();
+    // Under create_graph=True the forward result requires grad, so JoinDummies below records a node
+    // whose edges lead back to this op's inputs; in a plain first-order backward grad mode is off and
+    // JoinDummies is the identity.
+    const variable_list saved = ctx->get_saved_variables();
+    const std::vector<Tensor> fwd = {saved[0]};
     variable_list out;
     out.reserve(ndims.size() + 1);
-    out.push_back(grads[0]);
+    out.push_back(grads[0].defined() ? JoinDummies(grads[0], fwd) : grads[0]);
     size_t cursor = 0;
     for (size_t i = 0; i < ndims.size(); ++i) {
       const std::vector<int64_t> shape(sizes.begin() + cursor, sizes.begin() + cursor + ndims[i]);
@@ -251,7 +260,7 @@ struct JoinDummiesBackward : public Function<JoinDummiesBackward> {
                             .dtype(static_cast<at::ScalarType>(dtypes[i]))
                             .device(c10::Device(static_cast<c10::DeviceType>(devtypes[i]),
                                                 static_cast<c10::DeviceIndex>(devidx[i])));
-      out.push_back(at::zeros(shape, opts));  // dummies receive zeros (:1002-1011)
+      out.push_back(JoinDummies(at::zeros(shape, opts), fwd));  // dummies receive zeros (:1002-1011)
     }
     return out;
   }
@@ -371,6 +380,10 @@ std::vector<Tensor> Communicator::Irecv(const Tensor& input, int64_t source, int
 
 Tensor Communicator::Wait(const std::vector<Tensor>& handle) {
   TORCH_CHECK(handle.size() == 3, "mpi4torch_b200: a raw wait handle consists of exactly 3 tensors");
+  // MPIWaitBackward::forward reads the descriptor on the host: validate it first
+  TORCH_CHECK(handle[0].defined() && handle[0].device().is_cpu() && handle[0].scalar_type() == at::kDouble &&
+                  handle[0].numel() == 7 && handle[0].is_contiguous(),
+              "mpi4torch_b200: malformed wait handle descriptor");
   // Bifurcation guard (:1183-1202): the buffer handed to Wait must come straight
   // from Isend/Irecv, otherwise autograd would sum two gradient handles and an
   // in-flight receive would write to freed memory.

@@ -87,6 +87,8 @@ struct WgradComm {
   int prefetch;          // 1: W_avg[tile] = avg_scale * sum_ranks W[tile] after the update of the tile
   int64_t wavg_off;      // bf16 [N, K] buffer receiving the averaged weights on every rank
   float avg_scale;       // 1 / P
+  int debug;             // timing experiments (M4T_WGRAD_DEBUG): 1 no comm data movement, 2 no GEMM,
+                         // 4 local loads instead of multimem.ld_reduce, 8 local stores instead of multimem.st
 };
 
 struct __align__(8) Bars {
@@ -171,17 +173,22 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int row = row0 + u * kCommWarps;
-        if (row < kRows) {
+        if (row < kRows && !(wc.debug & 1)) {
           const int64_t off = tile_off + row * row_bytes;
-          s0[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
-          if (ksplit > 1) s1[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
+          if (wc.debug & 4) {
+            s0[u] = ld_vec(wc.heap[r] + wc.stage_off + off);
+            if (ksplit > 1) s1[u] = ld_vec(wc.heap[r] + wc.stage_off + wc.stage_stride + off);
+          } else {
+            s0[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
+            if (ksplit > 1) s1[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
+          }
           w[u] = ld_vec(wc.heap[r] + wc.w_off + off);
         }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int row = row0 + u * kCommWarps;
-        if (row < kRows) {
+        if (row < kRows && !(wc.debug & 1)) {
           const int64_t off = tile_off + row * row_bytes;
           float a[8], b[8], wv[8];
           VecOf<DType::BF16>::unpack(s0[u], a);
@@ -193,11 +200,12 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) wv[e] = fmaf(wc.scale, a[e], wv[e]);
-          multimem_st_vec(wc.mc_heap + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
+          if (wc.debug & 8) st_vec(wc.heap[r] + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
+          else multimem_st_vec(wc.mc_heap + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
         }
       }
     }
-    if (wc.prefetch) {
+    if (wc.prefetch && !(wc.debug & 1)) {
       // Next step's forward needs Allreduce(W) / P.  The rows this lane just multicast are final on
       // every rank once its stores are performed system-wide, so the parameter all-reduce of the
       // NEXT step can run here, under the GEMM of later tiles: same rows, same lane -> a per-thread
@@ -276,7 +284,7 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (lane == 0 && !(FUSED && (wc.debug & 2))) {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
@@ -307,7 +315,7 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
+    if (leader && lane == 0 && !(FUSED && (wc.debug & 2))) {
       constexpr uint32_t idesc = make_idesc_bf16_f32_mn(BM2, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -351,6 +359,14 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       const int k_blk = t - n_blk * k_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      if (FUSED && (wc.debug & 2)) {  // timing experiment: no GEMM, only the tile signals
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t* cnt = reinterpret_cast<uint32_t*>(wc.heap[t % wc.sync.size] + wc.cnt_off) + t;
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+        }
+        continue;
+      }
       tc::mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
       const int row = n_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
@@ -480,6 +496,8 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.prefetch = wavg_off >= 0 ? 1 : 0;
   wc.wavg_off = wavg_off >= 0 ? wavg_off : 0;
   wc.avg_scale = 1.0f / static_cast<float>(dc.sync.size);
+  static const int debug = static_cast<int>(env_i64("M4T_WGRAD_DEBUG", 0));  // read once: timing experiments only
+  wc.debug = debug;
   const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
   configure_w<true>();
   wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, wc);

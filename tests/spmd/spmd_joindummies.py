@@ -41,6 +41,40 @@ class TestJoinDummies(unittest.TestCase):
         self.assertEqual(d2.grad.dtype, torch.float32)
         self.assertTrue(torch.equal(d2.grad, torch.zeros_like(d2)))
 
+    def test_higher_order_graph_keeps_the_join(self):
+        """Under create_graph=True the gradients are re-joined to the forward result
+        (reference csrc/extension.cpp:1002-1022), so second derivatives see the dependency."""
+        a = rand(5, requires_grad=True)
+        d = rand(3, requires_grad=True)
+        y = m4t.JoinDummies(a * a, [d])
+        ga, gd = torch.autograd.grad(y.sum(), [a, d], create_graph=True)
+        self.assertTrue(torch.allclose(ga, 2 * a))
+        self.assertTrue(torch.equal(gd, torch.zeros_like(d)))
+        self.assertIsNotNone(gd.grad_fn)
+        self.assertIn("JoinDummiesBackward", gd.grad_fn.name())
+        (h,) = torch.autograd.grad(ga.sum() + gd.sum(), a)
+        self.assertTrue(torch.allclose(h, 2 * torch.ones_like(a)))
+        # first-order backward is unchanged: no graph is recorded
+        (g1,) = torch.autograd.grad(m4t.JoinDummies(a * a, [d]).sum(), a)
+        self.assertIsNone(g1.grad_fn)
+
+    def test_double_backward_through_a_send_recv_ring(self):
+        """Second derivative of sum_r (a_r^2 + a_{r-1}^2) through Isend/Recv/Wait with the
+        dependencies encoded by JoinDummies: d/da = 4a, d2/da2 = 4 (communication runs in the
+        first backward AND in the backward of that backward)."""
+        a = rand(7, requires_grad=True)
+        right, left = (comm.rank + 1) % P, (comm.rank + P - 1) % P
+        sq = a * a
+        handle = comm.Isend(sq, right, 3)
+        buf = m4t.JoinDummies(torch.empty_like(sq), [handle.dummy])
+        b = comm.Recv(buf, left, 3)
+        w = comm.Wait(m4t.JoinDummiesHandle(handle, [b]))
+        res = m4t.JoinDummies(sq + b, [w])
+        (g,) = torch.autograd.grad(res.sum(), a, create_graph=True)
+        self.assertTrue(torch.allclose(g, 4 * a))
+        (h,) = torch.autograd.grad(g.sum(), a)
+        self.assertTrue(torch.allclose(h, 4 * torch.ones_like(a)))
+
 
 if __name__ == "__main__":
     unittest.main()
