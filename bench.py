@@ -3,24 +3,28 @@
 
 Flagship step = BASELINE.json config "4096x4096 linear layer: Allreduce(params)
 -> GEMM fused, loss Allreduce backward": every rank holds a 4096x4096 bf16
-weight and a private batch; one step averages the weights (Allreduce fused into
-the GEMM operand path), runs the forward GEMM, all-reduces the scalar loss,
-back-propagates (wgrad GEMM + the adjoint Allreduce) and applies SGD.
+weight and a private batch; one step is, THROUGH THE AUTOGRAD GRAPH,
+
+    local = dp_linear_mse(x, W, t)            Allreduce(W)/size -> tcgen05 GEMM -> MSE epilogue
+    loss  = comm.Allreduce(local, MPI_SUM)    the library's differentiable Allreduce
+    loss.backward()                           adjoint Allreduce of the scalar, wgrad GEMM, adjoint
+                                              Allreduce of dW fused with the SGD update
 
     python bench.py --gpus N --steps K --warmup W            (N>1: under torchrun)
-    python bench.py --impl reference ...                      (reference arm)
+    python bench.py --impl reference ...                      (the unmodified reference, baseline/)
 
-Prints ONE JSON line on rank 0.  `value` = samples/s over the whole job, timed
-on the device (CUDA events, max over ranks); `e2e` = the same step through the
-public API including per-step H2D of the batch from pinned memory and D2H of
-the loss.  Extra keys report the Allreduce fwd+bwd bus bandwidth sweep and the
-CPU linear-regression step/s named by BASELINE.json's metric string.
+Prints ONE JSON line on rank 0.  `value` = samples/s over the whole job, timed on the device (CUDA
+events, max over ranks); `e2e` = the same step through the public API including per-step H2D of the
+batch from pinned memory and D2H of the loss.  First-class extra keys: the Allreduce fwd+bwd bus
+bandwidth table (BASELINE.json's metric) and the CPU linear-regression step/s at world size 2.
+At N > 1 a self-check block runs before anything is timed ("checks").
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import time
 
@@ -34,22 +38,21 @@ PER_GPU_BATCH = 8192
 POOL = 4  # rotating input batches: 4 x (64 MiB x + 64 MiB t) >> 126 MB L2
 
 
-def reference_arm(args) -> int:
-    why = ("reference cannot be built: csrc/extension.cpp needs <mpi.h> and the image ships no MPI "
-           "(pip install --no-index --no-deps of /root/reference fails with 'mpi.h: No such file or directory'); "
-           "see DESIGN.md")
-    ref_dir = os.path.join(ROOT, "baseline", "_ref", "mpi4torch")
-    if os.path.isdir(ref_dir):
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
-            import mpi4torch  # noqa: F401
-
-            why = "reference imported unexpectedly; no MPI launcher (mpirun) exists in this image to run it"
-        except Exception as exc:  # pragma: no cover
-            why = f"reference import failed: {type(exc).__name__}: {exc}"[:300]
-    if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
-    return 0
+def linreg_cpu_step_per_s() -> object:
+    """BASELINE.json config 1 (CPU, world size 2) through this library's launcher and shm backend."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_PORT", "MASTER_ADDR", "M4T_JOB_ID",
+                        "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK")}
+    env["M4T_CUDA"] = "0"
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    try:
+        res = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2",
+                              os.path.join(ROOT, "benchmarks", "linreg_steps.py"), "--steps", "10", "--no-gloo"],
+                             capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["ours_step_per_s"]
+    except Exception as exc:  # pragma: no cover
+        return {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
 
 def main() -> int:
@@ -60,10 +63,16 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-extras", action="store_true", help="skip the allreduce sweep / regression extras")
+    ap.add_argument("--no-checks", action="store_true", help="skip the multi-GPU self-check block")
     ap.add_argument("--unfused", action="store_true", help="force the unfused Allreduce + GEMM composition")
+    ap.add_argument("--plain-sgd", action="store_true", help="weight.grad + separate SGD instead of the optimizer in backward")
+    ap.add_argument("--full-sweep", action="store_true", help="1 KiB .. 1 GiB in x4 steps instead of the quick table")
     args = ap.parse_args()
     if args.impl == "reference":
-        return reference_arm(args)
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import reference_arm
+
+        return reference_arm.run(args)
 
     import torch
 
@@ -87,37 +96,60 @@ def main() -> int:
     _C = m4t._C
     B = args.batch
 
+    # ---------------- multi-GPU self checks (before anything is timed) ----------------
+    checks = None
+    if size > 1 and not args.no_checks:
+        from benchmarks.selfcheck import run_checks
+
+        checks = run_checks(comm, dev)
+        if not checks.get("ok", False):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "self-check failed", "checks": checks}), flush=True)
+            return 2
+
     torch.manual_seed(1234 + rank)
-    model = DPLinearModel(IN_F, OUT_F, comm, device=dev, dtype=torch.bfloat16, lr=1e-5, fused=not args.unfused)
+    model = DPLinearModel(IN_F, OUT_F, comm, device=dev, dtype=torch.bfloat16, lr=1e-5, fused=not args.unfused,
+                          sgd_in_backward=not args.plain_sgd)
     xs = [torch.randn(B, IN_F, device=dev, dtype=torch.bfloat16) for _ in range(POOL)]
     ts = [torch.randn(B, OUT_F, device=dev, dtype=torch.bfloat16) for _ in range(POOL)]
 
-    def step(i: int):
-        return model.train_step(xs[i % POOL], ts[i % POOL])
+    def step(i: int, mdl=model):
+        return mdl.train_step(xs[i % POOL], ts[i % POOL])
 
     def max_ranks(v: float) -> float:
         t = torch.tensor([v], dtype=torch.float64)
         return float(comm.Allreduce(t, m4t.MPI_MAX)[0])
 
-    # ---------------- device-timed region ----------------
+    def timed(fn, steps: int, warmup: int):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        comm.Barrier()
+        l0 = _C.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        comm.Barrier()
+        e0.record()
+        out = None
+        for i in range(steps):
+            out = fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        comm.Barrier()
+        return max_ranks(e0.elapsed_time(e1)), _C.kernel_launch_count() - l0, out
+
+    # ---------------- device-timed region (the headline) ----------------
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     comm.Barrier()
-    sampler = ClockSampler(gpu_index=dev.index).start() if rank == 0 else None
-    launches0 = _C.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    comm.Barrier()
-    e0.record()
-    for i in range(args.steps):
-        loss = step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    comm.Barrier()
-    dev_ms = max_ranks(e0.elapsed_time(e1))
-    launches = _C.kernel_launch_count() - launches0
+    sampler = ClockSampler(gpu_index=dev.index).start() if rank == size - 1 else None  # not on the rank that prints
+    table0 = dict(_C.kernel_launch_table())
+    dev_ms, launches, loss = timed(step, args.steps, 0)
     final_loss = float(loss)
+    # which tensor-core / fused kernels really ran in the timed region (launches per step)
+    path = {k: (v - table0.get(k, 0)) / args.steps for k, v in dict(_C.kernel_launch_table()).items()
+            if v - table0.get(k, 0) > 0}
 
     # ---------------- end-to-end region (public API + H2D/D2H every step) ----------------
     pin_x = [torch.randn(B, IN_F, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
@@ -159,7 +191,21 @@ def main() -> int:
     torch.cuda.synchronize()
     e2e_s = max_ranks(time.perf_counter() - t0)
     comm.Barrier()
-    clocks = sampler.stop() if sampler is not None else None
+    clock_summary = sampler.stop() if sampler is not None else None
+    # the sampling rank hands its summary to rank 0 (host-side, after all timing)
+    blob = torch.zeros(4, dtype=torch.float64)
+    if clock_summary is not None:
+        reasons = clock_summary.get("reasons", [])
+        code = sum(1 << i for i, k in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                   if k in reasons)
+        blob = torch.tensor([clock_summary.get("sm_mhz") or 0.0, clock_summary.get("sm_max_mhz") or 0.0, float(code),
+                             float(clock_summary.get("samples", 0))], dtype=torch.float64)
+    blob = comm.Allreduce(blob, m4t.MPI_SUM)
+    code = int(blob[2])
+    clocks = {"sm_mhz": float(blob[0]), "sm_max_mhz": float(blob[1]),
+              "reasons": [k for i, k in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                          if code >> i & 1],
+              "samples": int(blob[3]), "sampled_gpu": size - 1}
 
     total_samples = float(B) * size * args.steps
     value = total_samples / (dev_ms * 1e-3)
@@ -180,15 +226,15 @@ def main() -> int:
         "data": "synthetic (random-init 4096x4096 weight, random batches)",
         "impl": "ours",
         "config": {
-            "model": "dp_linear_4096x4096 (Allreduce(params)->GEMM, loss Allreduce, SGD)",
+            "model": "dp_linear_4096x4096 (Allreduce(params)->GEMM, loss Allreduce, backward, SGD)",
             "global_batch": B * size,
             "seq_len": 1,
             "parallelism": f"dp{size}",
             "per_gpu_batch": B,
             "cold_cache": f"inputs rotate over {POOL} batches (>= {POOL * 2 * B * IN_F * 2 >> 20} MiB) > 126 MB L2",
-            "fused_forward": bool(model.fused and size > 1),
-            "fused_backward": bool(model.fused_wgrad and size > 1),
-            "prefetched_param_allreduce": bool(model.wavg_prefetch and model.fused_wgrad and size > 1),
+            "autograd": True,
+            "optimizer_in_backward": bool(model.sgd_in_backward and model._in_backward(xs[0])),
+            "kernels_per_step": path,
             "heap_mode": m4t.heap_mode(),
             "nvls": m4t.has_nvls(),
             "numa_bind": numa,
@@ -205,13 +251,30 @@ def main() -> int:
         },
         "final_loss": final_loss,
     }
+    if checks is not None:
+        out["checks"] = checks
     if not args.no_extras:
+        # the same step with weight.grad + a separate SGD update (no optimizer inside backward)
         try:
-            from benchmarks.extras import allreduce_busbw_sweep
-
-            out["allreduce_fwd_bwd_busbw_gbs"] = allreduce_busbw_sweep(comm, dev, quick=True)
+            plain = DPLinearModel(IN_F, OUT_F, comm, device=dev, dtype=torch.bfloat16, lr=1e-5, fused=not args.unfused,
+                                  sgd_in_backward=False, seed=1)
+            ms, _, _ = timed(lambda i: step(i, plain), max(5, args.steps // 2), 3)
+            out["plain_autograd_sgd_ms_per_step"] = ms / max(5, args.steps // 2)
+            del plain
         except Exception as exc:  # pragma: no cover
-            out["allreduce_fwd_bwd_busbw_gbs"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+            out["plain_autograd_sgd_ms_per_step"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        if size > 1:
+            try:
+                from benchmarks.extras import allreduce_busbw_sweep
+
+                out["allreduce_fwd_bwd_busbw_gbs"] = allreduce_busbw_sweep(comm, dev, quick=not args.full_sweep)
+                out["allreduce_sweep_dtype"] = "bfloat16"
+            except Exception as exc:  # pragma: no cover
+                out["allreduce_fwd_bwd_busbw_gbs"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        comm.Barrier()
+        if rank == 0:
+            out["linreg_cpu_np2_step_per_s"] = linreg_cpu_step_per_s()
+        comm.Barrier()
     if rank == 0:
         print(json.dumps(out), flush=True)
     return 0

@@ -349,14 +349,20 @@ def comm_from_mpi4py(comm) -> MPI_Communicator:
     except AttributeError as exc:  # pragma: no cover
         raise RuntimeError("mpi4py is not available!") from exc
     world = __getattr__("COMM_WORLD") if "COMM_WORLD" not in globals() else globals()["COMM_WORLD"]
-    if size == world.size and rank == world.rank:
-        return world
     if not hasattr(comm, "allgather"):
+        # no way to learn the members: only a communicator that looks like the world is accepted
+        if size == world.size and rank == world.rank:
+            return world
         raise RuntimeError(
             "mpi4torch_b200: the communicator has "
             f"rank {rank}/{size} but this process is rank {world.rank}/{world.size}, and it offers no "
             "allgather() to discover its members")
+    # The world-or-Split decision must be the same on every rank (Split is collective over the
+    # world): decide from the member list, which all ranks of the group see identically, never from
+    # this rank's own position (a reordered world keeps some ranks in place).
     members = [int(r) for r in comm.allgather(world.rank)]
+    if members == list(range(world.size)):
+        return world
     sub = world.Split(min(members), rank)
     if sub.size != size or sub.rank != rank:
         raise RuntimeError(f"mpi4torch_b200: rebuilt communicator is {sub.rank}/{sub.size}, expected {rank}/{size}")

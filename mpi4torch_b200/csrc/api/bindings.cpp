@@ -125,6 +125,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     else if (key == "force_algo") t.force_algo = static_cast<int>(value);
     else TORCH_CHECK(false, "unknown tuning key ", key);
   });
+  m.def("kernel_launch_table", [] {
+    py::dict d;
+    for (const auto& kv : kernel_launch_table()) d[py::str(kv.first)] = static_cast<int64_t>(kv.second);
+    return d;
+  }, "Launch counts of the named (tensor-core / fused) kernels in this process.");
   m.def("kernel_launch_count", [] { return static_cast<int64_t>(kernel_launch_count()); },
         "Kernels launched by this library in this process.");
   // Slab-plan introspection (tests): every job as a dict of plain integers.

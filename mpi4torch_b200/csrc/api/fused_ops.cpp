@@ -158,8 +158,16 @@ void allreduce_axpy_(Tensor param, const Tensor& grad, double scale, int64_t max
   comm->raw_allreduce_axpy_(param, grad, scale, max_blocks);
 }
 
-// G = dy^T @ x on the tcgen05 path with MN-major operands (no transposed copies).  Experimental.
-Tensor wgrad_bf16(const Tensor& dy, const Tensor& x) {
+const float* grad_scale_ptr(const c10::optional<Tensor>& gs, const Tensor& like) {
+  if (!gs.has_value() || !gs->defined()) return nullptr;
+  TORCH_CHECK(gs->is_cuda() && gs->device() == like.device() && gs->scalar_type() == at::kFloat && gs->numel() == 1,
+              "mpi4torch_b200: grad_scale must be a one-element fp32 tensor on the same device");
+  return gs->data_ptr<float>();
+}
+
+// G = grad_scale * dy^T @ x on the tcgen05 path with MN-major operands (no transposed copies).
+// grad_scale is a device scalar (the upstream gradient of the loss as autograd delivers it).
+Tensor wgrad_bf16(const Tensor& dy, const Tensor& x, const c10::optional<Tensor>& grad_scale) {
   check_2d_bf16(dy, "dy");
   check_2d_bf16(x, "x");
   TORCH_CHECK(dy.size(0) == x.size(0), "mpi4torch_b200: batch dimensions differ");
@@ -168,8 +176,25 @@ Tensor wgrad_bf16(const Tensor& dy, const Tensor& x) {
   std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
   launch_wgrad_bf16(dy.data_ptr(), x.data_ptr(), gw.data_ptr(), dy.size(0), dy.size(1), x.size(1), dy.stride(0),
                     x.stride(0), gw.stride(0), backend().device_comm().sm_count,
-                    c10::cuda::getCurrentCUDAStream(x.device().index()).stream());
+                    c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), grad_scale_ptr(grad_scale, x));
   return gw;
+}
+
+// w += scale * grad_scale * dy^T @ x: the single-rank SGD step as the wgrad GEMM's own epilogue
+// (no gradient tensor, one kernel).  Not a collective.
+void wgrad_sgd_(Tensor w, const Tensor& dy, const Tensor& x, double scale, const c10::optional<Tensor>& grad_scale) {
+  check_2d_bf16(dy, "dy");
+  check_2d_bf16(x, "x");
+  check_2d_bf16(w, "w");
+  TORCH_CHECK(dy.size(0) == x.size(0) && w.size(0) == dy.size(1) && w.size(1) == x.size(1),
+              "mpi4torch_b200: wgrad_sgd_ shape mismatch");
+  TORCH_CHECK(scale != 0.0, "mpi4torch_b200: wgrad_sgd_ needs a non-zero scale");
+  c10::cuda::CUDAGuard guard(x.device());
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  launch_wgrad_bf16(dy.data_ptr(), x.data_ptr(), w.data_ptr(), dy.size(0), dy.size(1), x.size(1), dy.stride(0),
+                    x.stride(0), w.stride(0), backend().device_comm().sm_count,
+                    c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), grad_scale_ptr(grad_scale, x),
+                    static_cast<float>(scale));
 }
 
 bool wgrad_bf16_ok(const Tensor& dy, const Tensor& x) {
@@ -191,24 +216,28 @@ bool wgrad_allreduce_sgd_supported(const Tensor& w, const Tensor& dy, const Tens
 
 // w += scale * sum_ranks(dy^T @ x): backward GEMM, gradient all-reduce and SGD step in one kernel.
 // Collective; `w` must be a replicated symmetric_empty() tensor.  Experimental (M4T_FUSED_WGRAD=1).
-void wgrad_allreduce_sgd_(Tensor w, const Tensor& dy, const Tensor& x, double scale) {
+void wgrad_allreduce_sgd_(Tensor w, const Tensor& dy, const Tensor& x, double scale,
+                          const c10::optional<Tensor>& grad_scale) {
   TORCH_CHECK(wgrad_allreduce_sgd_supported(w, dy, x), "mpi4torch_b200: fused wgrad->Allreduce->SGD does not support these tensors");
   c10::cuda::CUDAGuard guard(x.device());
   std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
   backend().fused_wgrad_update(w.data_ptr(), dy.data_ptr(), x.data_ptr(), dy.size(0), w.size(0), w.size(1), dy.stride(0),
                                x.stride(0), static_cast<float>(scale),
-                               c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), false);
+                               c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), false,
+                               grad_scale_ptr(grad_scale, x));
 }
 
 // Same kernel, and additionally the parameter all-reduce of the NEXT forward: returns
 // W_avg = (1/size) * sum_ranks w_new (symmetric-heap memory, valid until the next call).
-Tensor wgrad_allreduce_sgd_prefetch_(Tensor w, const Tensor& dy, const Tensor& x, double scale) {
+Tensor wgrad_allreduce_sgd_prefetch_(Tensor w, const Tensor& dy, const Tensor& x, double scale,
+                                     const c10::optional<Tensor>& grad_scale) {
   TORCH_CHECK(wgrad_allreduce_sgd_supported(w, dy, x), "mpi4torch_b200: fused wgrad->Allreduce->SGD does not support these tensors");
   c10::cuda::CUDAGuard guard(x.device());
   std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
   const void* wavg = backend().fused_wgrad_update(w.data_ptr(), dy.data_ptr(), x.data_ptr(), dy.size(0), w.size(0), w.size(1),
                                                   dy.stride(0), x.stride(0), static_cast<float>(scale),
-                                                  c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), true);
+                                                  c10::cuda::getCurrentCUDAStream(x.device().index()).stream(), true,
+                                                  grad_scale_ptr(grad_scale, x));
   return torch::from_blob(const_cast<void*>(wavg), {w.size(0), w.size(1)}, w.options().requires_grad(false));
 }
 
@@ -240,13 +269,16 @@ std::tuple<Tensor, Tensor> linear_mse_forward_local(const Tensor& x, const Tenso
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
-  m.def("wgrad_allreduce_sgd_prefetch_(Tensor(a!) w, Tensor dy, Tensor x, float scale) -> Tensor", &wgrad_allreduce_sgd_prefetch_);
+  m.def("wgrad_allreduce_sgd_prefetch_(Tensor(a!) w, Tensor dy, Tensor x, float scale, Tensor? grad_scale=None) -> Tensor",
+        &wgrad_allreduce_sgd_prefetch_);
+  m.def("wgrad_sgd_(Tensor(a!) w, Tensor dy, Tensor x, float scale, Tensor? grad_scale=None) -> ()", &wgrad_sgd_);
   m.def("linear_mse_forward_local(Tensor x, Tensor w_avg, Tensor target, float loss_scale, float grad_scale) -> (Tensor, Tensor)",
         &linear_mse_forward_local);
-  m.def("wgrad_bf16(Tensor dy, Tensor x) -> Tensor", &wgrad_bf16);
+  m.def("wgrad_bf16(Tensor dy, Tensor x, Tensor? grad_scale=None) -> Tensor", &wgrad_bf16);
   m.def("wgrad_bf16_supported(Tensor dy, Tensor x) -> bool", &wgrad_bf16_ok);
   m.def("wgrad_allreduce_sgd_supported(Tensor w, Tensor dy, Tensor x) -> bool", &wgrad_allreduce_sgd_supported);
-  m.def("wgrad_allreduce_sgd_(Tensor(a!) w, Tensor dy, Tensor x, float scale) -> ()", &wgrad_allreduce_sgd_);
+  m.def("wgrad_allreduce_sgd_(Tensor(a!) w, Tensor dy, Tensor x, float scale, Tensor? grad_scale=None) -> ()",
+        &wgrad_allreduce_sgd_);
   m.def("linear_mse_forward(Tensor x, Tensor w, Tensor target, float scale, float loss_scale, float grad_scale, "
         "bool allow_fused) -> (Tensor, Tensor, Tensor)",
         &linear_mse_forward);

@@ -1,3 +1,6 @@
+#include <map>
+#include <mutex>
+#include <string>
 // Allreduce over NVLink 5 / NVSwitch: one launch per collective, forward AND
 // backward (the adjoint of Allreduce(SUM) is Allreduce(SUM), reference
 // csrc/extension.cpp:265-272), with the adjacent elementwise work fused in:
@@ -505,6 +508,25 @@ std::atomic<unsigned long long> g_kernel_launches{0};
 unsigned long long kernel_launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
 void note_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 
+namespace {
+std::mutex g_table_mu;
+std::map<std::string, unsigned long long>& launch_table() {
+  static std::map<std::string, unsigned long long> t;
+  return t;
+}
+}  // namespace
+
+void note_kernel_launch(const char* name) {
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> g(g_table_mu);
+  launch_table()[name] += 1;
+}
+
+std::vector<std::pair<std::string, unsigned long long>> kernel_launch_table() {
+  std::lock_guard<std::mutex> g(g_table_mu);
+  return {launch_table().begin(), launch_table().end()};
+}
+
 bool nvls_supported(DType dt, ReduceOp op) { return nvls_kind(dt, op) != NvlsKind::NONE; }
 
 int64_t allreduce_stage_bytes(int64_t n, DType dt, ArAlgo algo, int size) {
@@ -544,7 +566,8 @@ void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n
   a.nvec = (n * dtype_size(dt) + 15) / 16;
   a.slot_bytes = ((a.nvec * 16 + 127) / 128) * 128;
   a.aligned = is_aligned16(in) && is_aligned16(out) && (!epi.accumulate || is_aligned16(epi.accumulate));
-  a.skip_mask = static_cast<int>(env_i64("M4T_AR_DEBUG_SKIP", 0));
+  static const int skip_mask = static_cast<int>(env_i64("M4T_AR_DEBUG_SKIP", 0));  // read once (timing experiments)
+  a.skip_mask = skip_mask;
   a.sym_in_off = -1;
   M4T_CHECK(allreduce_stage_bytes(n, dt, algo, dc.sync.size) <= dc.half_bytes,
             "allreduce of " << n << " elements does not fit the staging half (" << dc.half_bytes << " B)");
@@ -564,7 +587,8 @@ void launch_allreduce(const DeviceComm& dc, const void* in, void* out, int64_t n
   const int64_t shard = (a.chunk_vecs + P - 1) / P;
   blocks = static_cast<int>(std::min<int64_t>(blocks, std::max<int64_t>(1, (shard + kThreads - 1) / kThreads)));
   // Pipelined role-split kernels: one 1024-thread CTA per SM, >= 2 chunks to overlap.
-  const bool pipelined = env_i64("M4T_AR_PIPE", 1) != 0 && a.nvec > a.chunk_vecs;
+  static const bool pipe_enabled = env_i64("M4T_AR_PIPE", 1) != 0;  // read once
+  const bool pipelined = pipe_enabled && a.nvec > a.chunk_vecs;
   if (pipelined) blocks = std::min(blocks, dc.sm_count);
   // zero copy: single-chunk kernels only (the chunk loop of the two-shot kernel indexes one buffer)
   if (!pipelined && a.nvec <= a.chunk_vecs && sym_in_off >= 0 && (sym_in_off & 15) == 0) a.sym_in_off = sym_in_off;

@@ -265,7 +265,7 @@ CUtensorMap make_tmap(const void* base, int64_t rows, int64_t cols, int64_t ld, 
 void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, what << " launch failed: " << cudaGetErrorString(e));
-  note_kernel_launch();
+  note_kernel_launch(what);
 }
 
 template <bool FUSED, int EPI> void configure_once() {
@@ -346,7 +346,8 @@ void launch_fused_allreduce_gemm(const DeviceComm& dc, const void* x, void* y, i
   cm.flags_off = flags_off;
   cm.scale = scale;
   cm.do_barrier = 1;
-  cm.debug_skip = static_cast<int>(env_i64("M4T_FUSED_DEBUG", 0));
+  static const int fused_debug = static_cast<int>(env_i64("M4T_FUSED_DEBUG", 0));  // read once
+  cm.debug_skip = fused_debug;
   if (cm.debug_skip & 2) g.M = 0;  // timing experiment: communication only, no GEMM tiles
   // the grid must be identical on every rank (per-block barrier + counter targets)
   const int grid = fused_gemm_grid(dc);

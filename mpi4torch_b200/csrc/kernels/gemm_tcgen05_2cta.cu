@@ -313,7 +313,7 @@ void launch_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int64_t M, 
   }
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "gemm_bf16_tn_2cta launch failed: " << cudaGetErrorString(e));
-  note_kernel_launch();
+  note_kernel_launch(mse ? "gemm_2cta_mse_epilogue" : "gemm_2cta");
 }
 
 // Fused Allreduce->GEMM on CTA pairs.  Same contract as launch_fused_allreduce_gemm.
@@ -346,7 +346,8 @@ void launch_fused_allreduce_gemm_2cta(const DeviceComm& dc, const void* x, void*
   cm.flags_off = flags_off;
   cm.scale = scale;
   cm.do_barrier = 1;
-  cm.debug_skip = static_cast<int>(env_i64("M4T_FUSED_DEBUG", 0));
+  static const int fused_debug = static_cast<int>(env_i64("M4T_FUSED_DEBUG", 0));  // read once
+  cm.debug_skip = fused_debug;
   if (cm.debug_skip & 2) g.M = 0;  // timing experiment: communication only, no GEMM tiles
   const int grid = fused_gemm_grid(dc);  // identical on every rank, even (whole CTA pairs)
   if (mse) {
@@ -363,7 +364,7 @@ void launch_fused_allreduce_gemm_2cta(const DeviceComm& dc, const void* x, void*
   }
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "fused_allreduce_gemm_2cta launch failed: " << cudaGetErrorString(e));
-  note_kernel_launch();
+  note_kernel_launch(mse ? "fused_allreduce_gemm_2cta_mse" : "fused_allreduce_gemm_2cta");
 }
 
 }  // namespace m4t

@@ -1,6 +1,9 @@
 // Host-callable launchers of the sm_100a kernels.  Torch-free; the CUDA backend
 // (runtime/cuda_backend.cpp) fills a DeviceComm once and passes it by value.
 #pragma once
+#include <string>
+#include <utility>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "../runtime/common.h"
@@ -28,6 +31,9 @@ struct DeviceComm {
 // "gpu_launches" evidence).
 unsigned long long kernel_launch_count();
 void note_kernel_launch();
+// Same, and additionally tallied under `name` (bench.py reports which code paths really ran).
+void note_kernel_launch(const char* name);
+std::vector<std::pair<std::string, unsigned long long>> kernel_launch_table();
 
 enum class ArAlgo : int { AUTO = 0, ONESHOT = 1, TWOSHOT = 2, NVLS = 3, LOCAL = 4 };
 
@@ -124,7 +130,10 @@ int fused_gemm_grid(const DeviceComm& dc);
 bool wgrad_bf16_supported(int64_t Mb, int64_t N, int64_t K, const void* dy, const void* x, const void* g, int64_t ldy,
                           int64_t ldx, int64_t ldg);
 void launch_wgrad_bf16(const void* dy, const void* x, void* g, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
-                       int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream);
+                       int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream, const float* gscale = nullptr,
+                       float axpy = 0.0f);
+// gscale: optional device scalar folded into the epilogue; axpy != 0: g <- g + axpy * gscale * (dy^T x)
+// (the single-rank SGD step as the GEMM's own epilogue).
 // wgrad GEMM -> reduce-scatter through the switch -> W += scale * sum -> multicast of the new
 // weights, ONE kernel.  W (bf16 [N,K] contiguous) lives at heap offset w_off on every rank and
 // must be replicated (identical on all ranks), as it is under data-parallel SGD.
@@ -134,7 +143,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
                                uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
-                               int64_t epoch_off = -1);
+                               int64_t epoch_off = -1, const float* gscale = nullptr);
 // epoch_off >= 0: tile_target / done_target are PER-CALL increments and the call index lives in the local
 // device word at that heap offset (advanced by the kernel): no host-side step state, graph-capturable.
 // wavg_off >= 0: additionally leaves (1/P) * sum_ranks W_new in the bf16 [N,K] buffer at that heap

@@ -67,6 +67,9 @@ struct WgradArgs {
   int Mb, N, K;
   int ldo;              // leading dimension of out (elements)
   int ksplit;
+  const float* gscale;  // optional device scalar multiplied into every output element (the upstream
+                        // gradient of the loss: autograd hands it over as a tensor, never through the host)
+  float axpy;           // plain mode with axpy != 0: out <- out + axpy * gscale * G  (single-rank SGD epilogue)
 };
 
 struct WgradComm {
@@ -372,18 +375,33 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       const int row = n_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
       uint16_t* orow = reinterpret_cast<uint16_t*>(static_cast<char*>(g.out) + h * g.out_split_stride) +
                        static_cast<int64_t>(row) * g.ldo + k_blk * BN;
+      const float gs = (g.gscale ? __ldg(g.gscale) : 1.0f) * (g.axpy != 0.0f ? g.axpy : 1.0f);
+      const bool axpy = !FUSED && g.axpy != 0.0f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
+        Vec16 prev[4];
+        if (axpy) {  // the four 16-byte pieces of this lane's row are requested before the TMEM load
+#pragma unroll
+          for (int v = 0; v < 4; ++v) prev[v] = ld_vec(orow + c * 32 + v * 8);
+        }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32);
         tc::tmem_ld_32x32b_x32(taddr, r);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           Vec16 o;
+          if (axpy) {
+            float wv[8];
+            VecOf<DType::BF16>::unpack(prev[v], wv);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o.w[e] = pack2(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+            for (int e = 0; e < 8; ++e) wv[e] = fmaf(gs, __uint_as_float(r[v * 8 + e]), wv[e]);
+            o = VecOf<DType::BF16>::pack(wv);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o.w[e] = pack2(gs * __uint_as_float(r[v * 8 + 2 * e]), gs * __uint_as_float(r[v * 8 + 2 * e + 1]));
+          }
           st_vec(orow + c * 32 + v * 8, o);
         }
       }
@@ -435,7 +453,7 @@ bool wgrad_bf16_supported(int64_t Mb, int64_t N, int64_t K, const void* dy, cons
 }
 
 void launch_wgrad_bf16(const void* dy, const void* x, void* gout, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
-                       int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream) {
+                       int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream, const float* gscale, float axpy) {
   M4T_CHECK(wgrad_bf16_supported(Mb, N, K, dy, x, gout, ldy, ldx, ldg),
             "unsupported wgrad shape/alignment for the tcgen05 path (N % 256, K % 256, batch % 64)");
   const CUtensorMap ta = make_tmap_mn(dy, Mb, N, ldy);
@@ -448,13 +466,15 @@ void launch_wgrad_bf16(const void* dy, const void* x, void* gout, int64_t Mb, in
   g.K = static_cast<int>(K);
   g.ldo = static_cast<int>(ldg);
   g.ksplit = 1;
+  g.gscale = gscale;
+  g.axpy = axpy;
   const int tiles = static_cast<int>((N / BM2) * (K / BN));
   const int clusters = std::max(1, std::min(tiles, sm_count / 2));
   configure_w<false>();
   wgrad_bf16_nt_2cta_kernel<false><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, WgradComm{});
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "wgrad_bf16 launch failed: " << cudaGetErrorString(e));
-  note_kernel_launch();
+  note_kernel_launch(axpy != 0.0f ? "wgrad_2cta_sgd_epilogue" : "wgrad_2cta");
 }
 
 int64_t fused_wgrad_tiles(int64_t N, int64_t K) { return (N / BM2) * (K / BN); }
@@ -464,7 +484,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
                                uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
-                               int64_t epoch_off) {
+                               int64_t epoch_off, const float* gscale) {
   M4T_CHECK(dc.mc_heap != nullptr, "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping");
   M4T_CHECK(ksplit == 1 || ksplit == 2, "ksplit must be 1 or 2");
   M4T_CHECK((Mb / BK) % ksplit == 0, "batch / 64 must be divisible by ksplit");
@@ -480,6 +500,8 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   g.K = static_cast<int>(K);
   g.ldo = static_cast<int>(K);
   g.ksplit = ksplit;
+  g.gscale = gscale;
+  g.axpy = 0.0f;
   WgradComm wc{};
   wc.sync = dc.sync;
   for (int p = 0; p < dc.sync.size; ++p) wc.heap[p] = dc.heap[p];
@@ -503,7 +525,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, wc);
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "fused_wgrad_update launch failed: " << cudaGetErrorString(e));
-  note_kernel_launch();
+  note_kernel_launch(wc.prefetch ? "fused_wgrad_reduce_scatter_sgd_prefetch" : "fused_wgrad_reduce_scatter_sgd");
 }
 
 }  // namespace m4t

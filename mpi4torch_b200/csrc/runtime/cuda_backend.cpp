@@ -325,10 +325,11 @@ int64_t CudaBackend::symm_alloc(int64_t bytes) {
 
 bool CudaBackend::fused_linear_available(int64_t N, int64_t K) const {
   if (size() <= 1 || !has_nvls()) return false;
-  if (env_i64("M4T_FUSED_LINEAR", 1) == 0) return false;
+  static const int64_t fused_linear_mode = env_i64("M4T_FUSED_LINEAR", 1);  // read once
+  if (fused_linear_mode == 0) return false;
   // in-switch reduction only pays off from ~4 ranks (measured: at P=2 the
   // separate peer-load allreduce + GEMM is as fast as the fused kernel)
-  if (size() < tune_.nvls_min_ranks && env_i64("M4T_FUSED_LINEAR", 1) != 2) return false;
+  if (size() < tune_.nvls_min_ranks && fused_linear_mode != 2) return false;
   if (N % 256 != 0 || 256 % size() != 0 || K % 64 != 0) return false;
   const int64_t need = 3 * N * K * 2 + 4096;
   return fused_.count((N << 32) | K) > 0 || symm_cursor_ + need + 4096 <= symm_bytes_;
@@ -392,9 +393,8 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
 
 bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, int64_t K) const {
   if (size() <= 1 || !has_nvls()) return false;
-  const int64_t mode = env_i64("M4T_FUSED_WGRAD", 0);  // experimental: opt-in
+  static const int64_t mode = env_i64("M4T_FUSED_WGRAD", 1);  // read once; 0 disables the fused backward
   if (mode == 0) return false;
-  if (size() < tune_.nvls_min_ranks && mode != 2) return false;
   if (N % 256 != 0 || K % 256 != 0 || Mb % 128 != 0) return false;
   const char* wb = static_cast<const char*>(w);
   const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
@@ -405,7 +405,7 @@ bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, in
 
 const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                             int64_t ldy, int64_t ldx, float scale, cudaStream_t stream,
-                                            bool prefetch_avg) {
+                                            bool prefetch_avg, const float* gscale) {
   check_device_error();
   M4T_CHECK(fused_wgrad_available(w, Mb, N, K), "fused wgrad->Allreduce->SGD unavailable for N=" << N << " K=" << K
                                                     << " (needs NVLS, M4T_FUSED_WGRAD=1 and a symmetric weight)");
@@ -415,7 +415,8 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
   if (it == wgrad_.end()) {
     FusedWgradState st;
     // two work units per tile even out the last wave on 74 CTA pairs (M4T_WGRAD_KSPLIT=1 disables)
-    st.ksplit = (env_i64("M4T_WGRAD_KSPLIT", 2) >= 2 && (Mb / 64) % 2 == 0) ? 2 : 1;
+    static const int64_t ksplit_env = env_i64("M4T_WGRAD_KSPLIT", 2);  // read once
+    st.ksplit = (ksplit_env >= 2 && (Mb / 64) % 2 == 0) ? 2 : 1;
     st.stage_stride = round_up64(N * K * 2, 1024);
     st.stage_off = symm_alloc(st.stage_stride * st.ksplit);
     st.cnt_off = symm_alloc(fused_wgrad_tiles(N, K) * 4);
@@ -433,7 +434,7 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
   const uint32_t done_target = static_cast<uint32_t>(size() * fused_gemm_grid(dc_));
   launch_fused_wgrad_update(dc_, dy, x, Mb, N, K, ldy, ldx, w_off, st.stage_off, st.stage_stride, st.cnt_off,
                             st.done_off, st.ksplit, tile_target, done_target, scale, prefetch_avg ? st.wavg_off : -1,
-                            stream, st.epoch_off);
+                            stream, st.epoch_off, gscale);
   return prefetch_avg ? symm_ptr(st.wavg_off) : nullptr;
 }
 

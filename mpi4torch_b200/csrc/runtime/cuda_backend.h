@@ -81,7 +81,8 @@ class CudaBackend final : public Backend {
   // prefetch_avg: also all-reduce the updated weights (x 1/size) into a symmetric buffer whose
   // address is returned - the next forward can then run as a plain local GEMM.
   const void* fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
-                                 int64_t ldx, float scale, cudaStream_t stream, bool prefetch_avg = false);
+                                 int64_t ldx, float scale, cudaStream_t stream, bool prefetch_avg = false,
+                                 const float* gscale = nullptr);
 
   // Throws if a device-side wait timed out since the last check.
   void check_device_error();

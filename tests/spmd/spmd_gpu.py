@@ -243,25 +243,85 @@ class TestFusedAllreduceLinear(unittest.TestCase):
 
 @unittest.skipUnless(CUDA, "needs the CUDA backend")
 class TestFusedTrainingStep(unittest.TestCase):
-    def test_fast_step_matches_autograd_step(self):
+    def _reference_step(self, w, x, t, lr):
+        """The same step written with plain fp32 torch ops + the library's differentiable Allreduce."""
+        w = w.detach().float().requires_grad_()
+        w_avg = comm.Allreduce(w, m4t.MPI_SUM) / P
+        y = x.float() @ w_avg.to(torch.bfloat16).float().t()
+        local = (y - t.float()).square().sum() / (x.shape[0] * P)
+        loss = comm.Allreduce(local.reshape(1), m4t.MPI_SUM)
+        loss.backward()
+        return float(loss), (w.detach() - lr * w.grad)
+
+    def test_autograd_step_matches_fp32_reference(self):
+        """loss.backward() through dp_linear_mse + Allreduce: every configuration of the model (optimizer
+        inside the backward kernel or not, fused forward or not) against the fp32 composition."""
         from mpi4torch_b200.models import DPLinearModel
 
-        fast = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=3, fast=True)
-        slow = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=3, fast=False, fused=False)
-        g = torch.Generator().manual_seed(77 + R)
-        for step in range(3):
-            x = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
-            t = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)
-            lf = float(fast.train_step(x, t))
-            ls = float(slow.train_step(x, t))
-            self.assertLess(abs(lf - ls) / (abs(ls) + 1e-6), 2e-2, f"step {step}: {lf} vs {ls}")
-        diff = (fast.weight.float() - slow.weight.float()).abs().max().item()
-        self.assertLess(diff, 3e-2)
-        # all ranks hold identical weights after the fused allreduce+SGD epilogue
-        self.assertTrue(torch.equal(fast.weight.detach(), comm.Bcast_(fast.weight.detach().clone(), 0)))
+        for in_bwd, fused in ((True, True), (False, True), (False, False)):
+            model = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=3, fused=fused,
+                                  sgd_in_backward=in_bwd)
+            g = torch.Generator().manual_seed(77 + R)
+            for step in range(3):
+                x = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
+                t = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)
+                ref_loss, ref_w = self._reference_step(model.weight, x, t, 1e-2)
+                lf = float(model.train_step(x, t))
+                self.assertLess(abs(lf - ref_loss) / (abs(ref_loss) + 1e-6), 1e-2, f"{in_bwd},{fused} step {step}")
+                diff = (model.weight.detach().float() - ref_w).abs().max().item()
+                self.assertLess(diff, 2e-2, f"{in_bwd},{fused} step {step}")
+                self.assertIsNone(model.weight.grad)
+            # all ranks hold bit-identical weights after the fused reduce-scatter + SGD + multicast
+            self.assertTrue(torch.equal(model.weight.detach(), comm.Bcast_(model.weight.detach().clone(), 0)))
 
-    @unittest.skipUnless(os.environ.get("M4T_TEST_EXPERIMENTAL", "0") == "1" and os.environ.get("M4T_FUSED_WGRAD", "0") != "0",
-                         "experimental kernel: set M4T_TEST_EXPERIMENTAL=1 M4T_FUSED_WGRAD=2")
+    def test_in_backward_optimizer_is_active_when_supported(self):
+        from mpi4torch_b200.models import DPLinearModel
+        from mpi4torch_b200.ops import in_backward_sgd_supported
+
+        model = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=4)
+        x = torch.randn(384, 256).to(torch.bfloat16).to(DEVICE)
+        t = torch.randn(384, 512).to(torch.bfloat16).to(DEVICE)
+        expect = P == 1 or m4t.has_nvls()
+        self.assertEqual(in_backward_sgd_supported(x, model.weight, comm), expect)
+        loss = model.loss(x, t)
+        self.assertIn("MPIAllreduceSumBackward", loss.grad_fn.name())  # the loss Allreduce is a graph node
+        w0 = model.weight.detach().clone()
+        loss.backward()
+        if expect:
+            self.assertIsNone(model.weight.grad)           # the update happened inside backward
+            self.assertFalse(torch.equal(w0, model.weight.detach()))
+        else:
+            self.assertIsNotNone(model.weight.grad)
+        # a hand-made change of the weight invalidates the prefetched parameter average
+        with torch.no_grad():
+            model.weight.mul_(0.5)
+        ref_loss, _ = self._reference_step(model.weight, x, t, 1e-2)
+        l2 = float(model.train_step(x, t))
+        self.assertLess(abs(l2 - ref_loss) / (abs(ref_loss) + 1e-6), 1e-2)
+
+    def test_stacked_fused_layers_keep_their_saved_average(self):
+        """Three equal-shape fused forwards before backward (advisor finding, round 1): the saved W_avg
+        must survive the two-deep symmetric buffer being overwritten."""
+        from mpi4torch_b200.ops import allreduce_linear
+
+        n = k = 256
+        ws = [torch.randn(n, k, generator=torch.Generator().manual_seed(60 + 7 * i + R)).to(torch.bfloat16).mul_(0.1)
+              for i in range(3)]
+        x = torch.randn(128, k, generator=torch.Generator().manual_seed(5 + R)).to(torch.bfloat16).to(DEVICE)
+        outs = []
+        for force in (False, True):
+            xi = x.clone().requires_grad_()
+            params = [w.to(DEVICE).requires_grad_() for w in ws]
+            h = xi
+            for p in params:
+                h = allreduce_linear(h, p, comm, force_unfused=force)
+            h.float().square().sum().backward()
+            outs.append((xi.grad.float(), [p.grad.float() for p in params]))
+        scale = outs[1][0].abs().max().item() + 1e-6
+        self.assertLess((outs[0][0] - outs[1][0]).abs().max().item() / scale, 5e-2)
+        for a, b in zip(outs[0][1], outs[1][1]):
+            self.assertLess((a - b).abs().max().item() / (b.abs().max().item() + 1e-6), 5e-2)
+
     def test_fused_wgrad_update_matches_composition(self):
         if P < 2 or not m4t.has_nvls():
             return
@@ -271,14 +331,16 @@ class TestFusedTrainingStep(unittest.TestCase):
         w = m4t.symmetric_empty((N, K), torch.bfloat16)
         w.copy_(w0)
         gr = torch.Generator().manual_seed(100 + R)
+        gs = torch.full((1,), 2.0, device=DEVICE)
         for step in range(3):
             dy = torch.randn(Mb, N, generator=gr).to(torch.bfloat16).to(DEVICE)
             x = torch.randn(Mb, K, generator=gr).to(torch.bfloat16).to(DEVICE)
             ref_w = w.detach().clone()
-            gw = (dy.float().t() @ x.float()).to(torch.bfloat16)
+            use_gs = step == 2
+            gw = ((2.0 if use_gs else 1.0) * (dy.float().t() @ x.float())).to(torch.bfloat16)
             torch.ops.mpi4torch_b200.allreduce_axpy_(ref_w, gw, -0.01 / P)
             self.assertTrue(torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_supported(w, dy, x))
-            torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(w, dy, x, -0.01 / P)
+            torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_(w, dy, x, -0.01 / P, gs if use_gs else None)
             torch.cuda.synchronize()
             self.assertLess((w.float() - ref_w.float()).abs().max().item(), 2e-2, f"step {step}")
             self.assertTrue(torch.equal(w, comm.Bcast_(w.detach().clone(), 0)))
@@ -307,13 +369,13 @@ class TestFusedTrainingStep(unittest.TestCase):
             self.assertTrue(torch.equal(y, ref), str(dt))
             self.assertTrue(torch.equal(x, src), "input must be untouched")
 
-    @unittest.skipUnless(os.environ.get("M4T_TEST_EXPERIMENTAL", "0") == "1", "CUDA-graph capture of the step: set M4T_TEST_EXPERIMENTAL=1")
     def test_graphed_step_matches_eager_step(self):
         from mpi4torch_b200.models import DPLinearModel
 
-        eager = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False)
-        graphed = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False)
-        eager.fused_wgrad = graphed.fused_wgrad = False  # independent of the M4T_FUSED_WGRAD environment
+        # prefetch=False: the captured step re-averages the weights itself, so resetting them by hand below is visible
+        eager = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False, prefetch=False)
+        graphed = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=5, fused=False,
+                                prefetch=False)
         g = torch.Generator().manual_seed(300 + R)
         x = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
         t = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)
@@ -321,6 +383,7 @@ class TestFusedTrainingStep(unittest.TestCase):
         replay, sx, st, loss = graphed.make_graphed_step(x, t)
         with torch.no_grad():
             graphed.weight.copy_(w0)  # undo the warm-up / capture steps
+        graphed.optimizer.invalidate()
         for step in range(3):
             xb = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)
             tb = torch.randn(384, 512, generator=g).to(torch.bfloat16).to(DEVICE)

@@ -121,6 +121,38 @@ class TestSplit(unittest.TestCase):
         self.assertEqual(float(y[0]), float(sum(members)))
         self.assertEqual(torch.ops.mpi4torch_b200.comm_from_fortran(0).GetSize(), P)
 
+    def test_comm_from_mpi4py_reordered_world_is_decided_collectively(self):
+        """A world-sized communicator with reversed ranks (comm.Split(0, key=-rank)): the middle rank of
+        an odd world keeps its index, yet every rank must take the Split path (advisor finding, round 1)."""
+        order = list(range(P - 1, -1, -1))  # new rank i is world rank P-1-i
+
+        class Reversed:
+            def Get_size(self):
+                return P
+
+            def Get_rank(self):
+                return order.index(R)
+
+            def allgather(self, value):
+                assert value == R
+                return list(order)
+
+        sub = m4t.comm_from_mpi4py(Reversed())
+        self.assertEqual((sub.rank, sub.size), (P - 1 - R, P))
+        if P > 1:
+            self.assertFalse(sub.is_world)
+        g = sub.Allgather(torch.full((1,), float(R), dtype=torch.double, device=DEVICE), 0)
+        self.assertEqual(g.cpu().tolist(), [float(w) for w in order])
+
+        class Identity(Reversed):
+            def Get_rank(self):
+                return R
+
+            def allgather(self, value):
+                return list(range(P))
+
+        self.assertTrue(m4t.comm_from_mpi4py(Identity()).is_world)
+
     def test_errors(self):
         lone = comm.Split(-1 if R == 0 else 0, 0)  # MPI_UNDEFINED: rank 0 stays alone
         self.assertEqual(lone.size, 1 if R == 0 else P - 1)
