@@ -251,6 +251,22 @@ class MPI_Communicator:
         ``scatteraxis`` on this rank (the adjoint of :meth:`Allgather`)."""
         return self._comm.Reduce_scatter(tensor, op, scatteraxis, numelem)
 
+    def Reduce_scatterFused(self, tensor: torch.Tensor, op: int, scatteraxis: int, numelem: int, scale: float,
+                            accumulate: Optional[torch.Tensor]) -> torch.Tensor:
+        """``accumulate + scale * Reduce_scatter(tensor, op)`` in ONE kernel: the scale, the cast to the
+        output dtype and the accumulation into an existing gradient run in the reducing kernel's
+        epilogue (the reference's Allgather backward adds the scattered pieces with a separate ``+=``,
+        csrc/extension.cpp:616-631).  Backward: ``Allgather(scale * grad)``; ``accumulate`` receives the
+        incoming gradient."""
+        return self._comm.Reduce_scatterFused(tensor, op, scatteraxis, numelem, scale, accumulate)
+
+    def assume_uniform_sizes(self, on: bool = True) -> None:
+        """Promise that every rank passes identically shaped tensors and the same ``numelem`` to
+        Gather / Allgather / Scatter / Alltoall / Reduce_scatter.  The host-side size exchange (the
+        reference's ``MPI_Gather`` / ``MPI_Allgather`` of axis lengths, csrc/extension.cpp:540,675) is then
+        skipped and these ops become pure stream work, capturable into a CUDA graph."""
+        self._comm.AssumeUniformSizes(on)
+
     def Isend(self, tensor: torch.Tensor, dest: int, tag: int) -> WaitHandle:
         """Start a non-blocking send."""
         return WaitHandle(self._comm.Isend(tensor, dest, tag))

@@ -149,17 +149,25 @@ struct MPIAllgatherBackward : public Function<MPIAllgatherBackward> {
 // ----------------------------------------------------------- Reduce_scatter
 struct MPIReduceScatterBackward : public Function<MPIReduceScatterBackward> {
   static Tensor forward(AutogradContext* ctx, const Tensor& input, c10::intrusive_ptr<Communicator> comm, int64_t op,
-                        int64_t axis, int64_t numelem) {
+                        int64_t axis, int64_t numelem, double scale, bool has_scale,
+                        const c10::optional<Tensor>& accumulate) {
     const int64_t ax = axis < 0 ? axis + input.dim() : axis;
     ctx->saved_data["comm"] = comm;
     ctx->saved_data["op"] = op;
     ctx->saved_data["axis"] = ax;
-    return comm->raw_reduce_scatter(input, op, axis, numelem);
+    ctx->saved_data["scale"] = scale;
+    ctx->saved_data["has_scale"] = has_scale;
+    ctx->saved_data["has_acc"] = accumulate.has_value() && accumulate->defined();
+    return comm->raw_reduce_scatter(input, op, axis, numelem, scale, has_scale, accumulate);
   }
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     if (ctx->saved_data["op"].toInt() != kOpSum) unimplemented_backward();
     auto comm = comm_from(ctx);
-    return {comm->Allgather(grads[0], ctx->saved_data["axis"].toInt()), Tensor(), Tensor(), Tensor(), Tensor()};
+    Tensor g = grads[0];
+    if (ctx->saved_data["has_scale"].toBool()) g = g * ctx->saved_data["scale"].toDouble();
+    Tensor gacc = ctx->saved_data["has_acc"].toBool() ? grads[0] : Tensor();
+    return {comm->Allgather(g, ctx->saved_data["axis"].toInt()), Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor(),
+            gacc};
   }
 };
 
@@ -367,7 +375,13 @@ Tensor Communicator::Alltoall(const Tensor& input, int64_t gatheraxis, int64_t s
 
 Tensor Communicator::Reduce_scatter(const Tensor& input, int64_t op, int64_t scatteraxis, int64_t numelem) {
   return MPIReduceScatterBackward::apply(input, c10::intrusive_ptr<Communicator>::reclaim_copy(this), op, scatteraxis,
-                                         numelem);
+                                         numelem, 1.0, false, c10::optional<Tensor>());
+}
+
+Tensor Communicator::Reduce_scatterFused(const Tensor& input, int64_t op, int64_t scatteraxis, int64_t numelem, double scale,
+                                         const c10::optional<Tensor>& accumulate) {
+  return MPIReduceScatterBackward::apply(input, c10::intrusive_ptr<Communicator>::reclaim_copy(this), op, scatteraxis,
+                                         numelem, scale, true, accumulate);
 }
 
 std::vector<Tensor> Communicator::Isend(const Tensor& input, int64_t dest, int64_t tag) {

@@ -62,6 +62,9 @@ TORCH_LIBRARY(mpi4torch_b200, m) {
       .def("Scatter", &Communicator::Scatter)
       .def("Alltoall", &Communicator::Alltoall)
       .def("Reduce_scatter", &Communicator::Reduce_scatter)
+      .def("Reduce_scatterFused", &Communicator::Reduce_scatterFused)
+      .def("AssumeUniformSizes", &Communicator::AssumeUniformSizes)
+      .def("UniformSizes", &Communicator::UniformSizes)
       .def("Isend", &Communicator::Isend)
       .def("Irecv", &Communicator::Irecv)
       .def("Wait", &Communicator::Wait)
@@ -123,6 +126,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     else if (key == "slab_blocks") t.slab_blocks = static_cast<int>(value);
     else if (key == "p2p_blocks") t.p2p_blocks = static_cast<int>(value);
     else if (key == "force_algo") t.force_algo = static_cast<int>(value);
+    else if (key == "wgrad_debug") set_wgrad_debug(static_cast<int>(value));
     else TORCH_CHECK(false, "unknown tuning key ", key);
   });
   m.def("kernel_launch_table", [] {

@@ -263,6 +263,14 @@ void Communicator::raw_reduce_(Tensor& work, int64_t op_, int64_t root) {
   }
 }
 
+void Communicator::exchange_meta(const int64_t* mine, int words, int64_t* all) {
+  if (uniform_) {  // AssumeUniformSizes: every rank holds the same words, no host round
+    for (int64_t p = 0; p < size_; ++p) std::copy(mine, mine + words, all + p * words);
+    return;
+  }
+  cx().control().allgather_i64(mine, words, all);
+}
+
 Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root, bool all) {
   NvtxRange nvtx_range_("m4t::Gather");
   TORCH_CHECK(all || (root >= 0 && root < size_), "mpi4torch_b200: Gather root ", root, " out of range");
@@ -276,7 +284,7 @@ Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root
   // one metadata round: [axis length, before, after]
   int64_t mine[3] = {a3.axis, a3.before, a3.after};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
-  cx().control().allgather_i64(mine, 3, allmeta.data());
+  exchange_meta(mine, 3, allmeta.data());
   std::vector<int64_t> lens(static_cast<size_t>(size_));
   for (int64_t p = 0; p < size_; ++p) {
     lens[p] = allmeta[p * 3];
@@ -312,7 +320,7 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
   mine[1] = nd;
   for (int64_t i = 0; i < nd; ++i) mine[2 + i] = in.size(i);
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * kMetaWords);
-  cx().control().allgather_i64(mine.data(), kMetaWords, allmeta.data());
+  exchange_meta(mine.data(), kMetaWords, allmeta.data());
   const int64_t* rootmeta = allmeta.data() + root * kMetaWords;
   const int64_t rnd = rootmeta[1];
   std::vector<int64_t> rshape(rootmeta + 2, rootmeta + 2 + rnd);
@@ -351,7 +359,7 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
   const auto shape = in.sizes().vec();
   int64_t mine[2] = {numelem, shape[gaxis]};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 2);
-  cx().control().allgather_i64(mine, 2, allmeta.data());
+  exchange_meta(mine, 2, allmeta.data());
   std::vector<int64_t> counts(static_cast<size_t>(size_)), glen(static_cast<size_t>(size_));
   for (int64_t p = 0; p < size_; ++p) {
     counts[p] = allmeta[p * 2];
@@ -377,7 +385,8 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
   return r.from_comm(out);
 }
 
-Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_t axis_, int64_t numelem) {
+Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_t axis_, int64_t numelem, double scale,
+                                        bool has_scale, const c10::optional<Tensor>& accumulate) {
   NvtxRange nvtx_range_("m4t::Reduce_scatter");
   TORCH_CHECK(numelem >= 0, "mpi4torch_b200: Reduce_scatter numelem must be non-negative");
   const ReduceOp op = to_op(op_);
@@ -391,7 +400,7 @@ Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_
   const Axis3 a3 = split_axis(shape, axis);
   int64_t mine[3] = {numelem, a3.before * a3.after, a3.axis};
   std::vector<int64_t> allmeta(static_cast<size_t>(size_) * 3);
-  cx().control().allgather_i64(mine, 3, allmeta.data());
+  exchange_meta(mine, 3, allmeta.data());
   std::vector<int64_t> counts(static_cast<size_t>(size_));
   int64_t total = 0;
   for (int64_t p = 0; p < size_; ++p) {
@@ -407,7 +416,18 @@ Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_
   auto out_shape = shape;
   out_shape[axis] = numelem;
   Tensor out = at::empty(out_shape, in.options());
-  r.be->reduce_pull(plan, in.data_ptr(), out.data_ptr(), dt, op, Epilogue{}, r.stream);
+  Epilogue epi;
+  epi.scale = scale;
+  epi.has_scale = has_scale;
+  Tensor acc;
+  if (accumulate.has_value() && accumulate->defined()) {
+    TORCH_CHECK(accumulate->sizes().vec() == out_shape && accumulate->scalar_type() == input.scalar_type() &&
+                    accumulate->device() == input.device(),
+                "mpi4torch_b200: Reduce_scatter: the accumulate tensor must have the result's shape, dtype and device");
+    acc = r.to_comm(*accumulate);
+    epi.accumulate = acc.data_ptr();
+  }
+  r.be->reduce_pull(plan, in.data_ptr(), out.data_ptr(), dt, op, epi, r.stream);
   return r.from_comm(out);
 }
 

@@ -35,6 +35,11 @@ struct Communicator : torch::CustomClassHolder {
   Tensor Scatter(const Tensor& input, int64_t scatteraxis, int64_t numelem, int64_t root);
   Tensor Alltoall(const Tensor& input, int64_t gatheraxis, int64_t scatteraxis, int64_t numelem);
   Tensor Reduce_scatter(const Tensor& input, int64_t op, int64_t scatteraxis, int64_t numelem);
+  // out = accumulate + scale * Reduce_scatter(input): scale / cast / accumulate run in the reducing kernel's
+  // epilogue (the reference accumulates the scattered gradients with a separate `+=`, csrc/extension.cpp:616-631).
+  // Backward: Allgather of (scale * grad); `accumulate` receives the incoming gradient unchanged.
+  Tensor Reduce_scatterFused(const Tensor& input, int64_t op, int64_t scatteraxis, int64_t numelem, double scale,
+                             const c10::optional<Tensor>& accumulate);
 
   // ---- differentiable non-blocking point-to-point ---------------------------
   std::vector<Tensor> Isend(const Tensor& input, int64_t dest, int64_t tag);
@@ -48,6 +53,11 @@ struct Communicator : torch::CustomClassHolder {
   // reference gets sub-communicators from mpi4py, src/__init__.py:247-261.)
   c10::intrusive_ptr<Communicator> Split(int64_t color, int64_t key);
   bool IsWorld() const { return is_world_; }
+  // Promise that every rank passes identically shaped tensors and the same `numelem` to the variable-size
+  // ops (Gather / Allgather / Scatter / Alltoall / Reduce_scatter), as NCCL-style collectives require.  The
+  // host-side size exchange is then skipped: the ops become pure stream work (CUDA-graph capturable).
+  void AssumeUniformSizes(bool on) { uniform_ = on; }
+  bool UniformSizes() const { return uniform_; }
   // MPI_Comm_free: collective over the communicator; releases its segments and symmetric heap.
   // Without it a sub-communicator's resources live until the process finalizes.
   void Free();
@@ -64,7 +74,8 @@ struct Communicator : torch::CustomClassHolder {
   Tensor raw_gather(const Tensor& input, int64_t axis, int64_t root, bool all);
   Tensor raw_scatter(const Tensor& input, int64_t axis, int64_t numelem, int64_t root);
   Tensor raw_alltoall(const Tensor& input, int64_t gatheraxis, int64_t scatteraxis, int64_t numelem);
-  Tensor raw_reduce_scatter(const Tensor& input, int64_t op, int64_t axis, int64_t numelem);
+  Tensor raw_reduce_scatter(const Tensor& input, int64_t op, int64_t axis, int64_t numelem, double scale = 1.0,
+                            bool has_scale = false, const c10::optional<Tensor>& accumulate = c10::nullopt);
   std::vector<Tensor> raw_isend(const Tensor& input, int64_t dest, int64_t tag);
   std::vector<Tensor> raw_irecv(const Tensor& input, int64_t source, int64_t tag);
   Tensor raw_wait(const std::vector<Tensor>& handle);
@@ -82,6 +93,9 @@ struct Communicator : torch::CustomClassHolder {
   CommContext* ctx_;                        // world context (owned by World) or owned_.get()
   std::shared_ptr<CommContext> owned_;      // non-null for communicators created by Split
   int64_t rank_, size_;
+  bool uniform_ = false;
+  // one metadata round over the control plane, or a local fill under AssumeUniformSizes
+  void exchange_meta(const int64_t* mine, int words, int64_t* all);
 };
 
 // Differentiable dependency join (reference csrc/extension.cpp:1024-1046).

@@ -58,6 +58,31 @@ Tensor gemm_bf16_tn_2cta(const Tensor& x, const Tensor& w) {
   return y;
 }
 
+// y = a @ b with both operands row-major (dgrad: gy[M,N] @ W[N,K]); the weight is read in place through an
+// MN-major tcgen05 operand, no transposed copy.
+bool gemm_bf16_nn_ok(const Tensor& a, const Tensor& b) {
+  if (!(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.scalar_type() == at::kBFloat16 &&
+        b.scalar_type() == at::kBFloat16 && a.stride(1) == 1 && b.stride(1) == 1 && a.size(1) == b.size(0)))
+    return false;
+  return World::instance().cuda_ready() &&
+         gemm_bf16_nn_supported(a.size(0), b.size(1), a.size(1), a.data_ptr(), b.data_ptr(), a.data_ptr(), a.stride(0),
+                                b.stride(0), b.size(1));
+}
+
+Tensor gemm_bf16_nn(const Tensor& a, const Tensor& b) {
+  check_2d_bf16(a, "a");
+  check_2d_bf16(b, "b");
+  TORCH_CHECK(a.size(1) == b.size(0), "mpi4torch_b200: inner dimensions differ");
+  c10::cuda::CUDAGuard guard(a.device());
+  Tensor y = at::empty({a.size(0), b.size(1)}, a.options());
+  if (y.numel() == 0) return y;
+  std::lock_guard<std::recursive_mutex> g(World::instance().mutex());
+  launch_gemm_bf16_nn_2cta(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.size(0), b.size(1), a.size(1), a.stride(0),
+                           b.stride(0), y.stride(0), backend().device_comm().sm_count,
+                           c10::cuda::getCurrentCUDAStream(a.device().index()).stream());
+  return y;
+}
+
 bool gemm_bf16_tn_ok(const Tensor& x, const Tensor& w) {
   if (!(x.is_cuda() && w.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.scalar_type() == at::kBFloat16 &&
         w.scalar_type() == at::kBFloat16 && x.stride(1) == 1 && w.stride(1) == 1 && x.size(1) == w.size(1)))
@@ -285,6 +310,8 @@ TORCH_LIBRARY_FRAGMENT(mpi4torch_b200, m) {
   m.def("allreduce_axpy_(Tensor(a!) param, Tensor grad, float scale, int max_blocks=0) -> ()", &allreduce_axpy_);
   m.def("symmetric_empty(int[] shape, ScalarType dtype) -> Tensor", &symmetric_empty);
   m.def("gemm_bf16_tn(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn);
+  m.def("gemm_bf16_nn(Tensor a, Tensor b) -> Tensor", &gemm_bf16_nn);
+  m.def("gemm_bf16_nn_supported(Tensor a, Tensor b) -> bool", &gemm_bf16_nn_ok);
   m.def("gemm_bf16_tn_2cta(Tensor x, Tensor w) -> Tensor", &gemm_bf16_tn_2cta);
   m.def("gemm_bf16_tn_supported(Tensor x, Tensor w) -> bool", &gemm_bf16_tn_ok);
   m.def("allreduce_linear_supported(Tensor x, Tensor w) -> bool", &allreduce_linear_supported);

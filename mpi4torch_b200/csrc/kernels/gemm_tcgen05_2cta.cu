@@ -70,7 +70,21 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return static_cast<uint32_t>(float_to_bf16_bits(lo)) | (static_cast<uint32_t>(float_to_bf16_bits(hi)) << 16);
 }
 
-template <bool FUSED, int EPI>
+// B operand stored [K, N] row-major (the contraction dimension is the STRIDED one, as for the weight in
+// dgrad = gy @ W): TMA boxes of {64 contiguous n, BK k-rows}, MN-major SWIZZLE_128B canonical layout
+// (LBO = one 64-wide chunk, SBO = one 8-row swizzle atom), instruction-descriptor bit 16.
+constexpr int kBoxBytesMN = 64 * BK * 2;  // 8 KiB
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>(kBoxBytesMN >> 4) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;
+  d |= static_cast<uint64_t>(2u) << 61;
+  return d;
+}
+
+template <bool FUSED, int EPI, bool BMN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kWarps + (FUSED ? kCommWarps : 0)) * 32, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const Gemm2Args g, const CommArgs cm) {
@@ -140,7 +154,14 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint8_t* sb = sa + kABytes;
           if (leader) tc::mbar_arrive_expect_tx(&bars->full[stage], 2 * kStageBytes);  // both CTAs' bytes
           tc::tma_load_2d_2sm(sa, &tmap_a, &bars->full[stage], kb * BK, m_blk * BM2 + static_cast<int>(cta) * BMC);
-          tc::tma_load_2d_2sm(sb, &tmap_b, &bars->full[stage], kb * BK, n_blk * BN + static_cast<int>(cta) * BNH);
+          if (BMN) {
+#pragma unroll
+            for (int ch = 0; ch < BNH / 64; ++ch)
+              tc::tma_load_2d_2sm(sb + ch * kBoxBytesMN, &tmap_b, &bars->full[stage],
+                                  n_blk * BN + static_cast<int>(cta) * BNH + ch * 64, kb * BK);
+          } else {
+            tc::tma_load_2d_2sm(sb, &tmap_b, &bars->full[stage], kb * BK, n_blk * BN + static_cast<int>(cta) * BNH);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -151,7 +172,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM2, BN);
+      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM2, BN) | (BMN ? (1u << 16) : 0u);  // bit 16: B MN-major
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -167,11 +188,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t adesc = tc::make_smem_desc_k_sw128(sa);
-          const uint64_t bdesc = tc::make_smem_desc_k_sw128(sb);
+          const uint64_t bdesc = BMN ? make_smem_desc_mn_sw128(sb) : tc::make_smem_desc_k_sw128(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t koff = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-            tc::umma_bf16_ss_2sm(tmem_d, adesc + koff, bdesc + koff, idesc, (kb | k) ? 1u : 0u);
+            // MN-major: 16 k-rows = two 8-row swizzle atoms = 2048 bytes further into every chunk
+            const uint64_t koff_b = BMN ? static_cast<uint64_t>((k * UMMA_K * 128) >> 4) : koff;
+            tc::umma_bf16_ss_2sm(tmem_d, adesc + koff, bdesc + koff_b, idesc, (kb | k) ? 1u : 0u);
           }
           tc::umma_commit_2sm(&bars->empty[stage]);  // frees the stage in BOTH CTAs
           if (++stage == kStages) {
@@ -274,15 +297,43 @@ CUtensorMap make_tmap2(const void* base, int64_t rows, int64_t cols, int64_t ld,
   return make_tmap_bf16_sw128(base, rows, cols, ld, BK, box_rows);
 }
 
-template <bool FUSED, int EPI> void configure2() {
+template <bool FUSED, int EPI, bool BMN = false> void configure2() {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<FUSED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<FUSED, EPI, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
   });
 }
 
 }  // namespace
+
+bool gemm_bf16_nn_supported(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C, int64_t lda,
+                            int64_t ldb, int64_t ldc) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0 && al(A) && al(B) && al(C) && lda % 8 == 0 && ldb % 8 == 0 &&
+         ldc % 8 == 0 && lda >= K && ldb >= N && ldc >= N && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31);
+}
+
+// C[M,N] = A[M,K] * B[K,N], both row-major (the dgrad shape: gy @ W).
+void launch_gemm_bf16_nn_2cta(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                              int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream) {
+  M4T_CHECK(gemm_bf16_nn_supported(M, N, K, A, B, C, lda, ldb, ldc), "unsupported GEMM shape/alignment for the tcgen05 NN path");
+  const CUtensorMap ta = make_tmap2(A, M, K, lda, BMC);
+  const CUtensorMap tb = make_tmap_bf16_sw128(B, K, N, ldb, 64, BK);  // boxes of {64 n, BK k-rows}
+  Gemm2Args g{};
+  g.C = C;
+  g.M = static_cast<int>(M);
+  g.N = static_cast<int>(N);
+  g.K = static_cast<int>(K);
+  g.ldc = static_cast<int>(ldc);
+  const int tiles = static_cast<int>(((M + BM2 - 1) / BM2) * ((N + BN - 1) / BN));
+  const int clusters = std::max(1, std::min(tiles, sm_count / 2));
+  configure2<false, 0, true>();
+  gemm_bf16_tn_2cta_kernel<false, 0, true><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, CommArgs{});
+  cudaError_t e = cudaGetLastError();
+  M4T_CHECK(e == cudaSuccess, "gemm_bf16_nn_2cta launch failed: " << cudaGetErrorString(e));
+  note_kernel_launch("gemm_2cta_nn");
+}
 
 void launch_gemm_bf16_tn_2cta(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                               int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream, const MseEpilogue* mse) {

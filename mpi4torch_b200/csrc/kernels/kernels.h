@@ -129,6 +129,11 @@ int fused_gemm_grid(const DeviceComm& dc);
 // G[N,K] = dY[Mb,N]^T * X[Mb,K]: both operands MN-major, no transposed copies.
 bool wgrad_bf16_supported(int64_t Mb, int64_t N, int64_t K, const void* dy, const void* x, const void* g, int64_t ldy,
                           int64_t ldx, int64_t ldg);
+// C[M,N] = A[M,K] * B[K,N], both row-major bf16 (dgrad: gy @ W): the CTA-pair kernel with an MN-major B operand.
+bool gemm_bf16_nn_supported(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C, int64_t lda,
+                            int64_t ldb, int64_t ldc);
+void launch_gemm_bf16_nn_2cta(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                              int64_t ldb, int64_t ldc, int sm_count, cudaStream_t stream);
 void launch_wgrad_bf16(const void* dy, const void* x, void* g, int64_t Mb, int64_t N, int64_t K, int64_t ldy,
                        int64_t ldx, int64_t ldg, int sm_count, cudaStream_t stream, const float* gscale = nullptr,
                        float axpy = 0.0f);
@@ -137,6 +142,7 @@ void launch_wgrad_bf16(const void* dy, const void* x, void* g, int64_t Mb, int64
 // wgrad GEMM -> reduce-scatter through the switch -> W += scale * sum -> multicast of the new
 // weights, ONE kernel.  W (bf16 [N,K] contiguous) lives at heap offset w_off on every rank and
 // must be replicated (identical on all ranks), as it is under data-parallel SGD.
+void set_wgrad_debug(int mask);  // timing experiments (see WgradComm::debug)
 int64_t fused_wgrad_tiles(int64_t N, int64_t K);
 int fused_wgrad_signals_per_tile(int ksplit);
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,

@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 #include "kernels.h"
@@ -445,6 +446,10 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 }  // namespace
 
+// timing experiments only (scripts/wgrad_diag.py): initial value from M4T_WGRAD_DEBUG, changeable at run time
+static std::atomic<int> g_wgrad_debug{static_cast<int>(env_i64("M4T_WGRAD_DEBUG", 0))};
+void set_wgrad_debug(int mask) { g_wgrad_debug.store(mask, std::memory_order_relaxed); }
+
 bool wgrad_bf16_supported(int64_t Mb, int64_t N, int64_t K, const void* dy, const void* x, const void* g, int64_t ldy,
                           int64_t ldx, int64_t ldg) {
   return Mb > 0 && N > 0 && K > 0 && N % BM2 == 0 && K % BN == 0 && Mb % BK == 0 && aligned16(dy) && aligned16(x) &&
@@ -518,8 +523,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.prefetch = wavg_off >= 0 ? 1 : 0;
   wc.wavg_off = wavg_off >= 0 ? wavg_off : 0;
   wc.avg_scale = 1.0f / static_cast<float>(dc.sync.size);
-  static const int debug = static_cast<int>(env_i64("M4T_WGRAD_DEBUG", 0));  // read once: timing experiments only
-  wc.debug = debug;
+  wc.debug = g_wgrad_debug.load(std::memory_order_relaxed);
   const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
   configure_w<true>();
   wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, wc);

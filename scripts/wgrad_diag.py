@@ -1,5 +1,5 @@
-"""Timing variants of the fused backward (wgrad -> reduce-scatter -> SGD -> multicast), device events, max over ranks.
-VARIANT / M4T_WGRAD_DEBUG select the experiment; M4T_FUSED_WGRAD=2 must be set."""
+"""Timing variants of the fused backward (wgrad -> reduce-scatter -> SGD -> multicast), device events, max over
+ranks, all in one process (the experiment mask is switched with set_tuning("wgrad_debug", mask))."""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,18 +29,29 @@ def timeit(fn, n=10):
     return round(float(comm.Allreduce(v, m4t.MPI_MAX)[0]), 4)
 
 
-res = {"world": comm.size, "variant": os.environ.get("VARIANT", ""), "debug": os.environ.get("M4T_WGRAD_DEBUG", "0")}
-if os.environ.get("VARIANT", "") == "base":
-    gw = torch.empty(F, F, device=dev, dtype=torch.bfloat16)
-    res["wgrad_plain_ms"] = timeit(lambda: ops.wgrad_bf16(dy, x))
-    res["cublas_wgrad_ms"] = timeit(lambda: torch.mm(dy.t(), x, out=gw))
+def emit(d):
+    if comm.rank == 0:
+        print(json.dumps(d), flush=True)
+
+
+res = {"world": comm.size, "variant": "base"}
+gw = torch.empty(F, F, device=dev, dtype=torch.bfloat16)
+res["wgrad_plain_ms"] = timeit(lambda: ops.wgrad_bf16(dy, x))
+res["wgrad_sgd_epilogue_ms"] = timeit(lambda: ops.wgrad_sgd_(gw, dy, x, -1e-6))
+res["cublas_wgrad_ms"] = timeit(lambda: torch.mm(dy.t(), x, out=gw))
+if comm.size > 1:
     res["allreduce_axpy_32MiB_ms"] = timeit(lambda: ops.allreduce_axpy_(w, gw, -1e-6))
     res["allreduce_32MiB_ms"] = timeit(lambda: comm.Allreduce(gw, m4t.MPI_SUM))
-    one = torch.ones(1, device=dev)
-    res["allreduce_scalar_ms"] = timeit(lambda: comm.Allreduce(one, m4t.MPI_SUM), n=50)
-else:
-    assert ops.wgrad_allreduce_sgd_supported(w, dy, x)
-    res["fused_ms"] = timeit(lambda: ops.wgrad_allreduce_sgd_(w, dy, x, -1e-6))
-    res["fused_prefetch_ms"] = timeit(lambda: ops.wgrad_allreduce_sgd_prefetch_(w, dy, x, -1e-6))
-if comm.rank == 0:
-    print(json.dumps(res), flush=True)
+one = torch.ones(1, device=dev)
+res["allreduce_scalar_ms"] = timeit(lambda: comm.Allreduce(one, m4t.MPI_SUM), n=50)
+emit(res)
+if comm.size > 1 and ops.wgrad_allreduce_sgd_supported(w, dy, x):
+    for name, mask in (("full", 0), ("nocomm", 1), ("nogemm", 2), ("local_ld", 4), ("local_st", 8), ("local_ldst", 12),
+                       ("nogemm_local", 14)):
+        m4t._C.set_tuning("wgrad_debug", mask)
+        r = {"world": comm.size, "variant": name, "mask": mask}
+        r["fused_ms"] = timeit(lambda: ops.wgrad_allreduce_sgd_(w, dy, x, -1e-6))
+        if mask in (0, 2):
+            r["fused_prefetch_ms"] = timeit(lambda: ops.wgrad_allreduce_sgd_prefetch_(w, dy, x, -1e-6))
+        emit(r)
+    m4t._C.set_tuning("wgrad_debug", 0)

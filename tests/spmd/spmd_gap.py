@@ -8,7 +8,7 @@ import unittest
 import torch
 
 import mpi4torch_b200 as m4t
-from common import DEVICE, comm, rand
+from common import DEVICE, comm, ones, rand
 
 P, R = comm.size, comm.rank
 
@@ -159,6 +159,40 @@ class TestFusedEpilogue(unittest.TestCase):
         y.sum().backward()
         self.assertTrue(torch.allclose(x.grad, torch.ones_like(x)))  # (1/P) * Allreduce(ones)
         self.assertTrue(torch.equal(acc.grad, torch.ones_like(acc)))
+
+    def test_reduce_scatter_fused_scale_accumulate(self):
+        """accumulate + scale * Reduce_scatter(x) in the reducing kernel's epilogue, forward and backward
+        (the reference adds the scattered gradient pieces with a separate +=, csrc/extension.cpp:616-631)."""
+        x = (ones(2, 3 * P) * (comm.rank + 1)).requires_grad_()
+        acc = (ones(2, 3) * 10.0).requires_grad_()
+        y = comm.Reduce_scatterFused(x, m4t.MPI_SUM, 1, 3, 0.5, acc)
+        self.assertTrue(torch.equal(y, 10.0 + 0.5 * P * (P + 1) / 2 * ones(2, 3)))
+        (y * (comm.rank + 1)).sum().backward()
+        # adjoint: Allgather(scale * grad): column block r carries rank r's weight
+        want = torch.cat([0.5 * (r + 1) * ones(2, 3) for r in range(P)], dim=1)
+        self.assertTrue(torch.equal(x.grad, want))
+        self.assertTrue(torch.equal(acc.grad, (comm.rank + 1) * ones(2, 3)))
+        # bf16 in, bf16 out, fp32 accumulation inside
+        xb = torch.full((4, 2 * P), 0.25, dtype=torch.bfloat16, device=DEVICE)
+        yb = comm.Reduce_scatterFused(xb, m4t.MPI_SUM, 1, 2, 1.0 / P, None)
+        self.assertEqual(yb.dtype, torch.bfloat16)
+        self.assertTrue(torch.equal(yb.float(), torch.full((4, 2), 0.25, device=DEVICE)))
+
+    def test_uniform_size_hint_skips_the_metadata_round(self):
+        comm.assume_uniform_sizes(True)
+        try:
+            x = ones(2, 3) * comm.rank
+            g = comm.Allgather(x, 0)
+            self.assertEqual(tuple(g.shape), (2 * P, 3))
+            self.assertTrue(torch.equal(g[2 * (P - 1):], (P - 1) * ones(2, 3)))
+            a = comm.Alltoall(ones(P, 4) * comm.rank, 1, 0, 1)
+            self.assertEqual(tuple(a.shape), (1, 4 * P))
+            rs = comm.Reduce_scatter(ones(P, 2), m4t.MPI_SUM, 0, 1)
+            self.assertTrue(torch.equal(rs, P * ones(1, 2)))
+            s = comm.Scatter(torch.arange(2.0 * P, dtype=torch.double, device=DEVICE), 0, 2, 0)
+            self.assertEqual(s.cpu().tolist(), [2.0 * comm.rank, 2.0 * comm.rank + 1])
+        finally:
+            comm.assume_uniform_sizes(False)
 
     def test_mean_of_parameters_is_identical_everywhere(self):
         w = rand(1000)
