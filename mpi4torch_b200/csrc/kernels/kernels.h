@@ -144,12 +144,14 @@ void launch_wgrad_bf16(const void* dy, const void* x, void* g, int64_t Mb, int64
 // must be replicated (identical on all ranks), as it is under data-parallel SGD.
 void set_wgrad_debug(int mask);  // timing experiments (see WgradComm::debug)
 int64_t fused_wgrad_tiles(int64_t N, int64_t K);
-int fused_wgrad_signals_per_tile(int ksplit);
+int fused_wgrad_signals_per_unit();   // signals on a tile counter per work unit and rank
+int fused_wgrad_max_unicast_ranks();  // largest world the peer-load (no multicast) mode supports
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
                                uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
-                               int64_t epoch_off = -1, const float* gscale = nullptr);
+                               int64_t epoch_off = -1, const float* gscale = nullptr, bool use_multicast = true);
+// tile_target = signals per WORK UNIT summed over ranks (the kernel multiplies by the tile's number of units).
 // epoch_off >= 0: tile_target / done_target are PER-CALL increments and the call index lives in the local
 // device word at that heap offset (advanced by the kernel): no host-side step state, graph-capturable.
 // wavg_off >= 0: additionally leaves (1/P) * sum_ranks W_new in the bf16 [N,K] buffer at that heap

@@ -1,6 +1,5 @@
 // Weight-gradient GEMM on CTA pairs, optionally fused with the gradient
-// all-reduce and the SGD update (EXPERIMENTAL: compiled and SASS-checked, not
-// yet run on hardware - enabled only by M4T_FUSED_WGRAD=1 / the explicit ops).
+// all-reduce and the SGD update.
 //
 //   G[N,K] = dY[Mb,N]^T * X[Mb,K]          (bf16 in, fp32 accumulate in TMEM)
 //
@@ -15,9 +14,10 @@
 // Fused mode (the backward of the data-parallel linear layer, where the
 // reference does wgrad GEMM -> MPI_Allreduce -> optimizer step as three passes
 // over the gradient, csrc/extension.cpp:197-260 + the example's SGD loop):
-//   * the batch contraction is split in `ksplit` halves so that 2*tiles work
-//     units fill the 74 CTA pairs evenly (256 tiles alone would leave the last
-//     wave 46 % empty);
+//   * tiles that fill whole waves of the 74 CTA pairs run over the full batch; only the
+//     tiles of the last, partial wave are split in `ksplit` batch halves (256 tiles =
+//     3 waves of 74 + 34 tiles -> 68 half units: 3.5 tile times instead of 4), so
+//     only those tiles produce two partial buffers;
 //   * the epilogue writes each partial tile as bf16 into this rank's symmetric
 //     staging buffer and bumps the tile's counter ON THE OWNER rank (tile t is
 //     owned by rank t % P) with a release-scoped remote red;
@@ -61,6 +61,7 @@ constexpr int kWarps = 6;
 constexpr int kCommWarps = 4;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 constexpr int kSignalsPerUnit = 8;  // 4 epilogue warps x 2 CTAs arrive on the tile counter
+constexpr int kMaxUnicastRanks = 3;  // peer-load mode keeps ranks x rows x partial buffers requests in registers
 
 struct WgradArgs {
   void* out;            // plain: G [N, K]; fused: this rank's staging buffer(s)
@@ -91,8 +92,10 @@ struct WgradComm {
   int prefetch;          // 1: W_avg[tile] = avg_scale * sum_ranks W[tile] after the update of the tile
   int64_t wavg_off;      // bf16 [N, K] buffer receiving the averaged weights on every rank
   float avg_scale;       // 1 / P
+  int unicast;           // 1: peer loads / peer stores instead of multimem (no NVLS, or too few ranks for it to pay)
   int debug;             // timing experiments (M4T_WGRAD_DEBUG): 1 no comm data movement, 2 no GEMM,
-                         // 4 local loads instead of multimem.ld_reduce, 8 local stores instead of multimem.st
+                         // 4 local loads instead of multimem.ld_reduce, 8 local stores instead of multimem.st,
+                         // 16 no tile signals and no owner work, 32 no completion barrier
 };
 
 struct __align__(8) Bars {
@@ -122,6 +125,32 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32_mn(uint32_t umma_m, u
   return tc::make_idesc_bf16_f32(umma_m, umma_n) | (1u << 15) | (1u << 16);  // A and B MN-major
 }
 
+// Work-unit schedule shared by every role (and by the host for the counter targets): tiles
+// [0, whole) run over the full batch, tiles [whole, num_tiles) are split in `split` batch slices.
+struct UnitSched {
+  int whole, split, num_units;
+};
+__host__ __device__ inline UnitSched make_sched(int num_tiles, int num_clusters, int ksplit) {
+  UnitSched s;
+  s.split = ksplit;
+  s.whole = ksplit > 1 ? (num_tiles / num_clusters) * num_clusters : num_tiles;
+  s.num_units = s.whole + (num_tiles - s.whole) * ksplit;
+  return s;
+}
+// unit u -> tile t, slice h of `parts` slices
+__host__ __device__ inline void unit_to_tile(const UnitSched& s, int u, int& t, int& h, int& parts) {
+  if (u < s.whole) {
+    t = u;
+    h = 0;
+    parts = 1;
+  } else {
+    const int j = u - s.whole;
+    t = s.whole + j / s.split;
+    h = j - (j / s.split) * s.split;
+    parts = s.split;
+  }
+}
+
 __device__ __forceinline__ void bounded_wait_ge(const uint32_t* flag, uint32_t target, const SyncCtx& c) {
   if (static_cast<int32_t>(ld_acquire_sys_u32(flag) - target) >= 0) return;
   const unsigned long long t0 = globaltimer_ns();
@@ -136,17 +165,20 @@ __device__ __forceinline__ void bounded_wait_ge(const uint32_t* flag, uint32_t t
 }
 
 // Owner side of the fused mode; runs on kCommWarps warps of every CTA.
+// MC: reduce through the NVSwitch (multimem.ld_reduce / multimem.st); otherwise peer loads in rank
+// order and one store per peer (2-3 ranks, or no multicast mapping).
+template <bool MC>
 __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int first_thread, int cluster_id,
                                                    int num_clusters, uint32_t cta, int num_tiles, int k_tiles, int K,
-                                                   int ksplit) {
+                                                   const UnitSched sched) {
   const SyncCtx& c = wc.sync;
   const int P = c.size, r = c.rank;
   const int ct = threadIdx.x - first_thread;
   const int lane = ct & 31;
   const int cw = ct >> 5;
   constexpr int kCommThreads = kCommWarps * 32;
-  constexpr int kU = 8;         // rows in flight per warp (independent switch round trips)
-  constexpr int kRowSplit = 2;  // CTA pairs sharing one owned tile: shortens the tail after the last GEMM wave
+  constexpr int kU = MC ? 8 : 2;  // rows in flight per warp (x partial buffers x peers independent round trips)
+  constexpr int kRowSplit = 2;    // CTA pairs sharing one owned tile: shortens the tail after the last GEMM wave
   constexpr int kRows = BMC / kRowSplit;  // rows of this CTA's half handled per work item
   const uint32_t* my_cnt = reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.cnt_off);
   const int64_t row_bytes = static_cast<int64_t>(K) * 2;
@@ -154,17 +186,20 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   // completion barrier below, and only CTA 0 advances it after that barrier
   uint32_t* epoch_ptr = wc.epoch_off >= 0 ? reinterpret_cast<uint32_t*>(wc.heap[r] + wc.epoch_off) : nullptr;
   const uint32_t epoch = epoch_ptr ? *reinterpret_cast<volatile uint32_t*>(epoch_ptr) : 0u;
-  const uint32_t tile_target = epoch_ptr ? (epoch + 1u) * wc.tile_target : wc.tile_target;
-  const uint32_t done_target = epoch_ptr ? (epoch + 1u) * wc.done_target : wc.done_target;
+  const uint32_t calls = epoch_ptr ? epoch + 1u : 1u;
+  const uint32_t done_target = epoch_ptr ? calls * wc.done_target : wc.done_target;
+  const bool skip = (wc.debug & 1) != 0;
   // Work item w = (j-th owned tile, row slice s); item w is served by cluster w % num_clusters.
   // Owned tiles (t = r + j*P) finish in GEMM order, so consecutive items land on different CTA
-  // pairs and their switch round trips overlap; with 256 tiles / 8 ranks x 2 slices = 64 items
-  // almost every pair of the 74 has at most one.
+  // pairs and their round trips overlap.
   const int owned = r < num_tiles ? (num_tiles - r + P - 1) / P : 0;
-  for (int w_item = cluster_id; w_item < owned * kRowSplit; w_item += num_clusters) {
+  for (int w_item = cluster_id; w_item < owned * kRowSplit && !(wc.debug & 16); w_item += num_clusters) {
     const int j = w_item / kRowSplit;
     const int slice = w_item - j * kRowSplit;
     const int t = r + j * P;
+    const int parts = t < sched.whole ? 1 : sched.split;
+    // every rank's `parts` partial tiles are complete: kSignalsPerUnit signals per unit and rank, per call
+    const uint32_t tile_target = (epoch_ptr ? calls : 1u) * wc.tile_target * static_cast<uint32_t>(parts);
     if (lane == 0) bounded_wait_ge(my_cnt + t, tile_target, c);
     __syncwarp();
     const int n_blk = t / k_tiles;
@@ -172,19 +207,31 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
     // this CTA's rows of the item: kRows rows x 512 bytes, one row per warp pass
     const int64_t tile_off = (static_cast<int64_t>(n_blk) * BM2 + static_cast<int64_t>(cta) * BMC + slice * kRows) * row_bytes +
                              static_cast<int64_t>(k_blk) * BN * 2 + lane * 16;
-    for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
-      Vec16 s0[kU], s1[kU], w[kU];
+    for (int row0 = cw; row0 < kRows && !skip; row0 += kCommWarps * kU) {
+      // all loads of the kU rows (x partial buffers x peers) are issued before the first one is consumed
+      constexpr int kSrc = MC ? 1 : kMaxUnicastRanks;
+      Vec16 s[kU][kSrc][2], w[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int row = row0 + u * kCommWarps;
-        if (row < kRows && !(wc.debug & 1)) {
+        if (row < kRows) {
           const int64_t off = tile_off + row * row_bytes;
-          if (wc.debug & 4) {
-            s0[u] = ld_vec(wc.heap[r] + wc.stage_off + off);
-            if (ksplit > 1) s1[u] = ld_vec(wc.heap[r] + wc.stage_off + wc.stage_stride + off);
+          if (MC) {
+            if (wc.debug & 4) {
+              s[u][0][0] = ld_vec(wc.heap[r] + wc.stage_off + off);
+              if (parts > 1) s[u][0][1] = ld_vec(wc.heap[r] + wc.stage_off + wc.stage_stride + off);
+            } else {
+              s[u][0][0] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
+              if (parts > 1) s[u][0][1] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
+            }
           } else {
-            s0[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
-            if (ksplit > 1) s1[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
+#pragma unroll
+            for (int p = 0; p < kSrc; ++p) {
+              if (p < P) {
+                s[u][p][0] = ld_vec(wc.heap[p] + wc.stage_off + off);
+                if (parts > 1) s[u][p][1] = ld_vec(wc.heap[p] + wc.stage_off + wc.stage_stride + off);
+              }
+            }
           }
           w[u] = ld_vec(wc.heap[r] + wc.w_off + off);
         }
@@ -192,45 +239,89 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int row = row0 + u * kCommWarps;
-        if (row < kRows && !(wc.debug & 1)) {
+        if (row < kRows) {
           const int64_t off = tile_off + row * row_bytes;
           float a[8], b[8], wv[8];
-          VecOf<DType::BF16>::unpack(s0[u], a);
-          VecOf<DType::BF16>::unpack(w[u], wv);
-          if (ksplit > 1) {
-            VecOf<DType::BF16>::unpack(s1[u], b);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] += b[e];
+          for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+          for (int p = 0; p < kSrc; ++p) {  // fixed rank order: every run adds in the same order
+            if (MC || p < P) {
+              VecOf<DType::BF16>::unpack(s[u][p][0], b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] += b[e];
+              if (parts > 1) {
+                VecOf<DType::BF16>::unpack(s[u][p][1], b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += b[e];
+              }
+            }
           }
+          VecOf<DType::BF16>::unpack(w[u], wv);
 #pragma unroll
           for (int e = 0; e < 8; ++e) wv[e] = fmaf(wc.scale, a[e], wv[e]);
-          if (wc.debug & 8) st_vec(wc.heap[r] + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
-          else multimem_st_vec(wc.mc_heap + wc.w_off + off, VecOf<DType::BF16>::pack(wv));
+          const Vec16 o = VecOf<DType::BF16>::pack(wv);
+          if (MC && !(wc.debug & 8)) {
+            multimem_st_vec(wc.mc_heap + wc.w_off + off, o);
+          } else if (MC) {
+            st_vec(wc.heap[r] + wc.w_off + off, o);
+          } else {
+#pragma unroll
+            for (int p = 0; p < kSrc; ++p)
+              if (p < P) st_vec(wc.heap[p] + wc.w_off + off, o);
+          }
         }
       }
     }
-    if (wc.prefetch && !(wc.debug & 1)) {
-      // Next step's forward needs Allreduce(W) / P.  The rows this lane just multicast are final on
-      // every rank once its stores are performed system-wide, so the parameter all-reduce of the
+    if (wc.prefetch && !skip) {
+      // Next step's forward needs Allreduce(W) / P.  The rows this lane just wrote into every rank's
+      // copy are final once its stores are performed system-wide, so the parameter all-reduce of the
       // NEXT step can run here, under the GEMM of later tiles: same rows, same lane -> a per-thread
-      // fence orders the multimem.st above before the multimem.ld_reduce below.
+      // fence orders the stores above before the loads below.
       __threadfence_system();
       for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
-        Vec16 x[kU];
+        constexpr int kSrc = MC ? 1 : kMaxUnicastRanks;
+        Vec16 x[kU][kSrc];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int row = row0 + u * kCommWarps;
-          if (row < kRows) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + tile_off + row * row_bytes);
+          if (row < kRows) {
+            const int64_t off = tile_off + row * row_bytes;
+            if (MC) {
+              x[u][0] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + off);
+            } else {
+#pragma unroll
+              for (int p = 0; p < kSrc; ++p)
+                if (p < P) x[u][p] = ld_vec(wc.heap[p] + wc.w_off + off);
+            }
+          }
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int row = row0 + u * kCommWarps;
           if (row < kRows) {
-            float a[8];
-            VecOf<DType::BF16>::unpack(x[u], a);
+            const int64_t off = tile_off + row * row_bytes;
+            float a[8], b[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+            for (int p = 0; p < kSrc; ++p) {
+              if (MC || p < P) {
+                VecOf<DType::BF16>::unpack(x[u][p], b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += b[e];
+              }
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) a[e] *= wc.avg_scale;
-            multimem_st_vec(wc.mc_heap + wc.wavg_off + tile_off + row * row_bytes, VecOf<DType::BF16>::pack(a));
+            const Vec16 o = VecOf<DType::BF16>::pack(a);
+            if (MC) {
+              multimem_st_vec(wc.mc_heap + wc.wavg_off + off, o);
+            } else {
+#pragma unroll
+              for (int p = 0; p < kSrc; ++p)
+                if (p < P) st_vec(wc.heap[p] + wc.wavg_off + off, o);
+            }
           }
         }
       }
@@ -238,9 +329,14 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   }
   // completion: every CTA of every rank reports once; leaving the kernel means all weights are final
   asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
-  if (ct == 0) {
-    __threadfence_system();
-    asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(wc.mc_heap + wc.done_off), "r"(1u) : "memory");
+  if (ct == 0 && !(wc.debug & 32)) {
+    if (MC) {
+      asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(wc.mc_heap + wc.done_off), "r"(1u) : "memory");
+    } else {
+      __threadfence_system();
+      for (int p = 0; p < P; ++p)
+        asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(wc.heap[p] + wc.done_off), "r"(1u) : "memory");
+    }
     bounded_wait_ge(reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.done_off), done_target, c);
     if (epoch_ptr && blockIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(epoch_ptr) = epoch + 1u;
   }
@@ -264,8 +360,9 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   const int n_tiles = g.N / BM2;  // tiles along the rows of G
   const int k_tiles = g.K / BN;   // tiles along the columns of G
   const int num_tiles = n_tiles * k_tiles;
-  const int num_units = num_tiles * g.ksplit;
-  const int kb_per_unit = g.Mb / BK / g.ksplit;
+  const UnitSched sched = make_sched(num_tiles, num_clusters, g.ksplit);
+  const int num_units = sched.num_units;
+  const int kb_total = g.Mb / BK;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -292,8 +389,9 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       int stage = 0;
       uint32_t phase = 0;
       for (int u = cluster_id; u < num_units; u += num_clusters) {
-        const int t = u / g.ksplit;
-        const int h = u - t * g.ksplit;
+        int t, h, parts;
+        unit_to_tile(sched, u, t, h, parts);
+        const int kb_per_unit = kb_total / parts;
         const int n_blk = t / k_tiles;
         const int k_blk = t - n_blk * k_tiles;
         const int n0 = n_blk * BM2 + static_cast<int>(cta) * BMC;  // column of dY
@@ -330,6 +428,7 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         tc::mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        const int kb_per_unit = u < sched.whole ? kb_total : kb_total / sched.split;
         for (int kb = 0; kb < kb_per_unit; ++kb) {
           tc::mbar_wait(&bars->full[stage], phase);
           tc::tcgen05_fence_after();
@@ -357,8 +456,8 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     const int q = warp & 3;
     int it = 0;
     for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
-      const int t = u / g.ksplit;
-      const int h = u - t * g.ksplit;
+      int t, h, parts;
+      unit_to_tile(sched, u, t, h, parts);
       const int n_blk = t / k_tiles;
       const int k_blk = t - n_blk * k_tiles;
       const int acc = it & 1;
@@ -411,9 +510,9 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       if (lane == 0) {
         if (leader) tc::mbar_arrive(&bars->tmem_empty[acc]);
         else tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bars->tmem_empty[acc]), 0));
-        if (FUSED) {
-          // this warp's 32 rows of the partial tile are in local HBM: tell the owner
-          __threadfence_system();
+        if (FUSED && !(wc.debug & 16)) {
+          // this warp's 32 rows of the partial tile are in local HBM: tell the owner.  The release
+          // (a system-scope fence + the add) is cumulative over the warp's stores through __syncwarp.
           uint32_t* cnt = reinterpret_cast<uint32_t*>(wc.heap[t % wc.sync.size] + wc.cnt_off) + t;
           asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
         }
@@ -421,7 +520,8 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     }
   } else if (FUSED) {
     // ===================== reduce + update (both CTAs) ==================
-    comm_reduce_update(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, g.ksplit);
+    if (wc.unicast) comm_reduce_update<false>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    else comm_reduce_update<true>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
   }
 
   tc::tcgen05_fence_before();
@@ -483,14 +583,16 @@ void launch_wgrad_bf16(const void* dy, const void* x, void* gout, int64_t Mb, in
 }
 
 int64_t fused_wgrad_tiles(int64_t N, int64_t K) { return (N / BM2) * (K / BN); }
-int fused_wgrad_signals_per_tile(int ksplit) { return kSignalsPerUnit * ksplit; }
+int fused_wgrad_signals_per_unit() { return kSignalsPerUnit; }
+int fused_wgrad_max_unicast_ranks() { return kMaxUnicastRanks; }
 
 void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K,
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
                                uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
-                               int64_t epoch_off, const float* gscale) {
-  M4T_CHECK(dc.mc_heap != nullptr, "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping");
+                               int64_t epoch_off, const float* gscale, bool use_multicast) {
+  M4T_CHECK(use_multicast ? dc.mc_heap != nullptr : dc.sync.size <= kMaxUnicastRanks,
+            "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping beyond " << kMaxUnicastRanks << " ranks");
   M4T_CHECK(ksplit == 1 || ksplit == 2, "ksplit must be 1 or 2");
   M4T_CHECK((Mb / BK) % ksplit == 0, "batch / 64 must be divisible by ksplit");
   char* stage = dc.heap[dc.sync.rank] + stage_off;
@@ -523,6 +625,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.prefetch = wavg_off >= 0 ? 1 : 0;
   wc.wavg_off = wavg_off >= 0 ? wavg_off : 0;
   wc.avg_scale = 1.0f / static_cast<float>(dc.sync.size);
+  wc.unicast = use_multicast ? 0 : 1;
   wc.debug = g_wgrad_debug.load(std::memory_order_relaxed);
   const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
   configure_w<true>();

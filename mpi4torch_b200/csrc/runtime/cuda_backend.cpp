@@ -391,8 +391,12 @@ const void* CudaBackend::fused_allreduce_linear(const void* x, const void* w, vo
   return symm_ptr(st.wavg_off[par]);
 }
 
+bool CudaBackend::fused_wgrad_multicast() const { return has_nvls() && size() >= tune_.nvls_min_ranks; }
+
 bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, int64_t K) const {
-  if (size() <= 1 || !has_nvls()) return false;
+  if (size() <= 1) return false;
+  // in-switch reduction from nvls_min_ranks ranks up, peer loads / peer stores below that
+  if (!fused_wgrad_multicast() && size() > fused_wgrad_max_unicast_ranks()) return false;
   static const int64_t mode = env_i64("M4T_FUSED_WGRAD", 1);  // read once; 0 disables the fused backward
   if (mode == 0) return false;
   if (N % 256 != 0 || K % 256 != 0 || Mb % 128 != 0) return false;
@@ -430,11 +434,11 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
   const int64_t w_off = static_cast<const char*>(w) - dc_.heap[dc_.sync.rank];
   st.calls += 1;
   // per-call increments of the monotonic counters; the kernel multiplies by (device call index + 1)
-  const uint32_t tile_target = static_cast<uint32_t>(fused_wgrad_signals_per_tile(st.ksplit) * size());
+  const uint32_t tile_target = static_cast<uint32_t>(fused_wgrad_signals_per_unit() * size());
   const uint32_t done_target = static_cast<uint32_t>(size() * fused_gemm_grid(dc_));
   launch_fused_wgrad_update(dc_, dy, x, Mb, N, K, ldy, ldx, w_off, st.stage_off, st.stage_stride, st.cnt_off,
                             st.done_off, st.ksplit, tile_target, done_target, scale, prefetch_avg ? st.wavg_off : -1,
-                            stream, st.epoch_off, gscale);
+                            stream, st.epoch_off, gscale, fused_wgrad_multicast());
   return prefetch_avg ? symm_ptr(st.wavg_off) : nullptr;
 }
 

@@ -78,6 +78,7 @@ class CudaBackend final : public Backend {
   // in-switch reduce-scatter + SGD update + multicast of the new weights).  `w` must come from
   // symmetric_alloc() and be replicated across ranks.
   bool fused_wgrad_available(const void* w, int64_t Mb, int64_t N, int64_t K) const;
+  bool fused_wgrad_multicast() const;  // in-switch reduction (true) or peer loads/stores (false)
   // prefetch_avg: also all-reduce the updated weights (x 1/size) into a symmetric buffer whose
   // address is returned - the next forward can then run as a plain local GEMM.
   const void* fused_wgrad_update(void* w, const void* dy, const void* x, int64_t Mb, int64_t N, int64_t K, int64_t ldy,

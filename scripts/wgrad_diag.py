@@ -46,8 +46,8 @@ one = torch.ones(1, device=dev)
 res["allreduce_scalar_ms"] = timeit(lambda: comm.Allreduce(one, m4t.MPI_SUM), n=50)
 emit(res)
 if comm.size > 1 and ops.wgrad_allreduce_sgd_supported(w, dy, x):
-    for name, mask in (("full", 0), ("nocomm", 1), ("nogemm", 2), ("local_ld", 4), ("local_st", 8), ("local_ldst", 12),
-                       ("nogemm_local", 14)):
+    for name, mask in (("full", 0), ("nocomm", 1), ("nogemm", 2), ("gemm_only_done_barrier", 16), ("gemm_only", 48),
+                       ("local_ldst", 12), ("nogemm_local", 14)):
         m4t._C.set_tuning("wgrad_debug", mask)
         r = {"world": comm.size, "variant": name, "mask": mask}
         r["fused_ms"] = timeit(lambda: ops.wgrad_allreduce_sgd_(w, dy, x, -1e-6))

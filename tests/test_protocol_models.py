@@ -18,31 +18,56 @@ def units_of_cluster(cluster_id, num_clusters, num_units):
     return range(cluster_id, num_units, num_clusters)
 
 
+def make_sched(num_tiles, num_clusters, ksplit):
+    """make_sched / unit_to_tile of the kernel: whole waves of tiles run over the full batch, only the tiles
+    of the last partial wave are split in `ksplit` batch slices."""
+    whole = (num_tiles // num_clusters) * num_clusters if ksplit > 1 else num_tiles
+    return whole, ksplit, whole + (num_tiles - whole) * ksplit
+
+
+def unit_to_tile(sched, u):
+    whole, split, _ = sched
+    if u < whole:
+        return u, 0, 1
+    j = u - whole
+    return whole + j // split, j % split, split
+
+
 @pytest.mark.parametrize("N,K,P,num_clusters,ksplit", [(1024, 512, 4, 3, 2), (512, 256, 8, 5, 2), (768, 768, 2, 7, 1),
                                                       (4096, 4096, 8, 74, 2)])
 def test_fused_wgrad_work_distribution(N, K, P, num_clusters, ksplit):
     n_tiles, k_tiles = N // BM2, K // BN
     num_tiles = n_tiles * k_tiles
-    num_units = num_tiles * ksplit
+    sched = make_sched(num_tiles, num_clusters, ksplit)
+    num_units = sched[2]
     small = N * K <= 1 << 20
 
     # --- GEMM epilogue: every (split, row, col) of the staging buffers written once; tile counters ---
     staged = np.zeros((ksplit, N, K), dtype=np.int8) if small else None
     signals = np.zeros(num_tiles, dtype=np.int64)  # per rank; the owner sums over P ranks
+    parts_of = np.zeros(num_tiles, dtype=np.int64)
+    kb_covered = np.zeros(num_tiles, dtype=np.int64)  # batch blocks contracted per tile (in units of 1/ksplit)
     for cluster in range(num_clusters):
         for u in units_of_cluster(cluster, num_clusters, num_units):
-            t, h = divmod(u, ksplit)
+            t, h, parts = unit_to_tile(sched, u)
+            assert 0 <= t < num_tiles and 0 <= h < parts
+            parts_of[t] = parts
+            kb_covered[t] += ksplit // parts
             n_blk, k_blk = divmod(t, k_tiles)
             for cta, q in itertools.product(range(2), range(4)):
                 if small:
                     r0 = n_blk * BM2 + cta * BMC + q * 32
                     staged[h, r0:r0 + 32, k_blk * BN:(k_blk + 1) * BN] += 1
                 signals[t] += 1
+    assert (kb_covered == ksplit).all()  # every tile contracts the whole batch exactly once
     if small:
-        assert (staged == 1).all()
-    assert (signals == SIGNALS_PER_UNIT * ksplit).all()
-    tile_target_per_epoch = SIGNALS_PER_UNIT * ksplit * P  # host: calls * signals_per_tile(ksplit) * size
-    assert (signals * P == tile_target_per_epoch).all()
+        for t in range(num_tiles):  # buffer h of tile t is written once iff the tile has a slice h
+            n_blk, k_blk = divmod(t, k_tiles)
+            blk = staged[:, n_blk * BM2:(n_blk + 1) * BM2, k_blk * BN:(k_blk + 1) * BN]
+            for h in range(ksplit):
+                assert (blk[h] == (1 if h < parts_of[t] else 0)).all()
+    # host: tile_target = signals_per_unit * size per call; the kernel multiplies by the tile's number of units
+    assert (signals * P == SIGNALS_PER_UNIT * P * parts_of).all()
 
     # --- owner side: every element of W updated by exactly one (rank, cluster, cta, warp, lane, trip) ---
     updated = np.zeros((N, K), dtype=np.int8) if small else None
@@ -74,16 +99,21 @@ def test_fused_wgrad_work_distribution(N, K, P, num_clusters, ksplit):
     assert P * grid == P * 2 * num_clusters  # host: done_target = calls * size * fused_gemm_grid
 
 
-def test_unit_schedule_keeps_both_halves_of_a_tile_adjacent():
-    # two work units of one tile run on neighbouring CTA pairs in the same wave, so the owner can
-    # start reducing a tile as soon as that wave finishes
+def test_unit_schedule_fills_the_last_wave():
+    # flagship shape: 256 tiles on 74 CTA pairs = 3 whole waves + 34 tiles; those are split in two batch halves
+    # (68 units <= 74 pairs), so the kernel takes 3.5 tile times instead of 4 and only 34 tiles have two partials
     num_clusters, ksplit, num_tiles = 74, 2, 256
-    wave_of = {}
+    sched = make_sched(num_tiles, num_clusters, ksplit)
+    assert sched == (222, 2, 290)
+    cost = [0.0] * num_clusters
     for cluster in range(num_clusters):
-        for it, u in enumerate(units_of_cluster(cluster, num_clusters, num_tiles * ksplit)):
-            wave_of[u] = it
-    late = [t for t in range(num_tiles) if wave_of[2 * t] != wave_of[2 * t + 1]]
-    assert len(late) == 0, late[:5]
+        for u in units_of_cluster(cluster, num_clusters, sched[2]):
+            cost[cluster] += 1.0 / unit_to_tile(sched, u)[2]
+    assert max(cost) == 3.5
+    # both halves of a split tile run in the same (last) wave on neighbouring pairs
+    for t in range(sched[0], num_tiles):
+        u0 = sched[0] + 2 * (t - sched[0])
+        assert u0 // num_clusters == (u0 + 1) // num_clusters == 3
 
 
 def _swizzle128(byte_off: int) -> int:
