@@ -218,7 +218,7 @@ def run(args) -> int:
     if not args.no_extras and rank == 0:
         try:
             res = subprocess.run([os.path.join(HERE, "mpi_shim", "bin", "mpirun"), "-np", "2", sys.executable,
-                                  os.path.join(HERE, "ref_linreg.py"), "--steps", "10"],
+                                  os.path.join(HERE, "ref_linreg.py"), "--steps", "30"],
                                  capture_output=True, text=True, timeout=300,
                                  env={k: v for k, v in os.environ.items()
                                       if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MPISHIM_RANK", "MPISHIM_SIZE")})

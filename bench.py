@@ -47,7 +47,7 @@ def linreg_cpu_step_per_s() -> object:
     env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
     try:
         res = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2",
-                              os.path.join(ROOT, "benchmarks", "linreg_steps.py"), "--steps", "10", "--no-gloo"],
+                              os.path.join(ROOT, "benchmarks", "linreg_steps.py"), "--steps", "30", "--no-gloo"],
                              capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
         line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
         return json.loads(line)["ours_step_per_s"]

@@ -70,8 +70,11 @@ def main():
     run(model.loss, init, 3)  # warm-up
     comm.Barrier()
     times, p = run(model.loss, init, args.steps)
-    tmax = float(comm.Allreduce(torch.tensor([sum(times)], dtype=torch.double), m4t.MPI_MAX)[0])
-    res["ours_step_per_s"] = args.steps / tmax
+    # median step time (max over ranks): robust against scheduling noise on a shared host; the mean is kept too
+    med = sorted(times)[len(times) // 2]
+    agg = comm.Allreduce(torch.tensor([med, sum(times)], dtype=torch.double), m4t.MPI_MAX)
+    res["ours_step_per_s"] = 1.0 / float(agg[0])
+    res["ours_step_per_s_mean"] = args.steps / float(agg[1])
     res["ours_params"] = p.tolist()
     if not args.no_gloo and comm.size > 1:
         import torch.distributed as dist
