@@ -58,7 +58,7 @@ constexpr int kABytes = (BMC / kChunk) * kBoxBytes;  // 16 KiB
 constexpr int kBBytes = (BNH / kChunk) * kBoxBytes;  // 16 KiB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kWarps = 6;
-constexpr int kCommWarps = 4;
+constexpr int kCommWarps = 8;   // owner role: in-flight round trips scale with warps x rows (registers hold the data)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 constexpr int kSignalsPerUnit = 8;  // 4 epilogue warps x 2 CTAs arrive on the tile counter
 constexpr int kMaxUnicastRanks = 3;  // peer-load mode keeps ranks x rows x partial buffers requests in registers
@@ -165,9 +165,9 @@ __device__ __forceinline__ void bounded_wait_ge(const uint32_t* flag, uint32_t t
 }
 
 // Owner side of the fused mode; runs on kCommWarps warps of every CTA.
-// MC: reduce through the NVSwitch (multimem.ld_reduce / multimem.st); otherwise peer loads in rank
+// MC: reduce through the NVSwitch (multimem.ld_reduce / multimem.st); otherwise NSRC peer loads in rank
 // order and one store per peer (2-3 ranks, or no multicast mapping).
-template <bool MC>
+template <bool MC, int NSRC>
 __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int first_thread, int cluster_id,
                                                    int num_clusters, uint32_t cta, int num_tiles, int k_tiles, int K,
                                                    const UnitSched sched) {
@@ -177,7 +177,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   const int lane = ct & 31;
   const int cw = ct >> 5;
   constexpr int kCommThreads = kCommWarps * 32;
-  constexpr int kU = MC ? 8 : 2;  // rows in flight per warp (x partial buffers x peers independent round trips)
+  constexpr int kU = NSRC <= 2 ? 4 : 2;  // rows in flight per warp (x partial buffers x peers independent round trips)
   constexpr int kRowSplit = 2;    // CTA pairs sharing one owned tile: shortens the tail after the last GEMM wave
   constexpr int kRows = BMC / kRowSplit;  // rows of this CTA's half handled per work item
   const uint32_t* my_cnt = reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.cnt_off);
@@ -209,7 +209,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
                              static_cast<int64_t>(k_blk) * BN * 2 + lane * 16;
     for (int row0 = cw; row0 < kRows && !skip; row0 += kCommWarps * kU) {
       // all loads of the kU rows (x partial buffers x peers) are issued before the first one is consumed
-      constexpr int kSrc = MC ? 1 : kMaxUnicastRanks;
+      constexpr int kSrc = NSRC;
       Vec16 s[kU][kSrc][2], w[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
@@ -280,7 +280,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
       // fence orders the stores above before the loads below.
       __threadfence_system();
       for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
-        constexpr int kSrc = MC ? 1 : kMaxUnicastRanks;
+        constexpr int kSrc = NSRC;
         Vec16 x[kU][kSrc];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -520,8 +520,9 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     }
   } else if (FUSED) {
     // ===================== reduce + update (both CTAs) ==================
-    if (wc.unicast) comm_reduce_update<false>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
-    else comm_reduce_update<true>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    if (!wc.unicast) comm_reduce_update<true, 1>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    else if (wc.sync.size <= 2) comm_reduce_update<false, 2>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    else comm_reduce_update<false, kMaxUnicastRanks>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
   }
 
   tc::tcgen05_fence_before();
