@@ -97,6 +97,12 @@ void launch_p2p_send(const SyncCtx& sync, const P2pChannel& ch, const void* src,
 // Receiver: pulls chunks out of the sender's ring into `dst`, acknowledging tail flags.
 void launch_p2p_recv(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64_t bytes,
                      unsigned long long first_chunk, int blocks, cudaStream_t stream);
+// Copy-engine variants for large messages: same ring / flags / chunk numbering, payload moved by
+// cudaMemcpyAsync (no SM copies a byte), flags handled by one-warp kernels between the copies.
+void launch_p2p_send_ce(const SyncCtx& sync, const P2pChannel& ch, const void* src, int64_t bytes,
+                        unsigned long long first_chunk, cudaStream_t stream);
+void launch_p2p_recv_ce(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64_t bytes,
+                        unsigned long long first_chunk, cudaStream_t stream);
 
 // ---- tcgen05 GEMM + fused Allreduce->GEMM (gemm_tcgen05.cu) --------------------
 bool gemm_bf16_tn_supported(int64_t M, int64_t N, int64_t K, const void* A, const void* B, const void* C, int64_t lda,

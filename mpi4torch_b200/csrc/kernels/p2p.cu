@@ -12,6 +12,13 @@
 //
 // Flags are per slot and hold (chunk index + 1), monotone per slot, so blocks
 // may own different chunks concurrently (block b takes chunks b, b+G, ...).
+//
+// Large messages take the COPY-ENGINE path instead (launch_p2p_*_ce): the same ring, the same flags and
+// the same chunk numbering, but the payload moves with cudaMemcpyAsync - user buffer -> ring on the
+// sender's DMA engine, ring -> destination over NVLink on the receiver's DMA engine - in groups of up to
+// half a ring, and the flags are waited for / posted by one-warp kernels between the copies.  No SM
+// copies a byte, so a transfer overlaps a GEMM on the compute stream without taking SMs from it (the
+// reference's MPI_Isend/Irecv progress on the host; here the DMA engines do).
 #include <algorithm>
 
 #include "kernels.h"
@@ -95,6 +102,23 @@ __global__ void __launch_bounds__(kThreads) p2p_recv_kernel(const P2pArgs a) {
   }
 }
 
+// One warp; lane i handles slot s0 + i of a group of g <= 32 consecutive slots.
+// wait: flag[s0+i] >= target0 + i (skipped for lanes whose target is <= 0, i.e. first use of the slot)
+__global__ void __launch_bounds__(32) p2p_flag_wait_kernel(const uint32_t* flags, int s0, int g, long long target0,
+                                                            SyncCtx sync) {
+  const int i = threadIdx.x;
+  if (i < g) {
+    const long long tgt = target0 + i;
+    if (tgt > 0) wait_flag_ge(flags + s0 + i, static_cast<uint32_t>(tgt), sync);
+  }
+}
+// post: flag[s0+i] = value0 + i, released at system scope (the DMA copy before this kernel in stream
+// order has completed, so the payload is visible before the flag)
+__global__ void __launch_bounds__(32) p2p_flag_post_kernel(uint32_t* flags, int s0, int g, unsigned long long value0) {
+  const int i = threadIdx.x;
+  if (i < g) st_release_sys_u32(flags + s0 + i, static_cast<uint32_t>(value0 + static_cast<unsigned long long>(i)));
+}
+
 }  // namespace
 
 int64_t p2p_num_chunks(int64_t bytes, int64_t slot_bytes) {
@@ -137,6 +161,10 @@ void preload_p2p_kernels() {
   M4T_CHECK(e == cudaSuccess, "loading p2p_send_kernel failed: " << cudaGetErrorString(e));
   e = cudaFuncGetAttributes(&attr, p2p_recv_kernel);
   M4T_CHECK(e == cudaSuccess, "loading p2p_recv_kernel failed: " << cudaGetErrorString(e));
+  e = cudaFuncGetAttributes(&attr, p2p_flag_wait_kernel);
+  M4T_CHECK(e == cudaSuccess, "loading p2p_flag_wait_kernel failed: " << cudaGetErrorString(e));
+  e = cudaFuncGetAttributes(&attr, p2p_flag_post_kernel);
+  M4T_CHECK(e == cudaSuccess, "loading p2p_flag_post_kernel failed: " << cudaGetErrorString(e));
 }
 
 void launch_p2p_send(const SyncCtx& sync, const P2pChannel& ch, const void* src, int64_t bytes,
@@ -155,6 +183,65 @@ void launch_p2p_recv(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64
   blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(blocks, nchunks)));
   p2p_recv_kernel<<<blocks, kThreads, 0, stream>>>(a);
   check_launch("p2p_recv");
+}
+
+// ---------------------------------------------------------------------------
+// copy-engine path (large messages)
+// ---------------------------------------------------------------------------
+namespace {
+
+// Walks a message in groups of consecutive chunks that neither wrap the ring nor exceed half of it
+// (so the sender can refill one half while the receiver drains the other) nor 32 slots (one lane each).
+template <typename F> void for_each_group(const P2pChannel& ch, int64_t bytes, unsigned long long first_chunk, F&& f) {
+  const int64_t nchunks = p2p_num_chunks(bytes, ch.slot_bytes);
+  const int64_t gmax = std::max<int64_t>(1, std::min<int64_t>(ch.nslots / 2, 32));
+  for (int64_t k0 = 0; k0 < nchunks;) {
+    const unsigned long long cidx0 = first_chunk + static_cast<unsigned long long>(k0);
+    const int s0 = static_cast<int>(cidx0 % static_cast<unsigned long long>(ch.nslots));
+    const int64_t g = std::min<int64_t>(std::min<int64_t>(gmax, nchunks - k0), ch.nslots - s0);
+    const int64_t off = k0 * ch.slot_bytes;
+    const int64_t len = std::max<int64_t>(0, std::min<int64_t>(g * ch.slot_bytes, bytes - off));
+    f(cidx0, s0, static_cast<int>(g), off, len);
+    k0 += g;
+  }
+}
+
+}  // namespace
+
+void launch_p2p_send_ce(const SyncCtx& sync, const P2pChannel& ch, const void* src, int64_t bytes,
+                        unsigned long long first_chunk, cudaStream_t stream) {
+  for_each_group(ch, bytes, first_chunk, [&](unsigned long long cidx0, int s0, int g, int64_t off, int64_t len) {
+    // the slots must have been drained by the receiver: tail >= (chunk - nslots) + 1
+    const long long target0 = static_cast<long long>(cidx0) - ch.nslots + 1;
+    if (target0 + g - 1 > 0) {
+      p2p_flag_wait_kernel<<<1, 32, 0, stream>>>(ch.tail_flags, s0, g, target0, sync);
+      check_launch("p2p_flag_wait");
+    }
+    if (len > 0) {
+      cudaError_t e = cudaMemcpyAsync(ch.slots + static_cast<int64_t>(s0) * ch.slot_bytes, static_cast<const char*>(src) + off,
+                                      static_cast<size_t>(len), cudaMemcpyDeviceToDevice, stream);
+      M4T_CHECK(e == cudaSuccess, "p2p send copy failed: " << cudaGetErrorString(e));
+    }
+    p2p_flag_post_kernel<<<1, 32, 0, stream>>>(ch.head_flags, s0, g, cidx0 + 1ull);
+    check_launch("p2p_flag_post");
+  });
+}
+
+void launch_p2p_recv_ce(const SyncCtx& sync, const P2pChannel& ch, void* dst, int64_t bytes,
+                        unsigned long long first_chunk, cudaStream_t stream) {
+  for_each_group(ch, bytes, first_chunk, [&](unsigned long long cidx0, int s0, int g, int64_t off, int64_t len) {
+    p2p_flag_wait_kernel<<<1, 32, 0, stream>>>(ch.head_flags, s0, g, static_cast<long long>(cidx0) + 1, sync);
+    check_launch("p2p_flag_wait");
+    if (len > 0) {
+      // the ring is the peer's memory (or ours in push mode) seen through the symmetric mapping: the
+      // receiver's DMA engine pulls it over NVLink
+      cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst) + off, ch.slots + static_cast<int64_t>(s0) * ch.slot_bytes,
+                                      static_cast<size_t>(len), cudaMemcpyDeviceToDevice, stream);
+      M4T_CHECK(e == cudaSuccess, "p2p receive copy failed: " << cudaGetErrorString(e));
+    }
+    p2p_flag_post_kernel<<<1, 32, 0, stream>>>(ch.tail_flags, s0, g, cidx0 + 1ull);
+    check_launch("p2p_flag_post");
+  });
 }
 
 }  // namespace m4t

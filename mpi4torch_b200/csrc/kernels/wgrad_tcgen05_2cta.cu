@@ -228,8 +228,8 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 #pragma unroll
             for (int p = 0; p < kSrc; ++p) {
               if (p < P) {
-                s[u][p][0] = ld_vec(wc.heap[p] + wc.stage_off + off);
-                if (parts > 1) s[u][p][1] = ld_vec(wc.heap[p] + wc.stage_off + wc.stage_stride + off);
+                s[u][p][0] = ld_vec_sys(wc.heap[p] + wc.stage_off + off);
+                if (parts > 1) s[u][p][1] = ld_vec_sys(wc.heap[p] + wc.stage_off + wc.stage_stride + off);
               }
             }
           }
@@ -292,7 +292,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
             } else {
 #pragma unroll
               for (int p = 0; p < kSrc; ++p)
-                if (p < P) x[u][p] = ld_vec(wc.heap[p] + wc.w_off + off);
+                if (p < P) x[u][p] = ld_vec_sys(wc.heap[p] + wc.w_off + off);
             }
           }
         }

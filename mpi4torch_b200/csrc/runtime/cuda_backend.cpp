@@ -37,6 +37,9 @@ CudaBackend::CudaBackend(Control& ctl, int device, int64_t stage_mb, int64_t sym
   nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", 16))));
   slot_bytes_ = round_up64(std::max<int64_t>(4096, env_i64("M4T_P2P_SLOT_KB", 1024) * 1024), 128);
   p2p_push_ = env_i64("M4T_P2P_PUSH", 0) != 0;
+  // messages of at least this many bytes move on the copy engines (-1: never); both ends decide from the
+  // message size alone, so they always agree
+  p2p_ce_min_bytes_ = env_i64("M4T_P2P_CE_MIN_KB", 2048) < 0 ? -1 : env_i64("M4T_P2P_CE_MIN_KB", 2048) * 1024;
   p2p_head_off_ = kP2pHeadOff;
   p2p_tail_off_ = kP2pTailOff;
   p2p_off_ = kP2pRingOff;
@@ -497,7 +500,8 @@ int64_t CudaBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag
   free_event(ready);
   const unsigned long long first = send_chunks_[dest];
   M4T_LOG("rank %d isend -> %d tag %ld bytes %ld first_chunk %llu stream %p", rank(), dest, (long)tag, (long)bytes, first, (void*)user);
-  launch_p2p_send(dc_.sync, send_channel(dest), buf, bytes, first, tune_.p2p_blocks, ss);
+  if (p2p_ce_min_bytes_ >= 0 && bytes >= p2p_ce_min_bytes_) launch_p2p_send_ce(dc_.sync, send_channel(dest), buf, bytes, first, ss);
+  else launch_p2p_send(dc_.sync, send_channel(dest), buf, bytes, first, tune_.p2p_blocks, ss);
   send_chunks_[dest] += static_cast<unsigned long long>(p2p_num_chunks(bytes, slot_bytes_));
   Request rq;
   rq.is_recv = false;
@@ -534,7 +538,10 @@ void CudaBackend::launch_recv(const MsgDesc& d, int source, void* dst, cudaEvent
                                                << recv_chunks_[source] << ", message starts at " << first << ")");
   M4T_LOG("rank %d launch_recv <- %d tag %ld bytes %ld first_chunk %llu dst %p ready %p", rank(), source, (long)d.tag,
           (long)d.bytes, first, dst, (void*)ready);
-  launch_p2p_recv(dc_.sync, recv_channel(source), dst, static_cast<int64_t>(d.bytes), first, tune_.p2p_blocks, rs);
+  if (p2p_ce_min_bytes_ >= 0 && static_cast<int64_t>(d.bytes) >= p2p_ce_min_bytes_)
+    launch_p2p_recv_ce(dc_.sync, recv_channel(source), dst, static_cast<int64_t>(d.bytes), first, rs);
+  else
+    launch_p2p_recv(dc_.sync, recv_channel(source), dst, static_cast<int64_t>(d.bytes), first, tune_.p2p_blocks, rs);
   recv_chunks_[source] += static_cast<unsigned long long>(p2p_num_chunks(static_cast<int64_t>(d.bytes), slot_bytes_));
   M4T_CUDA(cudaEventRecord(done, rs));
 }
