@@ -156,7 +156,9 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
                                uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
-                               int64_t epoch_off = -1, const float* gscale = nullptr, bool use_multicast = true);
+                               int64_t epoch_off = -1, const float* gscale = nullptr, bool use_multicast = true,
+                               int64_t src_stride = 0);
+// src_stride (peer-store mode): the staging area holds one copy per SOURCE rank, src_stride bytes apart.
 // tile_target = signals per WORK UNIT summed over ranks (the kernel multiplies by the tile's number of units).
 // epoch_off >= 0: tile_target / done_target are PER-CALL increments and the call index lives in the local
 // device word at that heap offset (advanced by the kernel): no host-side step state, graph-capturable.

@@ -80,6 +80,8 @@ struct WgradComm {
   char* mc_heap;
   int64_t stage_off;     // partial-gradient staging (same offset on every rank)
   int64_t stage_stride;  // bytes between the ksplit partial buffers
+  int64_t src_stride;    // peer-store mode: bytes between the per-source-rank copies of the staging area in the
+                         // OWNER's heap (the epilogue pushes its partial tile there; the owner only reads locally)
   int64_t w_off;         // bf16 weights [N, K] (contiguous) inside every rank's heap
   int64_t cnt_off;       // u32 tile counters [tiles]
   int64_t done_off;      // u32 completion counter
@@ -228,8 +230,10 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 #pragma unroll
             for (int p = 0; p < kSrc; ++p) {
               if (p < P) {
-                s[u][p][0] = ld_vec_sys(wc.heap[p] + wc.stage_off + off);
-                if (parts > 1) s[u][p][1] = ld_vec_sys(wc.heap[p] + wc.stage_off + wc.stage_stride + off);
+                // pushed here by rank p's epilogue: local reads
+                const char* src = wc.heap[r] + wc.stage_off + static_cast<int64_t>(p) * wc.src_stride + off;
+                s[u][p][0] = ld_vec(src);
+                if (parts > 1) s[u][p][1] = ld_vec(src + wc.stage_stride);
               }
             }
           }
@@ -275,10 +279,14 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
     }
     if (wc.prefetch && !skip) {
       // Next step's forward needs Allreduce(W) / P.  The rows this lane just wrote into every rank's
-      // copy are final once its stores are performed system-wide, so the parameter all-reduce of the
-      // NEXT step can run here, under the GEMM of later tiles: same rows, same lane -> a per-thread
-      // fence orders the stores above before the loads below.
-      __threadfence_system();
+      // copy are the final values of this step, so the parameter all-reduce of the NEXT step can run here,
+      // under the GEMM of later tiles.  Every address read below was written above by THIS lane:
+      //  * peer-store mode: plain stores followed by loads of the same addresses - program order to the
+      //    same location from one thread is coherent without a fence (and a MEMBAR.SYS per lane and item,
+      //    waiting for every posted remote write to be acknowledged, was the most expensive instruction of
+      //    this role);
+      //  * multicast mode: the write fans out inside the switch, so the fence stays.
+      if (MC) __threadfence_system();
       for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
         constexpr int kSrc = NSRC;
         Vec16 x[kU][kSrc];
@@ -473,7 +481,13 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       tc::mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc::tcgen05_fence_after();
       const int row = n_blk * BM2 + static_cast<int>(cta) * BMC + q * 32 + lane;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(static_cast<char*>(g.out) + h * g.out_split_stride) +
+      // plain / multicast mode: this rank's own staging buffer.  Peer-store mode: the OWNER's staging area for
+      // this source rank - posted writes over NVLink, spread over the whole GEMM, so the owner never has to
+      // pull (no read round trips on the reduction path).
+      char* obase = static_cast<char*>(g.out);
+      if (FUSED && wc.unicast)
+        obase = wc.heap[t % wc.sync.size] + wc.stage_off + static_cast<int64_t>(wc.sync.rank) * wc.src_stride;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(obase + h * g.out_split_stride) +
                        static_cast<int64_t>(row) * g.ldo + k_blk * BN;
       const float gs = (g.gscale ? __ldg(g.gscale) : 1.0f) * (g.axpy != 0.0f ? g.axpy : 1.0f);
       const bool axpy = !FUSED && g.axpy != 0.0f;
@@ -591,7 +605,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
                                int64_t ldy, int64_t ldx, int64_t w_off, int64_t stage_off, int64_t stage_stride,
                                int64_t cnt_off, int64_t done_off, int ksplit, uint32_t tile_target,
                                uint32_t done_target, float scale, int64_t wavg_off, cudaStream_t stream,
-                               int64_t epoch_off, const float* gscale, bool use_multicast) {
+                               int64_t epoch_off, const float* gscale, bool use_multicast, int64_t src_stride) {
   M4T_CHECK(use_multicast ? dc.mc_heap != nullptr : dc.sync.size <= kMaxUnicastRanks,
             "the fused wgrad->Allreduce->SGD kernel needs the NVLS multicast mapping beyond " << kMaxUnicastRanks << " ranks");
   M4T_CHECK(ksplit == 1 || ksplit == 2, "ksplit must be 1 or 2");
@@ -616,6 +630,7 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.mc_heap = dc.mc_heap;
   wc.stage_off = stage_off;
   wc.stage_stride = stage_stride;
+  wc.src_stride = src_stride;
   wc.w_off = w_off;
   wc.cnt_off = cnt_off;
   wc.done_off = done_off;

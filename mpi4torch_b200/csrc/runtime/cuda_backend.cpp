@@ -406,7 +406,8 @@ bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, in
   const char* wb = static_cast<const char*>(w);
   const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
   if (!(wb >= arena && wb + N * K * 2 <= arena + symm_bytes_)) return false;  // must be switch-visible in place
-  const int64_t need = 3 * N * K * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;  // 2 partial buffers + W_avg prefetch
+  // 2 partial buffers (per source rank in peer-store mode) + W_avg prefetch
+  const int64_t need = (2 * (fused_wgrad_multicast() ? 1 : size()) + 1) * N * K * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;
   return wgrad_.count((N << 32) | K) > 0 || symm_cursor_ + need <= symm_bytes_;
 }
 
@@ -425,7 +426,10 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
     static const int64_t ksplit_env = env_i64("M4T_WGRAD_KSPLIT", 2);  // read once
     st.ksplit = (ksplit_env >= 2 && (Mb / 64) % 2 == 0) ? 2 : 1;
     st.stage_stride = round_up64(N * K * 2, 1024);
-    st.stage_off = symm_alloc(st.stage_stride * st.ksplit);
+    // multicast mode: one staging area per rank (own partials, pulled through the switch by the owners);
+    // peer-store mode: one area per SOURCE rank in every heap (the epilogues push to the owner)
+    st.src_stride = st.stage_stride * st.ksplit;
+    st.stage_off = symm_alloc(st.src_stride * (fused_wgrad_multicast() ? 1 : size()));
     st.cnt_off = symm_alloc(fused_wgrad_tiles(N, K) * 4);
     st.done_off = symm_alloc(16);
     st.epoch_off = symm_alloc(16);  // call index, kept on the device (graph-capturable launches)
@@ -441,7 +445,7 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
   const uint32_t done_target = static_cast<uint32_t>(size() * fused_gemm_grid(dc_));
   launch_fused_wgrad_update(dc_, dy, x, Mb, N, K, ldy, ldx, w_off, st.stage_off, st.stage_stride, st.cnt_off,
                             st.done_off, st.ksplit, tile_target, done_target, scale, prefetch_avg ? st.wavg_off : -1,
-                            stream, st.epoch_off, gscale, fused_wgrad_multicast());
+                            stream, st.epoch_off, gscale, fused_wgrad_multicast(), st.src_stride);
   return prefetch_avg ? symm_ptr(st.wavg_off) : nullptr;
 }
 

@@ -153,7 +153,7 @@ class CudaBackend final : public Backend {
   };
   std::unordered_map<int64_t, FusedLinearState> fused_;  // key = N << 32 | K
   struct FusedWgradState {
-    int64_t stage_off = 0, stage_stride = 0, cnt_off = 0, done_off = 0, wavg_off = -1, epoch_off = -1;
+    int64_t stage_off = 0, stage_stride = 0, src_stride = 0, cnt_off = 0, done_off = 0, wavg_off = -1, epoch_off = -1;
     int ksplit = 1;
     uint64_t calls = 0;
   };

@@ -351,6 +351,19 @@ class TestFusedTrainingStep(unittest.TestCase):
         torch.cuda.synchronize()
         expect = comm.AllreduceFused(w.detach().clone(), m4t.MPI_SUM, 1.0 / P, None)
         self.assertLess((w_avg.float() - expect.float()).abs().max().item(), 1e-2)
+        if P & (P - 1) == 0:
+            # replicated weights and a power-of-two world: the average of identical copies is exact, so a
+            # stale read-back (the update not yet visible when the average was taken) cannot hide
+            self.assertTrue(torch.equal(w_avg, w.detach()))
+        # a second, large step: the prefetched average must follow the NEW weights
+        w_before = w.detach().clone()
+        w_avg2 = torch.ops.mpi4torch_b200.wgrad_allreduce_sgd_prefetch_(w, dy, x, -1.0 / P)
+        torch.cuda.synchronize()
+        self.assertGreater((w.float() - w_before.float()).abs().max().item(), 1.0)
+        if P & (P - 1) == 0:
+            self.assertTrue(torch.equal(w_avg2, w.detach()))
+        else:
+            self.assertLess((w_avg2.float() - w.float()).abs().max().item(), 2e-2 * w.float().abs().max().item())
         t = torch.randn(Mb, N, generator=gr).to(torch.bfloat16).to(DEVICE)
         dy2, loss2 = torch.ops.mpi4torch_b200.linear_mse_forward_local(x, w_avg, t, 1.0, 1.0)
         ref = (x.float() @ w_avg.float().t() - t.float())
