@@ -60,6 +60,12 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kWarps = 6;
 constexpr int kCommWarps = 8;   // owner role: in-flight round trips scale with warps x rows (registers hold the data)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+// peer-store mode: every epilogue warp stages {32 rows x 64 columns} bf16 boxes (4 KiB, 128-byte swizzled rows)
+// in shared memory, double buffered, and hands them to the TMA store engine
+constexpr int kEpiBoxBytes = 32 * 128;
+constexpr int kEpiSmemBytes = 4 * 2 * kEpiBoxBytes;  // 4 epilogue warps x 2 buffers = 32 KiB
+// layout: [TMA ring][barriers, 1 KiB][epilogue boxes, 1024-byte aligned swizzle atoms] (+1 KiB alignment slack)
+constexpr int kSmemBytesFused = kStages * kStageBytes + 1024 + kEpiSmemBytes + 1024;
 constexpr int kSignalsPerUnit = 8;  // 4 epilogue warps x 2 CTAs arrive on the tile counter
 constexpr int kMaxUnicastRanks = 3;  // peer-load mode keeps ranks x rows x partial buffers requests in registers
 
@@ -98,6 +104,12 @@ struct WgradComm {
   int debug;             // timing experiments (M4T_WGRAD_DEBUG): 1 no comm data movement, 2 no GEMM,
                          // 4 local loads instead of multimem.ld_reduce, 8 local stores instead of multimem.st,
                          // 16 no tile signals and no owner work, 32 no completion barrier
+};
+
+// peer-store mode: tensor maps of this rank's staging area inside every OWNER's heap
+// ([ksplit * N rows, K columns] bf16, boxes of {64 columns, 32 rows}, 128-byte swizzle)
+struct PushMaps {
+  CUtensorMap owner[kMaxUnicastRanks];
 };
 
 struct __align__(8) Bars {
@@ -354,7 +366,7 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
 template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kWarps + (FUSED ? kCommWarps : 0)) * 32, 1)
 wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                          const WgradArgs g, const WgradComm wc) {
+                          const WgradArgs g, const WgradComm wc, const __grid_constant__ PushMaps push) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars* bars = reinterpret_cast<Bars*>(smem + kStages * kStageBytes);
@@ -484,13 +496,62 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
       // plain / multicast mode: this rank's own staging buffer.  Peer-store mode: the OWNER's staging area for
       // this source rank - posted writes over NVLink, spread over the whole GEMM, so the owner never has to
       // pull (no read round trips on the reduction path).
-      char* obase = static_cast<char*>(g.out);
-      if (FUSED && wc.unicast)
-        obase = wc.heap[t % wc.sync.size] + wc.stage_off + static_cast<int64_t>(wc.sync.rank) * wc.src_stride;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(obase + h * g.out_split_stride) +
+      uint16_t* orow = reinterpret_cast<uint16_t*>(static_cast<char*>(g.out) + h * g.out_split_stride) +
                        static_cast<int64_t>(row) * g.ldo + k_blk * BN;
       const float gs = (g.gscale ? __ldg(g.gscale) : 1.0f) * (g.axpy != 0.0f ? g.axpy : 1.0f);
       const bool axpy = !FUSED && g.axpy != 0.0f;
+      if (FUSED && wc.unicast) {
+        // Peer-store mode: push this warp's 32 x 256 piece of the partial tile into the OWNER's staging area for
+        // this source rank.  TMEM -> registers -> swizzled shared memory -> TMA bulk tensor store: whole 128-byte
+        // rows cross NVLink as posted writes issued by the copy engine of the SM, the warp itself never waits
+        // for them (only for its shared-memory buffer to be read), and the owner later reads everything locally.
+        uint8_t* ebuf = smem + kStages * kStageBytes + 1024 + q * (2 * kEpiBoxBytes);
+        const CUtensorMap* omap = &push.owner[t % wc.sync.size];
+        const int row0 = h * g.N + n_blk * BM2 + static_cast<int>(cta) * BMC + q * 32;  // first row of the box
+#pragma unroll 1
+        for (int c2 = 0; c2 < BN / 64; ++c2) {
+          uint8_t* buf = ebuf + (c2 & 1) * kEpiBoxBytes;
+          // the store that last used this buffer (two boxes ago) must have finished reading it
+          if (lane == 0) tc::tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + c2 * 64 + half * 32);
+            tc::tmem_ld_32x32b_x32(taddr, r);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              Vec16 o;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o.w[e] = pack2(gs * __uint_as_float(r[v * 8 + 2 * e]), gs * __uint_as_float(r[v * 8 + 2 * e + 1]));
+              // row `lane`, 16-byte chunk j of the 128-byte row, stored at chunk j ^ (row & 7) (SWIZZLE_128B)
+              const int j = half * 4 + v;
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(o.w[0], o.w[1], o.w[2], o.w[3]);
+            }
+          }
+          tc::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tc::tma_store_2d(omap, buf, k_blk * BN + c2 * 64, row0);
+            tc::tma_store_commit();
+          }
+        }
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) tc::mbar_arrive(&bars->tmem_empty[acc]);  // the accumulator is drained: the MMA warp may reuse it
+          else tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bars->tmem_empty[acc]), 0));
+          if (!(wc.debug & 16)) {
+            tc::tma_store_wait<0>();  // all four boxes have been written (performed), then publish them to the owner
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(wc.heap[t % wc.sync.size] + wc.cnt_off) + t;
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -552,7 +613,8 @@ CUtensorMap make_tmap_mn(const void* base, int64_t rows, int64_t cols, int64_t l
 template <bool FUSED> void configure_w() {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_nt_2cta_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_nt_2cta_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FUSED ? kSmemBytesFused : kSmemBytes);
     M4T_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(smem) failed: " << cudaGetErrorString(e));
   });
 }
@@ -591,7 +653,7 @@ void launch_wgrad_bf16(const void* dy, const void* x, void* gout, int64_t Mb, in
   const int tiles = static_cast<int>((N / BM2) * (K / BN));
   const int clusters = std::max(1, std::min(tiles, sm_count / 2));
   configure_w<false>();
-  wgrad_bf16_nt_2cta_kernel<false><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, WgradComm{});
+  wgrad_bf16_nt_2cta_kernel<false><<<2 * clusters, kWarps * 32, kSmemBytes, stream>>>(ta, tb, g, WgradComm{}, PushMaps{});
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "wgrad_bf16 launch failed: " << cudaGetErrorString(e));
   note_kernel_launch(axpy != 0.0f ? "wgrad_2cta_sgd_epilogue" : "wgrad_2cta");
@@ -645,7 +707,14 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   wc.debug = g_wgrad_debug.load(std::memory_order_relaxed);
   const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
   configure_w<true>();
-  wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytes, stream>>>(ta, tb, g, wc);
+  PushMaps push{};
+  if (!use_multicast) {
+    M4T_CHECK(stage_stride == N * K * 2, "peer-store mode expects densely packed partial buffers");
+    for (int p = 0; p < dc.sync.size; ++p)  // my staging area inside rank p's heap: rows [h * N + n] of K columns
+      push.owner[p] = make_tmap_bf16_sw128(dc.heap[p] + stage_off + static_cast<int64_t>(dc.sync.rank) * src_stride,
+                                           static_cast<int64_t>(ksplit) * N, K, K, 64, 32);
+  }
+  wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytesFused, stream>>>(ta, tb, g, wc, push);
   cudaError_t e = cudaGetLastError();
   M4T_CHECK(e == cudaSuccess, "fused_wgrad_update launch failed: " << cudaGetErrorString(e));
   note_kernel_launch(wc.prefetch ? "fused_wgrad_reduce_scatter_sgd_prefetch" : "fused_wgrad_reduce_scatter_sgd");

@@ -425,7 +425,7 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
     // two work units per tile even out the last wave on 74 CTA pairs (M4T_WGRAD_KSPLIT=1 disables)
     static const int64_t ksplit_env = env_i64("M4T_WGRAD_KSPLIT", 2);  // read once
     st.ksplit = (ksplit_env >= 2 && (Mb / 64) % 2 == 0) ? 2 : 1;
-    st.stage_stride = round_up64(N * K * 2, 1024);
+    st.stage_stride = N * K * 2;  // dense: the peer-store epilogue addresses [ksplit * N, K] through one tensor map
     // multicast mode: one staging area per rank (own partials, pulled through the switch by the owners);
     // peer-store mode: one area per SOURCE rank in every heap (the epilogues push to the owner)
     st.src_stride = st.stage_stride * st.ksplit;
