@@ -11,8 +11,8 @@ import re, collections
 txt = open('/tmp/m4t_sass.txt').read()
 funcs = re.split(r'\n\s*Function : ', txt)
 want = {
-  'gemm_bf16_tn_2cta_kernelILb1ELi1E': 'fused_allreduce_gemm_mse_cta_pair',
-  'gemm_bf16_tn_2cta_kernelILb0ELi0E': 'gemm_tcgen05_cta_pair',
+  'gemm_bf16_tn_2cta_kernelILb1ELi1ELb0E': 'fused_allreduce_gemm_mse_cta_pair',
+  'gemm_bf16_tn_2cta_kernelILb0ELi0ELb0E': 'gemm_tcgen05_cta_pair',
   'gemm_bf16_tn_kernelILb1ELi1E': 'fused_allreduce_gemm_mse_single_cta',
   'gemm_bf16_tn_kernelILb0ELi0E': 'gemm_tcgen05_single_cta',
   'allreduce_pipelined_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'allreduce_nvls_pipelined_bf16_sum',
@@ -20,7 +20,9 @@ want = {
   'allreduce_oneshot_kernelILNS_5DTypeE7ELNS_8ReduceOpE2E': 'allreduce_oneshot_bf16_sum',
   'wgrad_bf16_nt_2cta_kernelILb1E': 'fused_wgrad_reduce_scatter_sgd_cta_pair',
   'wgrad_bf16_nt_2cta_kernelILb0E': 'wgrad_mn_major_cta_pair',
-  'gemm_bf16_tn_2cta_kernelILb0ELi1E': 'gemm_mse_epilogue_cta_pair',
+  'gemm_bf16_tn_2cta_kernelILb0ELi1ELb0E': 'gemm_mse_epilogue_cta_pair',
+  'gemm_bf16_tn_2cta_kernelILb0ELi0ELb1E': 'gemm_nn_dgrad_cta_pair',
+  'p2p_flag_wait_kernel': 'p2p_copy_engine_flag_wait',
   'slab_reduce_vec_kernelILNS_5DTypeE7ELNS_8ReduceOpE2ELNS_8NvlsKindE2E': 'reduce_scatter_nvls_bf16_sum',
   'p2p_recv_kernel': 'p2p_recv',
   'slab_pull_kernelILi16E': 'slab_pull_16B',
