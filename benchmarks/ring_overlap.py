@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Isend/Irecv/Wait ring with JoinDummies, overlapped with compute
 (BASELINE.json config 5).  Measures, device-timed and max over ranks:
-  t_comm   ring exchange alone (forward + backward)
-  t_gemm   a GEMM chain alone
-  t_both   the exchange started before the GEMM chain, waited on after it
+  t_comm   ring exchange alone (forward + backward; buffers preallocated)
+  t_gemm   a differentiable GEMM chain alone (forward + backward)
+  t_both   the exchange started before the GEMM chain and waited on after it, one backward over both
 and reports overlap = (t_comm + t_gemm - t_both) / min(t_comm, t_gemm).
 
     python -m mpi4torch_b200.launch -np 8 benchmarks/ring_overlap.py [--mb 64]
@@ -31,8 +31,13 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     right, left = (R + 1) % P, (R + P - 1) % P
     n = args.mb * (1 << 20) // 2
-    a = torch.randn(4096, 4096, device=dev).to(torch.bfloat16)
+    a = torch.randn(4096, 4096, device=dev).to(torch.bfloat16).requires_grad_()
     b = torch.randn(4096, 4096, device=dev).to(torch.bfloat16)
+    # everything the exchange needs is allocated once: the timed region contains the p2p operations, the
+    # JoinDummies edges and autograd's own bookkeeping, nothing else
+    x = torch.full((n,), float(R), device=dev, dtype=torch.bfloat16).requires_grad_()
+    g_got = torch.ones(n, device=dev, dtype=torch.bfloat16)
+    g_c = torch.ones(4096, 4096, device=dev, dtype=torch.bfloat16)
 
     def gemm_chain():
         c = a
@@ -40,15 +45,25 @@ def main():
             c = c @ b
         return c
 
+    def gemm_fwd_bwd():
+        a.grad = None
+        gemm_chain().backward(g_c)
+
     def ring(with_compute: bool):
-        x = torch.full((n,), float(R), device=dev, dtype=torch.bfloat16).requires_grad_()
+        """Forward: Isend right / Irecv left, (GEMM chain on the compute stream), Wait both.  Backward: the Wait
+        nodes run first and START the reverse transfers, the GEMM chain's backward runs next, the Isend/Irecv
+        nodes run last and wait for the transfers - so compute can hide both directions."""
+        x.grad = None
+        a.grad = None
         s = comm.Isend(x, right, 0)
         r = comm.Irecv(m4t.JoinDummies(torch.empty_like(x), [s.dummy]), left, 0)
-        if with_compute:
-            gemm_chain()  # runs on the compute stream while the side streams move data
+        c = gemm_chain() if with_compute else None  # runs on the compute stream while the side streams move data
         sent = comm.Wait(m4t.JoinDummiesHandle(s, [r.dummy]))
         got = comm.Wait(m4t.JoinDummiesHandle(r, [sent]))
-        (got.float().sum()).backward()
+        if with_compute:
+            torch.autograd.backward([got, c], [g_got, g_c])
+        else:
+            got.backward(g_got)
         return got, x
 
     def timed(fn, iters=5):
@@ -69,7 +84,7 @@ def main():
     torch.cuda.synchronize()
     ok = bool((got.detach() == left).all()) and bool((x.grad == 1).all())
     t_comm = timed(lambda: ring(False))
-    t_gemm = timed(gemm_chain)
+    t_gemm = timed(gemm_fwd_bwd)
     t_both = timed(lambda: ring(True))
     overlap = (t_comm + t_gemm - t_both) / max(1e-9, min(t_comm, t_gemm))
     res = {"world": P, "message_mb": args.mb, "correct": ok, "t_comm_ms": t_comm, "t_gemm_ms": t_gemm, "t_both_ms": t_both,
