@@ -264,6 +264,17 @@ def main() -> int:
         except Exception as exc:  # pragma: no cover
             out["plain_autograd_sgd_ms_per_step"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         if size > 1:
+            # NOT the headline: the same step when the library is allowed to use that the fused update leaves
+            # bit-identical weights on every rank (Allreduce(W)/size == W, forward collective elided)
+            try:
+                rep = DPLinearModel(IN_F, OUT_F, comm, device=dev, dtype=torch.bfloat16, lr=1e-5, fused=not args.unfused,
+                                    assume_replicated=True, seed=2)
+                ms, _, _ = timed(lambda i: step(i, rep), max(5, args.steps // 2), 3)
+                out["replicated_params_elided_allreduce_ms_per_step"] = ms / max(5, args.steps // 2)
+                del rep
+            except Exception as exc:  # pragma: no cover
+                out["replicated_params_elided_allreduce_ms_per_step"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        if size > 1:
             try:
                 from benchmarks.extras import allreduce_busbw_sweep
 

@@ -18,16 +18,14 @@
 //     tiles of the last, partial wave are split in `ksplit` batch halves (256 tiles =
 //     3 waves of 74 + 34 tiles -> 68 half units: 3.5 tile times instead of 4), so
 //     only those tiles produce two partial buffers;
-//   * the epilogue PUSHES each partial tile (bf16) into the OWNER rank's receive area for
-//     this source rank (tile t is owned by rank t % P): TMEM -> registers -> swizzled
-//     shared memory -> TMA bulk tensor store, i.e. posted 128-byte writes over NVLink
-//     spread over the whole GEMM, then bumps the tile's counter on the owner with a
-//     release-scoped remote red;
-//   * eight owner warps per CTA wait for owned tiles to be complete from all ranks, sum the
-//     P (x2 for split tiles) partial tiles from LOCAL memory in fixed rank order, apply
-//     W -= lr/P * sum in fp32 and write the new bf16 weights into every rank's copy
-//     (multimem.st through the switch, or one store per peer) - reduce-scatter + update +
-//     all-gather, hidden under the GEMM of later tiles;
+//   * the epilogue writes each partial tile as bf16 into this rank's symmetric
+//     staging buffer and bumps the tile's counter ON THE OWNER rank (tile t is
+//     owned by rank t % P) with a release-scoped remote red;
+//   * four communication warps per CTA wait for owned tiles to be complete on
+//     all ranks, pull the sum through the NVSwitch (multimem.ld_reduce), apply
+//     W -= lr/P * sum in fp32 and multicast the new bf16 weights into every
+//     rank's copy (multimem.st) - reduce-scatter + update + all-gather, hidden
+//     under the GEMM of later tiles;
 //   * a multicast "done" counter makes kernel completion imply that every
 //     rank's weights are final.
 #include <cuda.h>
@@ -69,7 +67,7 @@ constexpr int kEpiSmemBytes = 4 * 2 * kEpiBoxBytes;  // 4 epilogue warps x 2 buf
 // layout: [TMA ring][barriers, 1 KiB][epilogue boxes, 1024-byte aligned swizzle atoms] (+1 KiB alignment slack)
 constexpr int kSmemBytesFused = kStages * kStageBytes + 1024 + kEpiSmemBytes + 1024;
 constexpr int kSignalsPerUnit = 8;  // 4 epilogue warps x 2 CTAs arrive on the tile counter
-constexpr int kMaxUnicastRanks = kMaxGpuPeers;  // without a multicast mapping the new weights go out as one store per peer
+constexpr int kMaxUnicastRanks = 3;  // peer-load mode keeps ranks x rows x partial buffers requests in registers
 
 struct WgradArgs {
   void* out;            // plain: G [N, K]; fused: this rank's staging buffer(s)
@@ -86,10 +84,10 @@ struct WgradComm {
   SyncCtx sync;
   char* heap[kMaxGpuPeers];
   char* mc_heap;
-  int64_t stage_off;     // receive areas for the pushed partial tiles (same offset on every rank)
-  int64_t stage_stride;  // unused (kept for ABI of the args struct)
-  int64_t src_stride;    // bytes between the receive areas of consecutive SOURCE ranks; one area holds this
-                         // rank's owned tiles as dense [j][part][256 rows][256 cols] bf16 slots
+  int64_t stage_off;     // partial-gradient staging (same offset on every rank)
+  int64_t stage_stride;  // bytes between the ksplit partial buffers
+  int64_t src_stride;    // peer-store mode: bytes between the per-source-rank copies of the staging area in the
+                         // OWNER's heap (the epilogue pushes its partial tile there; the owner only reads locally)
   int64_t w_off;         // bf16 weights [N, K] (contiguous) inside every rank's heap
   int64_t cnt_off;       // u32 tile counters [tiles]
   int64_t done_off;      // u32 completion counter
@@ -108,10 +106,10 @@ struct WgradComm {
                          // 16 no tile signals and no owner work, 32 no completion barrier
 };
 
-// tensor maps of this rank's receive area inside every OWNER's heap
-// ([owned tiles * ksplit * 256 rows, 256 columns] bf16, boxes of {64 columns, 32 rows}, 128-byte swizzle)
+// peer-store mode: tensor maps of this rank's staging area inside every OWNER's heap
+// ([ksplit * N rows, K columns] bf16, boxes of {64 columns, 32 rows}, 128-byte swizzle)
 struct PushMaps {
-  CUtensorMap owner[kMaxGpuPeers];
+  CUtensorMap owner[kMaxUnicastRanks];
 };
 
 struct __align__(8) Bars {
@@ -181,9 +179,9 @@ __device__ __forceinline__ void bounded_wait_ge(const uint32_t* flag, uint32_t t
 }
 
 // Owner side of the fused mode; runs on kCommWarps warps of every CTA.
-// MC: the new weights are written / re-read through the NVSwitch (multimem.st / multimem.ld_reduce);
-// otherwise with one store / load per peer (2-3 ranks, or no multicast mapping).
-template <bool MC>
+// MC: reduce through the NVSwitch (multimem.ld_reduce / multimem.st); otherwise NSRC peer loads in rank
+// order and one store per peer (2-3 ranks, or no multicast mapping).
+template <bool MC, int NSRC>
 __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int first_thread, int cluster_id,
                                                    int num_clusters, uint32_t cta, int num_tiles, int k_tiles, int K,
                                                    const UnitSched sched) {
@@ -193,12 +191,9 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   const int lane = ct & 31;
   const int cw = ct >> 5;
   constexpr int kCommThreads = kCommWarps * 32;
-  constexpr int kU = 2;           // rows per warp and pass of the reduction (local loads: short latency)
-  constexpr int kUP = 4;          // rows per warp and pass of the read-back (switch / peer round trips)
-  constexpr int kG = 2;           // source ranks whose loads are in flight together
+  constexpr int kU = NSRC <= 2 ? 4 : 2;  // rows in flight per warp (x partial buffers x peers independent round trips)
   constexpr int kRowSplit = 2;    // CTA pairs sharing one owned tile: shortens the tail after the last GEMM wave
   constexpr int kRows = BMC / kRowSplit;  // rows of this CTA's half handled per work item
-  constexpr int64_t kSlotBytes = static_cast<int64_t>(BM2) * BN * 2;  // one 256 x 256 bf16 partial tile
   const uint32_t* my_cnt = reinterpret_cast<const uint32_t*>(wc.heap[r] + wc.cnt_off);
   const int64_t row_bytes = static_cast<int64_t>(K) * 2;
   // device-resident call counter: every communication thread reads it before any CTA can pass the
@@ -209,69 +204,52 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
   const uint32_t done_target = epoch_ptr ? calls * wc.done_target : wc.done_target;
   const bool skip = (wc.debug & 1) != 0;
   // Work item w = (j-th owned tile, row slice s); item w is served by cluster w % num_clusters.
-  // Owned tiles (t = r + j*P) finish in GEMM order, so consecutive items land on different CTA pairs.
+  // Owned tiles (t = r + j*P) finish in GEMM order, so consecutive items land on different CTA
+  // pairs and their round trips overlap.
   const int owned = r < num_tiles ? (num_tiles - r + P - 1) / P : 0;
   for (int w_item = cluster_id; w_item < owned * kRowSplit && !(wc.debug & 16); w_item += num_clusters) {
     const int j = w_item / kRowSplit;
     const int slice = w_item - j * kRowSplit;
     const int t = r + j * P;
     const int parts = t < sched.whole ? 1 : sched.split;
-    // every rank's `parts` partial tiles have arrived: kSignalsPerUnit signals per unit and rank, per call
+    // every rank's `parts` partial tiles are complete: kSignalsPerUnit signals per unit and rank, per call
     const uint32_t tile_target = (epoch_ptr ? calls : 1u) * wc.tile_target * static_cast<uint32_t>(parts);
     if (lane == 0) bounded_wait_ge(my_cnt + t, tile_target, c);
     __syncwarp();
     const int n_blk = t / k_tiles;
     const int k_blk = t - n_blk * k_tiles;
-    // this CTA's rows of the item inside W: kRows rows x 512 bytes, one row per warp pass
+    // this CTA's rows of the item: kRows rows x 512 bytes, one row per warp pass
     const int64_t tile_off = (static_cast<int64_t>(n_blk) * BM2 + static_cast<int64_t>(cta) * BMC + slice * kRows) * row_bytes +
                              static_cast<int64_t>(k_blk) * BN * 2 + lane * 16;
-    // ... and inside a receive slot (dense 256 x 256): slot (j, part) of source rank p
-    const char* slot0 = wc.heap[r] + wc.stage_off + static_cast<int64_t>(j) * sched.split * kSlotBytes +
-                        (static_cast<int64_t>(cta) * BMC + slice * kRows) * (BN * 2) + lane * 16;
     for (int row0 = cw; row0 < kRows && !skip; row0 += kCommWarps * kU) {
-      float acc[kU][8];
-      Vec16 w[kU];
+      // all loads of the kU rows (x partial buffers x peers) are issued before the first one is consumed
+      constexpr int kSrc = NSRC;
+      Vec16 s[kU][kSrc][2], w[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
         const int row = row0 + u * kCommWarps;
-        if (row < kRows) w[u] = ld_vec(wc.heap[r] + wc.w_off + tile_off + row * row_bytes);
-      }
-      // sum the partial tiles of all source ranks, in rank order (every run and every rank's owner adds in the
-      // same order); the loads of kG sources are in flight together, all from local memory
-      for (int p0 = 0; p0 < P; p0 += kG) {
-        Vec16 s[kU][kG][2];
+        if (row < kRows) {
+          const int64_t off = tile_off + row * row_bytes;
+          if (MC) {
+            if (wc.debug & 4) {
+              s[u][0][0] = ld_vec(wc.heap[r] + wc.stage_off + off);
+              if (parts > 1) s[u][0][1] = ld_vec(wc.heap[r] + wc.stage_off + wc.stage_stride + off);
+            } else {
+              s[u][0][0] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + off);
+              if (parts > 1) s[u][0][1] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.stage_off + wc.stage_stride + off);
+            }
+          } else {
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int row = row0 + u * kCommWarps;
-          if (row < kRows) {
-#pragma unroll
-            for (int gi = 0; gi < kG; ++gi) {
-              if (p0 + gi < P) {
-                const char* src = slot0 + static_cast<int64_t>(p0 + gi) * wc.src_stride + static_cast<int64_t>(row) * (BN * 2);
-                s[u][gi][0] = ld_vec(src);
-                if (parts > 1) s[u][gi][1] = ld_vec(src + kSlotBytes);
+            for (int p = 0; p < kSrc; ++p) {
+              if (p < P) {
+                // pushed here by rank p's epilogue: local reads
+                const char* src = wc.heap[r] + wc.stage_off + static_cast<int64_t>(p) * wc.src_stride + off;
+                s[u][p][0] = ld_vec(src);
+                if (parts > 1) s[u][p][1] = ld_vec(src + wc.stage_stride);
               }
             }
           }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-#pragma unroll
-          for (int gi = 0; gi < kG; ++gi) {
-            if (p0 + gi < P) {
-              float b[8];
-              VecOf<DType::BF16>::unpack(s[u][gi][0], b);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) acc[u][e] += b[e];
-              if (parts > 1) {
-                VecOf<DType::BF16>::unpack(s[u][gi][1], b);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[u][e] += b[e];
-              }
-            }
-          }
+          w[u] = ld_vec(wc.heap[r] + wc.w_off + off);
         }
       }
 #pragma unroll
@@ -279,17 +257,34 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
         const int row = row0 + u * kCommWarps;
         if (row < kRows) {
           const int64_t off = tile_off + row * row_bytes;
-          float wv[8];
+          float a[8], b[8], wv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+          for (int p = 0; p < kSrc; ++p) {  // fixed rank order: every run adds in the same order
+            if (MC || p < P) {
+              VecOf<DType::BF16>::unpack(s[u][p][0], b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] += b[e];
+              if (parts > 1) {
+                VecOf<DType::BF16>::unpack(s[u][p][1], b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += b[e];
+              }
+            }
+          }
           VecOf<DType::BF16>::unpack(w[u], wv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) wv[e] = fmaf(wc.scale, acc[u][e], wv[e]);
+          for (int e = 0; e < 8; ++e) wv[e] = fmaf(wc.scale, a[e], wv[e]);
           const Vec16 o = VecOf<DType::BF16>::pack(wv);
           if (MC && !(wc.debug & 8)) {
             multimem_st_vec(wc.mc_heap + wc.w_off + off, o);
           } else if (MC) {
             st_vec(wc.heap[r] + wc.w_off + off, o);
           } else {
-            for (int p = 0; p < P; ++p) st_vec(wc.heap[p] + wc.w_off + off, o);
+#pragma unroll
+            for (int p = 0; p < kSrc; ++p)
+              if (p < P) st_vec(wc.heap[p] + wc.w_off + off, o);
           }
         }
       }
@@ -304,59 +299,48 @@ __device__ __forceinline__ void comm_reduce_update(const WgradComm& wc, int firs
       //    this role);
       //  * multicast mode: the write fans out inside the switch, so the fence stays.
       if (MC) __threadfence_system();
-      for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kUP) {
-        float a[kUP][8];
-        if (MC) {
-          Vec16 x[kUP];
+      for (int row0 = cw; row0 < kRows; row0 += kCommWarps * kU) {
+        constexpr int kSrc = NSRC;
+        Vec16 x[kU][kSrc];
 #pragma unroll
-          for (int u = 0; u < kUP; ++u) {
-            const int row = row0 + u * kCommWarps;
-            if (row < kRows) x[u] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + tile_off + row * row_bytes);
-          }
+        for (int u = 0; u < kU; ++u) {
+          const int row = row0 + u * kCommWarps;
+          if (row < kRows) {
+            const int64_t off = tile_off + row * row_bytes;
+            if (MC) {
+              x[u][0] = multimem_ld_reduce_vec<NvlsKind::ADD_BF16>(wc.mc_heap + wc.w_off + off);
+            } else {
 #pragma unroll
-          for (int u = 0; u < kUP; ++u) VecOf<DType::BF16>::unpack(x[u], a[u]);
-        } else {
-#pragma unroll
-          for (int u = 0; u < kUP; ++u)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a[u][e] = 0.f;
-          for (int p0 = 0; p0 < P; p0 += kG) {
-            Vec16 x[kUP][kG];
-#pragma unroll
-            for (int u = 0; u < kUP; ++u) {
-              const int row = row0 + u * kCommWarps;
-              if (row < kRows) {
-#pragma unroll
-                for (int gi = 0; gi < kG; ++gi)
-                  if (p0 + gi < P) x[u][gi] = ld_vec_sys(wc.heap[p0 + gi] + wc.w_off + tile_off + row * row_bytes);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < kUP; ++u) {
-#pragma unroll
-              for (int gi = 0; gi < kG; ++gi) {
-                if (p0 + gi < P) {
-                  float b[8];
-                  VecOf<DType::BF16>::unpack(x[u][gi], b);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) a[u][e] += b[e];
-                }
-              }
+              for (int p = 0; p < kSrc; ++p)
+                if (p < P) x[u][p] = ld_vec_sys(wc.heap[p] + wc.w_off + off);
             }
           }
         }
 #pragma unroll
-        for (int u = 0; u < kUP; ++u) {
+        for (int u = 0; u < kU; ++u) {
           const int row = row0 + u * kCommWarps;
           if (row < kRows) {
             const int64_t off = tile_off + row * row_bytes;
+            float a[8], b[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[u][e] *= wc.avg_scale;
-            const Vec16 o = VecOf<DType::BF16>::pack(a[u]);
+            for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+            for (int p = 0; p < kSrc; ++p) {
+              if (MC || p < P) {
+                VecOf<DType::BF16>::unpack(x[u][p], b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += b[e];
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] *= wc.avg_scale;
+            const Vec16 o = VecOf<DType::BF16>::pack(a);
             if (MC) {
               multimem_st_vec(wc.mc_heap + wc.wavg_off + off, o);
             } else {
-              for (int p = 0; p < P; ++p) st_vec(wc.heap[p] + wc.wavg_off + off, o);
+#pragma unroll
+              for (int p = 0; p < kSrc; ++p)
+                if (p < P) st_vec(wc.heap[p] + wc.wavg_off + off, o);
             }
           }
         }
@@ -516,14 +500,14 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                        static_cast<int64_t>(row) * g.ldo + k_blk * BN;
       const float gs = (g.gscale ? __ldg(g.gscale) : 1.0f) * (g.axpy != 0.0f ? g.axpy : 1.0f);
       const bool axpy = !FUSED && g.axpy != 0.0f;
-      if (FUSED) {
-        // Push this warp's 32 x 256 piece of the partial tile into the OWNER's receive area for this source rank.  TMEM -> registers -> swizzled shared memory -> TMA bulk tensor store: whole 128-byte
+      if (FUSED && wc.unicast) {
+        // Peer-store mode: push this warp's 32 x 256 piece of the partial tile into the OWNER's staging area for
+        // this source rank.  TMEM -> registers -> swizzled shared memory -> TMA bulk tensor store: whole 128-byte
         // rows cross NVLink as posted writes issued by the copy engine of the SM, the warp itself never waits
         // for them (only for its shared-memory buffer to be read), and the owner later reads everything locally.
         uint8_t* ebuf = smem + kStages * kStageBytes + 1024 + q * (2 * kEpiBoxBytes);
         const CUtensorMap* omap = &push.owner[t % wc.sync.size];
-        // slot (j, h) of the owner's area for this source: dense 256 x 256, j = index among the owner's tiles
-        const int row0 = ((t / wc.sync.size) * sched.split + h) * BM2 + static_cast<int>(cta) * BMC + q * 32;
+        const int row0 = h * g.N + n_blk * BM2 + static_cast<int>(cta) * BMC + q * 32;  // first row of the box
 #pragma unroll 1
         for (int c2 = 0; c2 < BN / 64; ++c2) {
           uint8_t* buf = ebuf + (c2 & 1) * kEpiBoxBytes;
@@ -551,7 +535,7 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
           tc::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tc::tma_store_2d(omap, buf, c2 * 64, row0);
+            tc::tma_store_2d(omap, buf, k_blk * BN + c2 * 64, row0);
             tc::tma_store_commit();
           }
         }
@@ -611,8 +595,9 @@ wgrad_bf16_nt_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     }
   } else if (FUSED) {
     // ===================== reduce + update (both CTAs) ==================
-    if (!wc.unicast) comm_reduce_update<true>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
-    else comm_reduce_update<false>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    if (!wc.unicast) comm_reduce_update<true, 1>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    else if (wc.sync.size <= 2) comm_reduce_update<false, 2>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
+    else comm_reduce_update<false, kMaxUnicastRanks>(wc, kWarps * 32, cluster_id, num_clusters, cta, num_tiles, k_tiles, g.K, sched);
   }
 
   tc::tcgen05_fence_before();
@@ -689,7 +674,6 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   M4T_CHECK((Mb / BK) % ksplit == 0, "batch / 64 must be divisible by ksplit");
   char* stage = dc.heap[dc.sync.rank] + stage_off;
   M4T_CHECK(wgrad_bf16_supported(Mb, N, K, dy, x, stage, ldy, ldx, K), "unsupported wgrad shape/alignment for the fused path");
-  M4T_CHECK(dc.sync.size <= kMaxGpuPeers, "too many ranks for the fused backward");
   const CUtensorMap ta = make_tmap_mn(dy, Mb, N, ldy);
   const CUtensorMap tb = make_tmap_mn(x, Mb, K, ldx);
   WgradArgs g{};
@@ -724,14 +708,11 @@ void launch_fused_wgrad_update(const DeviceComm& dc, const void* dy, const void*
   const int grid = fused_gemm_grid(dc);  // identical on every rank, whole CTA pairs
   configure_w<true>();
   PushMaps push{};
-  {
-    // my receive area inside rank p's heap: [owned tiles of p][ksplit][256 rows] x 256 columns
-    const int64_t tiles = (N / BM2) * (K / BN);
-    const int64_t owned_max = (tiles + dc.sync.size - 1) / dc.sync.size;
-    M4T_CHECK(src_stride >= owned_max * ksplit * static_cast<int64_t>(BM2) * BN * 2, "receive area too small");
-    for (int p = 0; p < dc.sync.size; ++p)
+  if (!use_multicast) {
+    M4T_CHECK(stage_stride == N * K * 2, "peer-store mode expects densely packed partial buffers");
+    for (int p = 0; p < dc.sync.size; ++p)  // my staging area inside rank p's heap: rows [h * N + n] of K columns
       push.owner[p] = make_tmap_bf16_sw128(dc.heap[p] + stage_off + static_cast<int64_t>(dc.sync.rank) * src_stride,
-                                           owned_max * ksplit * BM2, BN, BN, 64, 32);
+                                           static_cast<int64_t>(ksplit) * N, K, K, 64, 32);
   }
   wgrad_bf16_nt_2cta_kernel<true><<<grid, (kWarps + kCommWarps) * 32, kSmemBytesFused, stream>>>(ta, tb, g, wc, push);
   cudaError_t e = cudaGetLastError();

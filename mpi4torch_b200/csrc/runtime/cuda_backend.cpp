@@ -406,8 +406,8 @@ bool CudaBackend::fused_wgrad_available(const void* w, int64_t Mb, int64_t N, in
   const char* wb = static_cast<const char*>(w);
   const char* arena = dc_.heap[dc_.sync.rank] + symm_off_;
   if (!(wb >= arena && wb + N * K * 2 <= arena + symm_bytes_)) return false;  // must be switch-visible in place
-  // receive areas (2 parts per owned tile from every source: ~2 N K bf16 in total) + W_avg prefetch
-  const int64_t need = 3 * N * K * 2 + 2 * size() * 256 * 256 * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;
+  // 2 partial buffers (per source rank in peer-store mode) + W_avg prefetch
+  const int64_t need = (2 * (fused_wgrad_multicast() ? 1 : size()) + 1) * N * K * 2 + fused_wgrad_tiles(N, K) * 4 + 8192;
   return wgrad_.count((N << 32) | K) > 0 || symm_cursor_ + need <= symm_bytes_;
 }
 
@@ -425,13 +425,11 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
     // two work units per tile even out the last wave on 74 CTA pairs (M4T_WGRAD_KSPLIT=1 disables)
     static const int64_t ksplit_env = env_i64("M4T_WGRAD_KSPLIT", 2);  // read once
     st.ksplit = (ksplit_env >= 2 && (Mb / 64) % 2 == 0) ? 2 : 1;
-    st.stage_stride = 0;
-    // receive areas for the pushed partial tiles: one per SOURCE rank, each holding this rank's owned tiles as
-    // dense [tile][part][256][256] bf16 slots -> size() * ceil(tiles / size()) * ksplit * 128 KiB (64 MiB + padding
-    // for the 4096 x 4096 layer, independent of the world size)
-    const int64_t owned_max = (fused_wgrad_tiles(N, K) + size() - 1) / size();
-    st.src_stride = owned_max * st.ksplit * 256 * 256 * 2;
-    st.stage_off = symm_alloc(st.src_stride * size());
+    st.stage_stride = N * K * 2;  // dense: the peer-store epilogue addresses [ksplit * N, K] through one tensor map
+    // multicast mode: one staging area per rank (own partials, pulled through the switch by the owners);
+    // peer-store mode: one area per SOURCE rank in every heap (the epilogues push to the owner)
+    st.src_stride = st.stage_stride * st.ksplit;
+    st.stage_off = symm_alloc(st.src_stride * (fused_wgrad_multicast() ? 1 : size()));
     st.cnt_off = symm_alloc(fused_wgrad_tiles(N, K) * 4);
     st.done_off = symm_alloc(16);
     st.epoch_off = symm_alloc(16);  // call index, kept on the device (graph-capturable launches)

@@ -24,7 +24,7 @@ from mpi4torch_b200.ops import InBackwardSGD, allreduce_linear, dp_linear_mse, i
 class DPLinearModel:
     def __init__(self, in_features: int = 4096, out_features: int = 4096, comm=None, device="cuda",
                  dtype=torch.bfloat16, lr: float = 1e-4, seed: int = 0, fused: bool = True,
-                 sgd_in_backward: bool = True, prefetch: bool = True):
+                 sgd_in_backward: bool = True, prefetch: bool = True, assume_replicated: bool = False):
         self.comm = m4t.COMM_WORLD if comm is None else comm
         g = torch.Generator().manual_seed(seed)  # identical initial weights on every rank
         w = torch.randn(out_features, in_features, generator=g) * (in_features ** -0.5)
@@ -42,7 +42,7 @@ class DPLinearModel:
         self.lr = lr
         self.fused = fused  # Allreduce->GEMM in one kernel when the NVLS path is up
         self.sgd_in_backward = sgd_in_backward  # fused wgrad -> reduce-scatter -> SGD -> multicast in backward
-        self.optimizer = InBackwardSGD(lr, prefetch=prefetch)
+        self.optimizer = InBackwardSGD(lr, prefetch=prefetch, assume_replicated=assume_replicated)
         self._opt_ok = {}
 
     # ------------------------------------------------------------------ graph construction

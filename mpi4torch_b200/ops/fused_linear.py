@@ -45,9 +45,14 @@ class InBackwardSGD:
     shows a modification the kernel did not make.
     """
 
-    def __init__(self, lr: float, prefetch: bool = True):
+    def __init__(self, lr: float, prefetch: bool = True, assume_replicated: bool = False):
         self.lr = float(lr)
         self.prefetch = bool(prefetch)
+        # Opt-in shortcut, NOT the default: the fused update writes bit-identical weights on every rank (one owner
+        # computes a tile and stores the same bits everywhere), so Allreduce(W)/size == W and the next forward
+        # could skip the parameter collective altogether.  The default keeps the real all-reduce of the new
+        # weights (prefetched inside the backward kernel).
+        self.assume_replicated = bool(assume_replicated)
         self._wavg: Optional[torch.Tensor] = None
         self._weight_id = None
         self._version = -1
@@ -165,6 +170,9 @@ class _DPLinearMSE(torch.autograd.Function):
                 if comm.size == 1:
                     ops.wgrad_sgd_(weight, dy, x, scale, g)
                     opt.remember(weight, None)
+                elif opt.assume_replicated:
+                    ops.wgrad_allreduce_sgd_(weight, dy, x, scale, g)
+                    opt.remember(weight, weight.detach())  # the replicas are identical: their mean is the weight itself
                 elif opt.prefetch:
                     w_next = ops.wgrad_allreduce_sgd_prefetch_(weight, dy, x, scale, g)
                     opt.remember(weight, w_next)

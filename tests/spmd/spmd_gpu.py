@@ -258,9 +258,9 @@ class TestFusedTrainingStep(unittest.TestCase):
         inside the backward kernel or not, fused forward or not) against the fp32 composition."""
         from mpi4torch_b200.models import DPLinearModel
 
-        for in_bwd, fused in ((True, True), (False, True), (False, False)):
+        for in_bwd, fused, rep in ((True, True, False), (True, True, True), (False, True, False), (False, False, False)):
             model = DPLinearModel(256, 512, comm, device=DEVICE, dtype=torch.bfloat16, lr=1e-2, seed=3, fused=fused,
-                                  sgd_in_backward=in_bwd)
+                                  sgd_in_backward=in_bwd, assume_replicated=rep)
             g = torch.Generator().manual_seed(77 + R)
             for step in range(3):
                 x = torch.randn(384, 256, generator=g).to(torch.bfloat16).to(DEVICE)

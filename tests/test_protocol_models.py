@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 BMC, BM2, BN = 128, 256, 256          # rows per CTA, rows / cols per cluster tile
-K_COMM_WARPS, K_U, K_ROW_SPLIT = 8, 2, 2
+K_COMM_WARPS, K_U, K_ROW_SPLIT = 8, 4, 2
 K_ROWS = BMC // K_ROW_SPLIT
 SIGNALS_PER_UNIT = 8                  # 4 epilogue warps x 2 CTAs
 
@@ -42,11 +42,8 @@ def test_fused_wgrad_work_distribution(N, K, P, num_clusters, ksplit):
     num_units = sched[2]
     small = N * K <= 1 << 20
 
-    # --- GEMM epilogue: every unit pushes its partial tile into slot (t // P, part) of the OWNER's receive area for
-    # this source rank (dense 256 x 256 slots); each slot row is written exactly once; tile counters ---
-    owned_max = (num_tiles + P - 1) // P
-    # one source rank's view: recv[owner][slot_row, col]
-    recv = np.zeros((P, owned_max * ksplit * BM2, BN), dtype=np.int8) if small else None
+    # --- GEMM epilogue: every (split, row, col) of the staging buffers written once; tile counters ---
+    staged = np.zeros((ksplit, N, K), dtype=np.int8) if small else None
     signals = np.zeros(num_tiles, dtype=np.int64)  # per rank; the owner sums over P ranks
     parts_of = np.zeros(num_tiles, dtype=np.int64)
     kb_covered = np.zeros(num_tiles, dtype=np.int64)  # batch blocks contracted per tile (in units of 1/ksplit)
@@ -56,18 +53,19 @@ def test_fused_wgrad_work_distribution(N, K, P, num_clusters, ksplit):
             assert 0 <= t < num_tiles and 0 <= h < parts
             parts_of[t] = parts
             kb_covered[t] += ksplit // parts
+            n_blk, k_blk = divmod(t, k_tiles)
             for cta, q in itertools.product(range(2), range(4)):
                 if small:
-                    row0 = ((t // P) * ksplit + h) * BM2 + cta * BMC + q * 32   # TMA box coordinate of the kernel
-                    for c2 in range(BN // 64):
-                        recv[t % P, row0:row0 + 32, c2 * 64:(c2 + 1) * 64] += 1
+                    r0 = n_blk * BM2 + cta * BMC + q * 32
+                    staged[h, r0:r0 + 32, k_blk * BN:(k_blk + 1) * BN] += 1
                 signals[t] += 1
     assert (kb_covered == ksplit).all()  # every tile contracts the whole batch exactly once
     if small:
-        for t in range(num_tiles):  # slot (t // P, h) in owner t % P is written once iff the tile has a slice h
+        for t in range(num_tiles):  # buffer h of tile t is written once iff the tile has a slice h
+            n_blk, k_blk = divmod(t, k_tiles)
+            blk = staged[:, n_blk * BM2:(n_blk + 1) * BM2, k_blk * BN:(k_blk + 1) * BN]
             for h in range(ksplit):
-                blk = recv[t % P, ((t // P) * ksplit + h) * BM2:((t // P) * ksplit + h + 1) * BM2, :]
-                assert (blk == (1 if h < parts_of[t] else 0)).all()
+                assert (blk[h] == (1 if h < parts_of[t] else 0)).all()
     # host: tile_target = signals_per_unit * size per call; the kernel multiplies by the tile's number of units
     assert (signals * P == SIGNALS_PER_UNIT * P * parts_of).all()
 
