@@ -29,7 +29,6 @@ __device__ __forceinline__ void comm_allreduce_panels(const CommArgs& cm, int fi
   constexpr int BN = kPanelRows;
   const int n_tiles = n_panels;
   const int lane = threadIdx.x & 31;
-  struct { int K; } g{K};
     const SyncCtx& c = cm.sync;
     const int P = c.size, r = c.rank;
     const int ct = threadIdx.x - first_thread;  // 0 .. kCommWarps*32-1
@@ -46,7 +45,7 @@ __device__ __forceinline__ void comm_allreduce_panels(const CommArgs& cm, int fi
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kCommThreads));
     }
-    const int64_t row_bytes = static_cast<int64_t>(g.K) * 2;
+    const int64_t row_bytes = static_cast<int64_t>(K) * 2;
     const int rows_per_rank = BN / P;                      // host guarantees divisibility
     const int64_t slice_vecs = rows_per_rank * row_bytes / 16;
     DevEpilogue e;

@@ -34,7 +34,11 @@ CudaBackend::CudaBackend(Control& ctl, int device, int64_t stage_mb, int64_t sym
   tune_.p2p_blocks = static_cast<int>(env_i64("M4T_P2P_BLOCKS", 32));
   tune_.force_algo = static_cast<int>(env_i64("M4T_ALLREDUCE_ALGO", 0));
 
-  nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", 16))));
+  // 1 MiB slots; the copy-engine path moves half a ring per DMA, so a deeper ring means fewer, larger copies
+  // (64 MiB ring: 0.46 ms for a 64 MiB fwd+bwd exchange on 8 GPUs, 16 MiB ring: 0.64 ms).  Rings are per peer:
+  // the default keeps their total at 512 MiB per rank.
+  const int64_t default_slots = std::max<int64_t>(16, std::min<int64_t>(64, 512 / std::max(1, P)));
+  nslots_ = static_cast<int>(std::min<int64_t>(kMaxSlots, std::max<int64_t>(2, env_i64("M4T_P2P_SLOTS", default_slots))));
   slot_bytes_ = round_up64(std::max<int64_t>(4096, env_i64("M4T_P2P_SLOT_KB", 1024) * 1024), 128);
   p2p_push_ = env_i64("M4T_P2P_PUSH", 0) != 0;
   // messages of at least this many bytes move on the copy engines (-1: never); both ends decide from the
@@ -287,9 +291,12 @@ void CudaBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt
             "collective stages " << plan.max_stage_elems * es << " B per rank but the staging half is "
                                  << dc_.half_bytes << " B; raise M4T_STAGE_MB (M4T_SUB_STAGE_MB for communicators created by Split)");
   chain(s);
-  // experimental (M4T_AG_PUSH=1): Allgather as an NVSwitch multicast push; the
-  // eligibility test only looks at rank-independent quantities
-  static const bool ag_push = env_i64("M4T_AG_PUSH", 0) != 0;
+  // Allgather as an NVSwitch multicast push (each rank's shard leaves its GPU once, the switch replicates it)
+  // for shards up to 32 MiB, where it measured at or ahead of the pull kernel on 8 GPUs (0.51 vs 1.06 ms at
+  // 16 MiB per rank); larger shards pull (1.79 vs 1.91 ms at 64 MiB).  M4T_AG_PUSH=0/1 forces.  The
+  // eligibility test only looks at rank-independent quantities.
+  static const int64_t ag_push_mode = env_i64("M4T_AG_PUSH", -1);  // read once
+  const bool ag_push = ag_push_mode > 0 || (ag_push_mode < 0 && has_nvls() && plan.max_stage_elems * es <= (32ll << 20));
   if (ag_push && plan.replicated_output &&
       launch_allgather_push(dc_, plan, in, out, dt, grid_for(plan.max_out_elems, es, tune_.slab_blocks), s))
     return;

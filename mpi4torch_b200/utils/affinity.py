@@ -65,6 +65,49 @@ def gpu_local_cpus(device_index: int) -> Set[int]:
             pass
 
 
+def _parse_cpulist(text: str) -> Set[int]:
+    cpus: Set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def _numa_node_of(cpus: Set[int]) -> Optional[int]:
+    """NUMA node whose CPU list overlaps ``cpus`` most (None without /sys or on a single-node box)."""
+    base = "/sys/devices/system/node"
+    best, best_overlap, nodes = None, 0, 0
+    try:
+        for name in os.listdir(base):
+            if not name.startswith("node") or not name[4:].isdigit():
+                continue
+            nodes += 1
+            with open(os.path.join(base, name, "cpulist")) as f:
+                overlap = len(_parse_cpulist(f.read()) & cpus)
+            if overlap > best_overlap:
+                best, best_overlap = int(name[4:]), overlap
+    except OSError:
+        return None
+    return best if nodes > 1 else None
+
+
+def _prefer_numa_node(node: int) -> str:
+    """set_mempolicy(MPOL_PREFERRED, {node}) for the calling thread (inherited by threads it creates)."""
+    import ctypes
+
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()  # 1024 nodes
+        mask[node // (8 * ctypes.sizeof(ctypes.c_ulong))] = 1 << (node % (8 * ctypes.sizeof(ctypes.c_ulong)))
+        SYS_set_mempolicy, MPOL_PREFERRED = 238, 1  # x86_64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), 16 * 8 * ctypes.sizeof(ctypes.c_ulong) + 1)
+        return "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+    except Exception as exc:  # pragma: no cover
+        return f"{type(exc).__name__}"[:40]
+
+
 def bind_to_gpu_numa(device_index: Optional[int] = None) -> Dict[str, object]:
     """Restrict the calling thread (and the threads it creates from now on) to
     the CPUs local to its GPU.  Returns a small report for logs / bench JSON."""
@@ -95,6 +138,12 @@ def bind_to_gpu_numa(device_index: Optional[int] = None) -> Dict[str, object]:
         os.sched_setaffinity(0, target)
         report["bound"] = True
         report["cpus"] = len(target)
+        # CPU affinity only moves this thread; pinned staging buffers should also be ALLOCATED on the GPU's node no
+        # matter which thread (or driver helper thread) touches them first: prefer that node for all new pages.
+        node = _numa_node_of(target)
+        if node is not None:
+            report["numa_node"] = node
+            report["mempolicy"] = _prefer_numa_node(node)
     except Exception as exc:  # NVML missing, container cpuset, ...
         report["reason"] = f"{type(exc).__name__}: {exc}"[:120]
     return report
