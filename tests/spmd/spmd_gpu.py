@@ -194,10 +194,6 @@ class TestLargeP2P(unittest.TestCase):
         self.assertTrue(torch.equal(x.grad, right * torch.ones_like(x)))
 
 
-if __name__ == "__main__":
-    unittest.main()
-
-
 @unittest.skipUnless(CUDA, "needs the CUDA backend")
 class TestFusedAllreduceLinear(unittest.TestCase):
     def _weights(self, n, k):
@@ -412,3 +408,7 @@ class TestFusedTrainingStep(unittest.TestCase):
         gsrc = torch.full((1000,), float(R + 1), dtype=torch.float32, device=DEVICE)
         torch.ops.mpi4torch_b200.allreduce_axpy_(p, gsrc, -0.5)
         self.assertTrue(bool((p == 2.0 - 0.5 * P * (P + 1) / 2).all()))
+
+
+if __name__ == "__main__":
+    unittest.main()
