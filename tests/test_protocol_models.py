@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 BMC, BM2, BN = 128, 256, 256          # rows per CTA, rows / cols per cluster tile
-K_COMM_WARPS, K_U, K_ROW_SPLIT = 8, 4, 4
+K_COMM_WARPS, K_U, K_ROW_SPLIT = 8, 4, 2
 K_ROWS = BMC // K_ROW_SPLIT
 SIGNALS_PER_UNIT = 8                  # 4 epilogue warps x 2 CTAs
 
