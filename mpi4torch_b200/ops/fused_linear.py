@@ -219,4 +219,5 @@ def dp_linear_mse(x: torch.Tensor, weight: torch.Tensor, target: torch.Tensor, c
     if optimizer is not None:
         raise RuntimeError("mpi4torch_b200: InBackwardSGD is only available on the fused CUDA path")
     y = allreduce_linear(x, weight, c, force_unfused=not allow_fused)
-    return ((y.float() - target.float()).square().sum() * loss_scale).reshape(1)
+    acc = torch.float64 if y.dtype == torch.float64 else torch.float32  # accumulate in fp32 (fp64 inputs stay fp64)
+    return ((y.to(acc) - target.to(acc)).square().sum() * loss_scale).reshape(1)

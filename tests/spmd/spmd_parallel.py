@@ -282,5 +282,50 @@ class TestFunctionalOps(unittest.TestCase):
         self.assertTrue(torch.allclose(w.grad, expect_gw.expand(5, 4), rtol=1e-12, atol=1e-12))
 
 
+@unittest.skipUnless(DEVICE.type == "cpu", "composition path: exercised on the CPU backend (the fused path has its own GPU tests)")
+class TestDPLinearAutogradNode(unittest.TestCase):
+    """ops.dp_linear_mse / DPLinearModel on tensors the fused kernels do not take (CPU, fp32): the composition path
+    must give the same loss and the same all-reduced gradient as the hand-written data-parallel pattern of the
+    reference (examples/simple_linear_regression.py:27-35)."""
+
+    def test_loss_and_gradient_match_the_manual_pattern(self):
+        from mpi4torch_b200.ops import InBackwardSGD, dp_linear_mse
+
+        g = torch.Generator().manual_seed(11)
+        w0 = torch.randn(6, 5, generator=g, dtype=torch.double)
+        gr = torch.Generator().manual_seed(100 + comm.rank)
+        x = torch.randn(7, 5, generator=gr, dtype=torch.double).to(DEVICE)
+        t = torch.randn(7, 6, generator=gr, dtype=torch.double).to(DEVICE)
+        w = w0.clone().to(DEVICE).requires_grad_()
+        local = dp_linear_mse(x, w, t, comm, loss_scale=1.0 / (7 * comm.size))
+        self.assertEqual(tuple(local.shape), (1,))
+        loss = comm.Allreduce(local, m4t.MPI_SUM)
+        loss.backward()
+        w2 = w0.clone().to(DEVICE).requires_grad_()
+        w_avg = comm.Allreduce(w2, m4t.MPI_SUM) / comm.size
+        manual = comm.Allreduce(((x @ w_avg.t() - t) ** 2).sum() / (7 * comm.size), m4t.MPI_SUM)
+        manual.backward()
+        self.assertTrue(torch.allclose(loss.detach().reshape(()), manual.detach()))
+        self.assertTrue(torch.allclose(w.grad, w2.grad))
+        # gradients are identical on every rank (the adjoint Allreduce ran)
+        self.assertTrue(torch.equal(w.grad, comm.Bcast_(w.grad.clone(), 0)))
+        # the in-backward optimizer is a fused-kernel feature: asking for it elsewhere is an error, not a silent fallback
+        if DEVICE.type == "cpu":
+            with self.assertRaises(RuntimeError):
+                dp_linear_mse(x, w, t, comm, loss_scale=1.0, optimizer=InBackwardSGD(0.1))
+
+    def test_model_train_step_on_cpu_applies_plain_sgd(self):
+        from mpi4torch_b200.models import DPLinearModel
+
+        model = DPLinearModel(8, 4, comm, device=DEVICE, dtype=torch.float32, lr=0.05, seed=2)
+        g = torch.Generator().manual_seed(5 + comm.rank)
+        x = torch.randn(16, 8, generator=g).to(DEVICE)
+        t = torch.randn(16, 4, generator=g).to(DEVICE)
+        losses = [float(model.train_step(x, t)) for _ in range(5)]
+        self.assertLess(losses[-1], losses[0])
+        self.assertIsNone(model.weight.grad)
+        self.assertTrue(torch.equal(model.weight.detach(), comm.Bcast_(model.weight.detach().clone(), 0)))
+
+
 if __name__ == "__main__":
     unittest.main()
