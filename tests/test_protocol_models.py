@@ -230,3 +230,116 @@ def test_p2p_slot_ring_protocol_never_overwrites_unread_data(nslots, send_blocks
             tail[s] = c + 1
             b.pop(0)
     assert sorted(received) == list(range(sum(messages)))
+
+
+def _ce_groups(nslots, slot_bytes, nbytes, first_chunk):
+    """for_each_group of csrc/kernels/p2p.cu (copy-engine path): groups of consecutive chunks that neither wrap the
+    ring nor exceed half of it nor 32 slots.  Returns (cidx0, s0, g, off, length) tuples."""
+    nchunks = 1 if nbytes <= 0 else (nbytes + slot_bytes - 1) // slot_bytes
+    gmax = max(1, min(nslots // 2, 32))
+    out, k0 = [], 0
+    while k0 < nchunks:
+        cidx0 = first_chunk + k0
+        s0 = cidx0 % nslots
+        g = min(gmax, nchunks - k0, nslots - s0)
+        off = k0 * slot_bytes
+        out.append((cidx0, s0, g, off, max(0, min(g * slot_bytes, nbytes - off))))
+        k0 += g
+    return out
+
+
+@pytest.mark.parametrize("nslots", [2, 16, 64])
+@pytest.mark.parametrize("messages", [[5], [1, 70, 3], [64, 64, 1, 129], [0, 7, 0, 33]])
+def test_p2p_copy_engine_groups_and_flags(nslots, messages):
+    """Copy-engine p2p path: the sender's DMA fills a group of slots after waiting for their tail flags, then posts the
+    head flags; the receiver's DMA drains the group after waiting for the head flags, then posts the tail flags.
+    Kernel-path and copy-engine messages may alternate on one ring because both use the same chunk numbering.
+    Random interleaving of the two stream-ordered sides: nothing is overwritten unread, every byte range arrives
+    once, groups never wrap the ring."""
+    import random
+
+    slot = 4  # bytes per slot in the model
+    rng = random.Random(nslots * 7 + len(messages))
+    head, tail = [0] * nslots, [0] * nslots
+    content = [None] * nslots  # (message, chunk) held by a slot
+    first = 0
+    send_ops, recv_ops = [], []  # stream-ordered operation lists per side
+    for m, nchunks_or_bytes in enumerate(messages):
+        nbytes = nchunks_or_bytes * slot - (1 if nchunks_or_bytes > 1 else 0)  # ragged last chunk
+        nbytes = max(nbytes, 0)
+        groups = _ce_groups(nslots, slot, nbytes, first)
+        covered = 0
+        for cidx0, s0, g, off, length in groups:
+            assert s0 + g <= nslots and 1 <= g <= max(1, min(nslots // 2, 32))
+            assert off == covered
+            covered += length
+            send_ops.append((m, cidx0, s0, g))
+            recv_ops.append((m, cidx0, s0, g))
+        assert covered == nbytes
+        first += 1 if nbytes <= 0 else (nbytes + slot - 1) // slot
+    received = []
+    si = ri = steps = 0
+    while si < len(send_ops) or ri < len(recv_ops):
+        steps += 1
+        assert steps < 100000, "copy-engine protocol model deadlocked"
+        if rng.random() < 0.5 and si < len(send_ops):
+            m, cidx0, s0, g = send_ops[si]
+            # p2p_flag_wait_kernel on the tail flags: slot free once chunk (c - nslots) was consumed
+            if any(cidx0 + i >= nslots and tail[s0 + i] < cidx0 + i - nslots + 1 for i in range(g)):
+                continue
+            for i in range(g):
+                assert content[s0 + i] is None or content[s0 + i] in received, "slot overwritten before it was read"
+                content[s0 + i] = (m, cidx0 + i)
+            for i in range(g):
+                head[s0 + i] = cidx0 + i + 1  # p2p_flag_post_kernel after the DMA (stream order)
+            si += 1
+        elif ri < len(recv_ops):
+            m, cidx0, s0, g = recv_ops[ri]
+            if any(head[s0 + i] < cidx0 + i + 1 for i in range(g)):
+                continue
+            for i in range(g):
+                assert content[s0 + i] == (m, cidx0 + i)
+                received.append((m, cidx0 + i))
+            for i in range(g):
+                tail[s0 + i] = cidx0 + i + 1
+            ri += 1
+    assert len(received) == len(set(received)) == first
+
+
+def test_push_epilogue_box_coordinates_cover_the_staging_area_once():
+    """Peer-store mode of the fused backward (2-3 ranks): every epilogue warp of every work unit TMA-stores four
+    {64 columns x 32 rows} boxes into the owner's staging area for this source rank, laid out as [ksplit * N rows,
+    K columns].  Mirror of the coordinates in wgrad_bf16_nt_2cta_kernel: each element of part h of tile t is written
+    exactly once and only for the parts the schedule produces."""
+    N, K, ksplit, num_clusters = 1024, 512, 2, 3
+    n_tiles, k_tiles = N // BM2, K // BN
+    num_tiles = n_tiles * k_tiles
+    sched = make_sched(num_tiles, num_clusters, ksplit)
+    area = np.zeros((ksplit * N, K), dtype=np.int8)
+    for u in range(sched[2]):
+        t, h, parts = unit_to_tile(sched, u)
+        n_blk, k_blk = divmod(t, k_tiles)
+        for cta, q in itertools.product(range(2), range(4)):
+            row0 = h * N + n_blk * BM2 + cta * BMC + q * 32
+            for c2 in range(BN // 64):
+                col0 = k_blk * BN + c2 * 64
+                area[row0:row0 + 32, col0:col0 + 64] += 1
+    for t in range(num_tiles):
+        n_blk, k_blk = divmod(t, k_tiles)
+        parts = 1 if t < sched[0] else sched[1]
+        for h in range(ksplit):
+            blk = area[h * N + n_blk * BM2:h * N + (n_blk + 1) * BM2, k_blk * BN:(k_blk + 1) * BN]
+            assert (blk == (1 if h < parts else 0)).all(), (t, h)
+
+
+def test_swizzled_epilogue_box_is_bank_conflict_free_and_matches_tma_swizzle():
+    """The epilogue writes row r's 16-byte chunk j of a {32 rows x 128 bytes} box at r*128 + ((j ^ (r & 7)) << 4):
+    that is exactly TMA's SWIZZLE_128B (Swizzle<3,4,3> of the byte offset), and for a fixed j the 32 lanes of a warp
+    spread over all 8 sixteen-byte bank groups (4 lanes each = the minimum of 4 wavefronts for 512 bytes)."""
+    for j in range(8):
+        groups = {}
+        for r in range(32):
+            addr = r * 128 + ((j ^ (r & 7)) << 4)
+            assert addr == _swizzle128(r * 128 + j * 16)
+            groups.setdefault((addr % 128) // 16, []).append(r)
+        assert len(groups) == 8 and all(len(v) == 4 for v in groups.values())
