@@ -240,7 +240,7 @@ bool wgrad_allreduce_sgd_supported(const Tensor& w, const Tensor& dy, const Tens
 }
 
 // w += scale * sum_ranks(dy^T @ x): backward GEMM, gradient all-reduce and SGD step in one kernel.
-// Collective; `w` must be a replicated symmetric_empty() tensor.  Experimental (M4T_FUSED_WGRAD=1).
+// Collective; `w` must be a replicated symmetric_empty() tensor (M4T_FUSED_WGRAD=0 disables the kernel).
 void wgrad_allreduce_sgd_(Tensor w, const Tensor& dy, const Tensor& x, double scale,
                           const c10::optional<Tensor>& grad_scale) {
   TORCH_CHECK(wgrad_allreduce_sgd_supported(w, dy, x), "mpi4torch_b200: fused wgrad->Allreduce->SGD does not support these tensors");

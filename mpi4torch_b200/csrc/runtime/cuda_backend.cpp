@@ -423,7 +423,7 @@ const void* CudaBackend::fused_wgrad_update(void* w, const void* dy, const void*
                                             bool prefetch_avg, const float* gscale) {
   check_device_error();
   M4T_CHECK(fused_wgrad_available(w, Mb, N, K), "fused wgrad->Allreduce->SGD unavailable for N=" << N << " K=" << K
-                                                    << " (needs NVLS, M4T_FUSED_WGRAD=1 and a symmetric weight)");
+                                                    << " (needs a weight from symmetric_empty(), N % 256 == K % 256 == batch % 128 == 0, M4T_FUSED_WGRAD != 0)");
   M4T_CUDA(cudaSetDevice(device_));
   const int64_t key = (N << 32) | K;
   auto it = wgrad_.find(key);
