@@ -327,5 +327,39 @@ class TestDPLinearAutogradNode(unittest.TestCase):
         self.assertTrue(torch.equal(model.weight.detach(), comm.Bcast_(model.weight.detach().clone(), 0)))
 
 
+@unittest.skipUnless(DEVICE.type == "cpu", "added after the last GPU session of the round: exercised on the CPU backend")
+class TestShardedOptimizer(unittest.TestCase):
+    def test_sharded_sgd_matches_replicated_sgd_with_momentum(self):
+        """ShardedSGD (Reduce_scatterFused -> local shard update -> Allgather) against torch.optim.SGD on
+        all-reduced gradients, parameter count not divisible by the world size."""
+        from mpi4torch_b200.parallel import ShardedSGD
+
+        torch.manual_seed(3)
+        ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3)).to(DEVICE).double()
+        mod = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3)).to(DEVICE).double()
+        mod.load_state_dict(ref.state_dict())
+        opt_ref = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+        opt = ShardedSGD(mod.parameters(), lr=0.1, momentum=0.9, comm=comm)
+        g = torch.Generator().manual_seed(40 + comm.rank)
+        for _ in range(4):
+            x = torch.randn(6, 7, generator=g, dtype=torch.double).to(DEVICE)
+            y = torch.randn(6, 3, generator=g, dtype=torch.double).to(DEVICE)
+            opt_ref.zero_grad()
+            ((ref(x) - y) ** 2).mean().backward()
+            for p in ref.parameters():  # replicated optimizer: average the gradients, every rank steps everything
+                p.grad = comm.Allreduce(p.grad, m4t.MPI_SUM) / comm.size
+            opt_ref.step()
+            opt.zero_grad()
+            ((mod(x) - y) ** 2).mean().backward()
+            opt.step()
+            for a, b in zip(mod.parameters(), ref.parameters()):
+                self.assertTrue(torch.allclose(a, b, rtol=1e-12, atol=1e-12))
+        if comm.size > 1:
+            full = sum(p.numel() for p in mod.parameters()) * 8
+            self.assertLess(opt.state_bytes_per_rank(), full)
+        for p in mod.parameters():  # replicas stay identical
+            self.assertTrue(torch.equal(p.detach(), comm.Bcast_(p.detach().clone(), 0)))
+
+
 if __name__ == "__main__":
     unittest.main()
