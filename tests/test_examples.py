@@ -45,3 +45,11 @@ def test_pipeline_example_trains_across_three_stages_cpu():
     losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
     assert len(losses) >= 3 and losses[-1] < 0.6 * losses[0], losses
     assert "(3 stages, 4 micro-batches)" in res.stdout
+
+
+def test_sharded_optimizer_example_cpu():
+    res = run_spmd(3, ["examples/sharded_optimizer.py", "--device", "cpu", "--steps", "30"], device="cpu", timeout=300)
+    assert res.returncode == 0, res.stderr[-4000:]
+    losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
+    assert len(losses) >= 3 and losses[-1] < 0.5 * losses[0], losses
+    assert "optimizer state per rank" in res.stdout
