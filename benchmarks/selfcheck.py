@@ -104,15 +104,17 @@ def run_checks(comm, dev) -> Dict[str, object]:
     for _ in range(3):
         xb = torch.randn(512, 512, generator=g).to(torch.bfloat16).to(dev)
         tb = torch.randn(512, 512, generator=g).to(torch.bfloat16).to(dev)
-        w32 = model.weight.detach().float().requires_grad_()
+        # the fp32 reference composition runs on the HOST (CPU matmul + this library's shared-memory Allreduce), so
+        # that no library GEMM is launched on the GPU by the benchmark process
+        w32 = model.weight.detach().float().cpu().requires_grad_()
         w_avg = comm.Allreduce(w32, m4t.MPI_SUM) / P
-        yy = xb.float() @ w_avg.to(torch.bfloat16).float().t()
-        ref_loss = comm.Allreduce(((yy - tb.float()).square().sum() / (512 * P)).reshape(1), m4t.MPI_SUM)
+        yy = xb.float().cpu() @ w_avg.to(torch.bfloat16).float().t()
+        ref_loss = comm.Allreduce(((yy - tb.float().cpu()).square().sum() / (512 * P)).reshape(1), m4t.MPI_SUM)
         ref_loss.backward()
         ref_w = w32.detach() - 1e-2 * w32.grad
         got = float(model.train_step(xb, tb))
         ok = ok and abs(got - float(ref_loss.detach())) <= 1e-2 * abs(float(ref_loss.detach()))
-        ok = ok and float((model.weight.detach().float() - ref_w).abs().max()) <= 2e-2
+        ok = ok and float((model.weight.detach().float().cpu() - ref_w).abs().max()) <= 2e-2
         ok = ok and torch.equal(model.weight.detach(), comm.Bcast_(model.weight.detach().clone(), 0))
     res["dp_step_identical"] = _all_true(comm, ok)
 
