@@ -260,6 +260,31 @@ class TestErrorsAndMisc(unittest.TestCase):
         comm.Barrier()
         self.assertIn("rank", comm.describe())
 
+    def test_comm_from_mpi4py_with_the_bundled_mpi4py_sliver(self):
+        """A real (if minimal) mpi4py communicator: baseline/mpi_shim/python/mpi4py over the shared-memory MPI shim,
+        wired by the same RANK / WORLD_SIZE / MASTER_PORT variables the launcher exports (the reference's
+        tests/test_mpi4pyinterop.py, which also passes against the reference under this shim)."""
+        import os
+        import sys
+
+        root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        shim = os.path.join(root, "baseline", "mpi_shim")
+        if not os.path.exists(os.path.join(shim, "lib", "libmpi.so")) or "MASTER_PORT" not in os.environ:
+            self.skipTest("baseline/mpi_shim is not built (make -C baseline/mpi_shim)")
+        sys.path.insert(0, os.path.join(shim, "python"))
+        try:
+            import mpi4py.MPI as MPI
+        finally:
+            sys.path.pop(0)
+        self.assertEqual((MPI.COMM_WORLD.Get_rank(), MPI.COMM_WORLD.Get_size()), (R, P))
+        c = m4t.comm_from_mpi4py(MPI.COMM_WORLD)
+        self.assertTrue(c.is_world)
+        self.assertEqual((c.rank, c.size), (MPI.COMM_WORLD.rank, MPI.COMM_WORLD.size))
+        tmp = rand(10, requires_grad=True)
+        c.Allreduce(tmp, m4t.MPI_SUM).sum().backward()
+        self.assertTrue(torch.equal(tmp.grad, P * torch.ones_like(tmp)))
+        self.assertEqual(MPI.COMM_WORLD.allgather(R), list(range(P)))
+
     def test_mpi4py_shim(self):
         class FakeComm:
             def Get_size(self):

@@ -53,15 +53,16 @@ def _need_reference():
 
 
 def test_reference_test_suite_passes_under_the_shim(shim):
-    """The reference's own unittest files, unmodified, np = 2 (mpi4py interop cannot be imported: no mpi4py)."""
+    """The reference's own unittest files, unmodified, np = 2."""
     _need_reference()
     tests = Path(os.environ.get("M4T_REFERENCE_SRC", "/root/reference")) / "tests"
     if not tests.exists():
         pytest.skip("reference test files are not available")
-    res = _run([MPIRUN, "-np", 2, sys.executable, "-m", "unittest", "discover", "-s", tests, "-p", "test_[cjn]*.py"],
-               timeout=900, env={"PYTHONPATH": str(ROOT / "baseline" / "_ref")})
+    # all four files, including tests/test_mpi4pyinterop.py: `mpi4py` resolves to the sliver in baseline/mpi_shim/python
+    res = _run([MPIRUN, "-np", 2, sys.executable, "-m", "unittest", "discover", "-s", tests, "-p", "test_*.py"],
+               timeout=900, env={"PYTHONPATH": str(ROOT / "baseline" / "_ref") + os.pathsep + str(SHIM / "python")})
     assert res.returncode == 0, res.stderr[-4000:]
-    assert "OK" in res.stderr
+    assert "Ran 23 tests" in res.stderr and "OK" in res.stderr
 
 
 CROSS = r'''
