@@ -123,3 +123,13 @@ def test_single_rank_split_and_free():
         assert "freed" in str(exc)
     else:
         raise AssertionError("a freed communicator must raise")
+
+
+def test_numa_helpers_parse_sysfs_lists():
+    from mpi4torch_b200.utils import affinity
+
+    assert affinity._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity._parse_cpulist("") == set()
+    # on a single-node box there is nothing to prefer; on a multi-node box the node of CPU 0 contains CPU 0
+    node = affinity._numa_node_of({0})
+    assert node is None or isinstance(node, int)
