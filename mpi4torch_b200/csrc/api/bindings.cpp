@@ -129,6 +129,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     else if (key == "wgrad_debug") set_wgrad_debug(static_cast<int>(value));
     else TORCH_CHECK(false, "unknown tuning key ", key);
   });
+  m.def("slab_chunked_calls", [] { return slab_chunked_calls(); },
+        "Gather / Allgather / Reduce_scatter calls moved in pieces (share larger than a staging half).");
   m.def("kernel_launch_table", [] {
     py::dict d;
     for (const auto& kv : kernel_launch_table()) d[py::str(kv.first)] = static_cast<int64_t>(kv.second);

@@ -7,6 +7,8 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
+#include <atomic>
+#include <limits>
 #include <numeric>
 
 #include "../runtime/cuda_backend.h"
@@ -99,9 +101,24 @@ int64_t wrap_axis(int64_t axis, int64_t ndim, const char* what) {
   return axis < 0 ? axis + ndim : axis;
 }
 
+// Largest per-rank staged payload one slab collective may move at once: the CUDA backend's staging half (every
+// rank's share of a pull / reduce-scatter is staged there), unlimited on the shared-memory backend.
+// M4T_SLAB_CHUNK_BYTES (read once) lowers it on any backend - used by the tests to drive the chunked paths.
+std::atomic<int64_t> g_slab_chunked_calls{0};  // how often a slab collective had to be moved in pieces (introspection)
+
+int64_t slab_limit_bytes(const Route& r, CommContext& cx) {
+  static const int64_t forced = env_i64("M4T_SLAB_CHUNK_BYTES", 0);
+  int64_t limit = std::numeric_limits<int64_t>::max();
+  if (!r.staged && r.be != &cx.cpu() && cx.cuda_ready()) limit = cx.cuda()->half_bytes();
+  if (forced > 0) limit = std::min(limit, forced);
+  return limit;
+}
+
 uint32_t ptr_hash(const void* p) { return static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 0xffffffffu); }
 
 }  // namespace
+
+int64_t slab_chunked_calls() { return g_slab_chunked_calls.load(std::memory_order_relaxed); }
 
 Communicator::Communicator() : world_(&World::instance()) {
   ctx_ = world_->ctx().get();
@@ -293,11 +310,48 @@ Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root
                 " has different non-gather dimensions than rank ", rank_);
   }
   const int rroot = all ? 0 : static_cast<int>(root);
-  PullPlan plan = plan_gather(static_cast<int>(rank_), static_cast<int>(size_), rroot, a3.before, a3.after, lens, all);
   auto out_shape = shape;
   const bool i_receive = all || rank_ == root;
   // off-root the result has extent 0 along the gather axis (reference :538-554)
-  out_shape[axis] = i_receive ? std::accumulate(lens.begin(), lens.end(), int64_t{0}) : 0;
+  const int64_t total_len = std::accumulate(lens.begin(), lens.end(), int64_t{0});
+  out_shape[axis] = i_receive ? total_len : 0;
+  // A rank's share larger than one staging half is moved in pieces (every rank sees the same lengths and the same
+  // limit, so all ranks take the same decision): along `before` when whole rows fit, else along the gather axis.
+  const int64_t es = static_cast<int64_t>(in.element_size());
+  const int64_t max_len = *std::max_element(lens.begin(), lens.end());
+  const int64_t limit = slab_limit_bytes(r, cx());
+  if (a3.before * max_len * a3.after * es > limit && max_len > 0 && a3.after * es <= limit) {
+    g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+    Tensor in3 = in.view({a3.before, a3.axis, a3.after});
+    Tensor out = at::empty(out_shape, in.options());
+    Tensor out3 = out.view({a3.before, i_receive ? total_len : 0, a3.after});
+    const int64_t row_bytes = max_len * a3.after * es;  // one `before` row of the largest contributor
+    if (a3.before > 1) {
+      const int64_t nb = std::max<int64_t>(1, limit / std::max<int64_t>(row_bytes, 1));
+      for (int64_t b0 = 0; b0 < a3.before; b0 += nb) {
+        const int64_t n = std::min(nb, a3.before - b0);
+        Tensor part = raw_gather(in3.narrow(0, b0, n), 1, root, all);  // recurses into the axis split if one row is too big
+        if (i_receive) out3.narrow(0, b0, n).copy_(part);
+      }
+    } else {
+      const int64_t nc = (row_bytes + limit - 1) / limit;
+      std::vector<int64_t> displ(static_cast<size_t>(size_), 0);
+      for (int64_t p = 1; p < size_; ++p) displ[p] = displ[p - 1] + lens[p - 1];
+      for (int64_t k = 0; k < nc; ++k) {
+        const int64_t r0 = a3.axis * k / nc, r1 = a3.axis * (k + 1) / nc;
+        Tensor part = raw_gather(in3.narrow(1, r0, r1 - r0), 1, root, all);
+        if (!i_receive) continue;
+        int64_t toff = 0;
+        for (int64_t p = 0; p < size_; ++p) {  // piece k of rank p goes to its place inside rank p's block
+          const int64_t p0 = lens[p] * k / nc, p1 = lens[p] * (k + 1) / nc;
+          if (p1 > p0) out3.narrow(1, displ[p] + p0, p1 - p0).copy_(part.narrow(1, toff, p1 - p0));
+          toff += p1 - p0;
+        }
+      }
+    }
+    return r.from_comm(out);
+  }
+  PullPlan plan = plan_gather(static_cast<int>(rank_), static_cast<int>(size_), rroot, a3.before, a3.after, lens, all);
   Tensor out = at::empty(out_shape, in.options());
   r.be->pull(plan, in.data_ptr(), out.data_ptr(), dt, r.stream);
   return r.from_comm(out);
@@ -412,9 +466,57 @@ Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_
   if (total != a3.axis)
     throw std::invalid_argument("mpi4torch_b200: Reduce_scatter: sum of numelem (" + std::to_string(total) +
                                 ") does not match the scatter axis length (" + std::to_string(a3.axis) + ")");
-  ReducePlan plan = plan_reduce_scatter(static_cast<int>(rank_), static_cast<int>(size_), a3.before, a3.after, counts);
   auto out_shape = shape;
   out_shape[axis] = numelem;
+  {
+    // the whole input of every rank is staged: larger than a staging half -> pieces along `before`, else along the
+    // scatter axis (piece k of every destination's block, gathered into a temporary); same decision on all ranks
+    const int64_t es = static_cast<int64_t>(in.element_size());
+    const int64_t limit = slab_limit_bytes(r, cx());
+    const int64_t in_bytes = in.numel() * es;
+    if (in_bytes > limit && in.numel() > 0 && static_cast<int64_t>(size_) * a3.after * es <= limit) {
+      g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+      Tensor in3 = in.view({a3.before, a3.axis, a3.after});
+      Tensor out = at::empty(out_shape, in.options());
+      Tensor out3 = out.view({a3.before, numelem, a3.after});
+      Tensor acc3;
+      const bool has_acc = accumulate.has_value() && accumulate->defined();
+      if (has_acc) {
+        TORCH_CHECK(accumulate->sizes().vec() == out_shape && accumulate->scalar_type() == input.scalar_type() &&
+                        accumulate->device() == input.device(),
+                    "mpi4torch_b200: Reduce_scatter: the accumulate tensor must have the result's shape, dtype and device");
+        acc3 = r.to_comm(*accumulate).view({a3.before, numelem, a3.after});
+      }
+      auto acc_of = [&](const Tensor& piece) { return has_acc ? c10::optional<Tensor>(piece) : c10::optional<Tensor>(); };
+      const int64_t row_bytes = a3.axis * a3.after * es;
+      if (a3.before > 1) {
+        const int64_t nb = std::max<int64_t>(1, limit / std::max<int64_t>(row_bytes, 1));
+        for (int64_t b0 = 0; b0 < a3.before; b0 += nb) {
+          const int64_t n = std::min(nb, a3.before - b0);
+          Tensor part = raw_reduce_scatter(in3.narrow(0, b0, n), op_, 1, numelem, scale, has_scale,
+                                           acc_of(has_acc ? acc3.narrow(0, b0, n) : Tensor()));
+          out3.narrow(0, b0, n).copy_(part);
+        }
+      } else {
+        const int64_t nc = (row_bytes + limit - 1) / limit;
+        std::vector<int64_t> displ(static_cast<size_t>(size_), 0);
+        for (int64_t p = 1; p < size_; ++p) displ[p] = displ[p - 1] + counts[p - 1];
+        for (int64_t k = 0; k < nc; ++k) {
+          std::vector<Tensor> pieces;
+          for (int64_t p = 0; p < size_; ++p) {
+            const int64_t p0 = counts[p] * k / nc, p1 = counts[p] * (k + 1) / nc;
+            pieces.push_back(in3.narrow(1, displ[p] + p0, p1 - p0));
+          }
+          const int64_t m0 = numelem * k / nc, m1 = numelem * (k + 1) / nc;
+          Tensor part = raw_reduce_scatter(at::cat(pieces, 1), op_, 1, m1 - m0, scale, has_scale,
+                                           acc_of(has_acc ? acc3.narrow(1, m0, m1 - m0) : Tensor()));
+          if (m1 > m0) out3.narrow(1, m0, m1 - m0).copy_(part);
+        }
+      }
+      return r.from_comm(out);
+    }
+  }
+  ReducePlan plan = plan_reduce_scatter(static_cast<int>(rank_), static_cast<int>(size_), a3.before, a3.after, counts);
   Tensor out = at::empty(out_shape, in.options());
   Epilogue epi;
   epi.scale = scale;

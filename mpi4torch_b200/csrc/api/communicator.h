@@ -103,4 +103,8 @@ Tensor JoinDummies(const Tensor& loopthrough, const std::vector<Tensor>& dummies
 
 c10::intrusive_ptr<Communicator> comm_world();
 
+// Number of Gather / Allgather / Reduce_scatter calls that were moved in pieces because one rank's share exceeded a
+// staging half (or M4T_SLAB_CHUNK_BYTES); for tests and logs.
+int64_t slab_chunked_calls();
+
 }  // namespace m4t

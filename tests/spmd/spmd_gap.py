@@ -260,6 +260,32 @@ class TestErrorsAndMisc(unittest.TestCase):
         comm.Barrier()
         self.assertIn("rank", comm.describe())
 
+    def test_oversized_slab_ops_are_moved_in_pieces(self):
+        """With M4T_SLAB_CHUNK_BYTES set (tests/test_cpu_spmd.py runs the suites once with 64 bytes) every Gather /
+        Allgather / Reduce_scatter larger than the limit takes the chunked path - along `before` or along the axis - and
+        must give the same result; without the variable nothing is chunked on the shared-memory backend."""
+        import os
+
+        before = m4t._C.slab_chunked_calls()
+        x = (torch.arange(2 * (R + 2) * 3, dtype=torch.double, device=DEVICE) + 1000.0 * R).reshape(2, R + 2, 3)
+        g = comm.Allgather(x, 1)
+        off = sum(p + 2 for p in range(R))
+        self.assertTrue(torch.equal(g[:, off:off + R + 2], x))
+        flat = torch.arange(float(7 * P), dtype=torch.double, device=DEVICE) * (R + 1)   # before == 1: axis split
+        rs = comm.Reduce_scatter(flat, m4t.MPI_SUM, 0, 7)
+        want = torch.arange(7.0 * R, 7.0 * (R + 1), dtype=torch.double, device=DEVICE) * (P * (P + 1) / 2)
+        self.assertTrue(torch.equal(rs, want))
+        ga = comm.Gather(flat, 0, P - 1)
+        if R == P - 1:
+            self.assertTrue(torch.equal(ga[7 * P * R:], flat))
+        else:
+            self.assertEqual(ga.numel(), 0)
+        forced = int(os.environ.get("M4T_SLAB_CHUNK_BYTES", "0"))
+        if 0 < forced <= 64 and P > 1:
+            self.assertGreater(m4t._C.slab_chunked_calls(), before)
+        elif forced == 0 and DEVICE.type == "cpu":
+            self.assertEqual(m4t._C.slab_chunked_calls(), before)
+
     def test_comm_from_mpi4py_with_the_bundled_mpi4py_sliver(self):
         """A real (if minimal) mpi4py communicator: baseline/mpi_shim/python/mpi4py over the shared-memory MPI shim,
         wired by the same RANK / WORLD_SIZE / MASTER_PORT variables the launcher exports (the reference's
