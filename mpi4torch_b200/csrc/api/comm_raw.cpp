@@ -391,10 +391,51 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
     throw std::invalid_argument("mpi4torch_b200: Scatter: sum of numelem (" + std::to_string(total) +
                                 ") does not match the root tensor's axis length (" + std::to_string(rshape[axis]) + ")");
   const Axis3 a3 = split_axis(rshape, axis);
-  PullPlan plan = plan_scatter(static_cast<int>(rank_), static_cast<int>(size_), static_cast<int>(root), a3.before,
-                               a3.after, counts);
   auto out_shape = rshape;
   out_shape[axis] = numelem;
+  {
+    // root's whole tensor is staged: beyond a staging half it is moved in pieces - along `before` when whole rows fit,
+    // else piece k of every destination's block (root concatenates them); off-root tensors stay placeholders
+    const int64_t es = static_cast<int64_t>(in.element_size());
+    const int64_t limit = slab_limit_bytes(r, cx());
+    const int64_t row_bytes = a3.axis * a3.after * es;
+    if (a3.before * row_bytes > limit && row_bytes > 0 && static_cast<int64_t>(size_) * a3.after * es <= limit) {
+      g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+      const bool i_am_root = rank_ == root;
+      Tensor in3 = i_am_root ? in.view({a3.before, a3.axis, a3.after}) : in;
+      Tensor out = at::empty(out_shape, in.options());
+      Tensor out3 = out.view({a3.before, numelem, a3.after});
+      if (a3.before > 1) {
+        const int64_t nb = std::max<int64_t>(1, limit / row_bytes);
+        for (int64_t b0 = 0; b0 < a3.before; b0 += nb) {
+          const int64_t n = std::min(nb, a3.before - b0);
+          Tensor part = raw_scatter(i_am_root ? in3.narrow(0, b0, n) : in, 1, numelem, root);
+          out3.narrow(0, b0, n).copy_(part.view({n, numelem, a3.after}));
+        }
+      } else {
+        const int64_t nc = (row_bytes + limit - 1) / limit;
+        std::vector<int64_t> displ(static_cast<size_t>(size_), 0);
+        for (int64_t p = 1; p < size_; ++p) displ[p] = displ[p - 1] + counts[p - 1];
+        for (int64_t k = 0; k < nc; ++k) {
+          Tensor sub = in;
+          if (i_am_root) {
+            std::vector<Tensor> pieces;
+            for (int64_t p = 0; p < size_; ++p) {
+              const int64_t p0 = counts[p] * k / nc, p1 = counts[p] * (k + 1) / nc;
+              pieces.push_back(in3.narrow(1, displ[p] + p0, p1 - p0));
+            }
+            sub = at::cat(pieces, 1);
+          }
+          const int64_t m0 = numelem * k / nc, m1 = numelem * (k + 1) / nc;
+          Tensor part = raw_scatter(sub, 1, m1 - m0, root);
+          if (m1 > m0) out3.narrow(1, m0, m1 - m0).copy_(part.view({1, m1 - m0, a3.after}));
+        }
+      }
+      return r.from_comm(out);
+    }
+  }
+  PullPlan plan = plan_scatter(static_cast<int>(rank_), static_cast<int>(size_), static_cast<int>(root), a3.before,
+                               a3.after, counts);
   Tensor out = at::empty(out_shape, in.options());
   r.be->pull(plan, in.data_ptr(), out.data_ptr(), dt, r.stream);
   return r.from_comm(out);
@@ -430,9 +471,37 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
     if (total != shape[saxis])
       throw std::invalid_argument("mpi4torch_b200: Alltoall: sum of numelem (" + std::to_string(total) +
                                   ") does not match the scatter axis length (" + std::to_string(shape[saxis]) + ")");
-    plan = plan_alltoall(static_cast<int>(rank_), static_cast<int>(size_), shape, gaxis, saxis, glen, counts);
     out_shape[gaxis] = std::accumulate(glen.begin(), glen.end(), int64_t{0});
     out_shape[saxis] = numelem;
+    {
+      // every rank's whole input is staged: beyond a staging half, rows [k/nc, (k+1)/nc) of every rank's gather axis
+      // are exchanged per piece and land at their place inside that rank's block of the result
+      const int64_t es = static_cast<int64_t>(in.element_size());
+      const int64_t limit = slab_limit_bytes(r, cx());
+      int64_t rest = es;  // bytes of one gather-axis row
+      for (int64_t d = 0; d < nd; ++d)
+        if (d != gaxis) rest *= shape[d];
+      const int64_t max_len = *std::max_element(glen.begin(), glen.end());
+      if (max_len * rest > limit && rest > 0 && rest <= limit) {
+        g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+        const int64_t nc = (max_len * rest + limit - 1) / limit;
+        std::vector<int64_t> displ(static_cast<size_t>(size_), 0);
+        for (int64_t p = 1; p < size_; ++p) displ[p] = displ[p - 1] + glen[p - 1];
+        Tensor out = at::empty(out_shape, in.options());
+        for (int64_t k = 0; k < nc; ++k) {
+          const int64_t r0 = shape[gaxis] * k / nc, r1 = shape[gaxis] * (k + 1) / nc;
+          Tensor part = raw_alltoall(in.narrow(gaxis, r0, r1 - r0).contiguous(), gaxis, saxis, numelem);
+          int64_t toff = 0;
+          for (int64_t p = 0; p < size_; ++p) {
+            const int64_t p0 = glen[p] * k / nc, p1 = glen[p] * (k + 1) / nc;
+            if (p1 > p0) out.narrow(gaxis, displ[p] + p0, p1 - p0).copy_(part.narrow(gaxis, toff, p1 - p0));
+            toff += p1 - p0;
+          }
+        }
+        return r.from_comm(out);
+      }
+    }
+    plan = plan_alltoall(static_cast<int>(rank_), static_cast<int>(size_), shape, gaxis, saxis, glen, counts);
   }
   Tensor out = at::empty(out_shape, in.options());
   r.be->pull(plan, in.data_ptr(), out.data_ptr(), dt, r.stream);

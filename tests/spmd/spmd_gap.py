@@ -262,7 +262,7 @@ class TestErrorsAndMisc(unittest.TestCase):
 
     def test_oversized_slab_ops_are_moved_in_pieces(self):
         """With M4T_SLAB_CHUNK_BYTES set (tests/test_cpu_spmd.py runs the suites once with 64 bytes) every Gather /
-        Allgather / Reduce_scatter larger than the limit takes the chunked path - along `before` or along the axis - and
+        Allgather / Reduce_scatter / Scatter / Alltoall larger than the limit takes the chunked path - along `before` or along the axis - and
         must give the same result; without the variable nothing is chunked on the shared-memory backend."""
         import os
 
@@ -280,6 +280,36 @@ class TestErrorsAndMisc(unittest.TestCase):
             self.assertTrue(torch.equal(ga[7 * P * R:], flat))
         else:
             self.assertEqual(ga.numel(), 0)
+        # Scatter: uneven counts, `before` > 1 and before == 1; only root's tensor matters
+        counts = [p % 3 + 5 for p in range(P)]
+        src = torch.arange(float(2 * sum(counts) * 3), dtype=torch.double, device=DEVICE).reshape(2, sum(counts), 3)
+        sc = comm.Scatter(src if R == 0 else torch.zeros(1, dtype=torch.double, device=DEVICE), 1, counts[R], 0)
+        lo = sum(counts[:R])
+        self.assertTrue(torch.equal(sc, src[:, lo:lo + counts[R]]))
+        flat_src = torch.arange(float(sum(counts) * 4), dtype=torch.double, device=DEVICE).reshape(sum(counts), 4)
+        sc1 = comm.Scatter(flat_src if R == P - 1 else torch.zeros(1, dtype=torch.double, device=DEVICE), 0, counts[R], P - 1)
+        self.assertTrue(torch.equal(sc1, flat_src[lo:lo + counts[R]]))
+        # Alltoall with distinct axes: uneven gather lengths AND uneven scatter counts, with its gradient
+        xin = (torch.arange(float((R + 3) * sum(counts) * 2), dtype=torch.double, device=DEVICE) + 100.0 * R
+               ).reshape(R + 3, sum(counts), 2).requires_grad_()
+        a2a = comm.Alltoall(xin, 0, 1, counts[R])
+        self.assertEqual(tuple(a2a.shape), (sum(p + 3 for p in range(P)), counts[R], 2))
+        row = 0
+        for p in range(P):
+            want_p = (torch.arange(float((p + 3) * sum(counts) * 2), dtype=torch.double, device=DEVICE) + 100.0 * p
+                      ).reshape(p + 3, sum(counts), 2)[:, lo:lo + counts[R]]
+            self.assertTrue(torch.equal(a2a[row:row + p + 3].detach(), want_p))
+            row += p + 3
+        wgt = torch.arange(float(a2a.numel()), dtype=torch.double, device=DEVICE).reshape(a2a.shape) + R
+        (a2a * wgt).sum().backward()
+        # adjoint: my rows of every rank's weight block, concatenated along the scatter axis
+        col = 0
+        for p in range(P):
+            shape_p = (sum(q + 3 for q in range(P)), counts[p], 2)
+            wp = torch.arange(float(shape_p[0] * shape_p[1] * 2), dtype=torch.double, device=DEVICE).reshape(shape_p) + p
+            r0 = sum(q + 3 for q in range(R))
+            self.assertTrue(torch.equal(xin.grad[:, col:col + counts[p]], wp[r0:r0 + R + 3]))
+            col += counts[p]
         forced = int(os.environ.get("M4T_SLAB_CHUNK_BYTES", "0"))
         if 0 < forced <= 64 and P > 1:
             self.assertGreater(m4t._C.slab_chunked_calls(), before)
