@@ -114,6 +114,15 @@ int64_t slab_limit_bytes(const Route& r, CommContext& cx) {
   return limit;
 }
 
+// Suspends the AssumeUniformSizes promise for the pieces of a chunked call whose per-rank arguments differ
+// (window pieces of a re-partition, placeholder tensors off the Scatter root).
+struct UniformOff {
+  bool& flag;
+  bool saved;
+  explicit UniformOff(bool& f) : flag(f), saved(f) { flag = false; }
+  ~UniformOff() { flag = saved; }
+};
+
 uint32_t ptr_hash(const void* p) { return static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p) & 0xffffffffu); }
 
 }  // namespace
@@ -320,6 +329,20 @@ Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root
   const int64_t es = static_cast<int64_t>(in.element_size());
   const int64_t max_len = *std::max_element(lens.begin(), lens.end());
   const int64_t limit = slab_limit_bytes(r, cx());
+  if (a3.before * max_len * a3.after * es > limit && max_len > 0 && a3.after * es > limit && es <= limit) {
+    // not even one row of the trailing dimensions fits: split those first, the pieces recurse into the splits below
+    g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+    Tensor in3 = in.view({a3.before, a3.axis, a3.after});
+    Tensor out = at::empty(out_shape, in.options());
+    Tensor out3 = out.view({a3.before, i_receive ? total_len : 0, a3.after});
+    const int64_t na = limit / es;
+    for (int64_t c0 = 0; c0 < a3.after; c0 += na) {
+      const int64_t n = std::min(na, a3.after - c0);
+      Tensor part = raw_gather(in3.narrow(2, c0, n).contiguous(), 1, root, all);
+      if (i_receive) out3.narrow(2, c0, n).copy_(part);
+    }
+    return r.from_comm(out);
+  }
   if (a3.before * max_len * a3.after * es > limit && max_len > 0 && a3.after * es <= limit) {
     g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
     Tensor in3 = in.view({a3.before, a3.axis, a3.after});
@@ -399,8 +422,26 @@ Tensor Communicator::raw_scatter(const Tensor& input, int64_t axis_, int64_t num
     const int64_t es = static_cast<int64_t>(in.element_size());
     const int64_t limit = slab_limit_bytes(r, cx());
     const int64_t row_bytes = a3.axis * a3.after * es;
+    if (a3.before * row_bytes > limit && row_bytes > 0 && static_cast<int64_t>(size_) * a3.after * es > limit &&
+        static_cast<int64_t>(size_) * es <= limit) {
+      // one row per destination does not fit: split the trailing dimensions first
+      g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+      UniformOff uniform_off(uniform_);  // off-root tensors are placeholders for the pieces
+      const bool i_am_root = rank_ == root;
+      Tensor in3 = i_am_root ? in.view({a3.before, a3.axis, a3.after}) : in;
+      Tensor out = at::empty(out_shape, in.options());
+      Tensor out3 = out.view({a3.before, numelem, a3.after});
+      const int64_t na = limit / (es * static_cast<int64_t>(size_));
+      for (int64_t c0 = 0; c0 < a3.after; c0 += na) {
+        const int64_t n = std::min(na, a3.after - c0);
+        Tensor part = raw_scatter(i_am_root ? in3.narrow(2, c0, n).contiguous() : in, 1, numelem, root);
+        out3.narrow(2, c0, n).copy_(part.view({a3.before, numelem, n}));
+      }
+      return r.from_comm(out);
+    }
     if (a3.before * row_bytes > limit && row_bytes > 0 && static_cast<int64_t>(size_) * a3.after * es <= limit) {
       g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+      UniformOff uniform_off(uniform_);  // off-root tensors are placeholders for the pieces
       const bool i_am_root = rank_ == root;
       Tensor in3 = i_am_root ? in.view({a3.before, a3.axis, a3.after}) : in;
       Tensor out = at::empty(out_shape, in.options());
@@ -464,8 +505,40 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
   auto out_shape = shape;
   if (gaxis == saxis) {
     const Axis3 a3 = split_axis(shape, gaxis);
-    plan = plan_repartition(static_cast<int>(rank_), static_cast<int>(size_), a3.before, a3.after, glen, counts);
     out_shape[gaxis] = numelem;
+    {
+      // re-partition of one global axis: beyond a staging half the global rows are exchanged window by window - every
+      // rank contributes the rows it holds inside the window and asks for the rows it will own inside it
+      const int64_t es = static_cast<int64_t>(in.element_size());
+      const int64_t limit = slab_limit_bytes(r, cx());
+      const int64_t row_bytes = a3.before * a3.after * es;  // one global row across `before`
+      const int64_t max_len = *std::max_element(glen.begin(), glen.end());
+      const int64_t total_rows = std::accumulate(glen.begin(), glen.end(), int64_t{0});
+      const int64_t want_rows = std::accumulate(counts.begin(), counts.end(), int64_t{0});
+      if (max_len * row_bytes > limit && row_bytes > 0 && row_bytes <= limit && total_rows == want_rows) {
+        g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+        int64_t have0 = 0, own0 = 0;  // first global row I hold / I will own
+        for (int64_t p = 0; p < rank_; ++p) {
+          have0 += glen[p];
+          own0 += counts[p];
+        }
+        const int64_t window = std::max<int64_t>(1, limit / row_bytes);
+        Tensor out = at::empty(out_shape, in.options());
+        // the pieces are not uniform across ranks even when the whole call is: the promise is suspended for them
+        UniformOff uniform_off(uniform_);
+        for (int64_t w0 = 0; w0 < total_rows; w0 += window) {
+          const int64_t w1 = std::min(total_rows, w0 + window);
+          const int64_t hlo = std::max(w0, have0), hhi = std::min(w1, have0 + glen[rank_]);
+          const int64_t olo = std::max(w0, own0), ohi = std::min(w1, own0 + numelem);
+          const int64_t hn = std::max<int64_t>(0, hhi - hlo), on = std::max<int64_t>(0, ohi - olo);
+          Tensor sub = in.narrow(gaxis, hn > 0 ? hlo - have0 : 0, hn).contiguous();
+          Tensor part = raw_alltoall(sub, gaxis, saxis, on);
+          if (on > 0) out.narrow(gaxis, olo - own0, on).copy_(part);
+        }
+        return r.from_comm(out);
+      }
+    }
+    plan = plan_repartition(static_cast<int>(rank_), static_cast<int>(size_), a3.before, a3.after, glen, counts);
   } else {
     const int64_t total = std::accumulate(counts.begin(), counts.end(), int64_t{0});
     if (total != shape[saxis])
@@ -482,6 +555,26 @@ Tensor Communicator::raw_alltoall(const Tensor& input, int64_t gatheraxis_, int6
       for (int64_t d = 0; d < nd; ++d)
         if (d != gaxis) rest *= shape[d];
       const int64_t max_len = *std::max_element(glen.begin(), glen.end());
+      const int64_t per_dest = shape[saxis] > 0 ? rest / shape[saxis] * static_cast<int64_t>(size_) : 0;  // one scatter row per destination
+      if (max_len * rest > limit && rest > limit && per_dest > 0 && per_dest <= limit) {
+        // one gather-axis row does not fit: exchange piece k of every destination's block of the scatter axis
+        g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+        const int64_t nc = (rest + limit - 1) / limit;
+        std::vector<int64_t> sdispl(static_cast<size_t>(size_), 0);
+        for (int64_t p = 1; p < size_; ++p) sdispl[p] = sdispl[p - 1] + counts[p - 1];
+        Tensor out = at::empty(out_shape, in.options());
+        for (int64_t k = 0; k < nc; ++k) {
+          std::vector<Tensor> pieces;
+          for (int64_t p = 0; p < size_; ++p) {
+            const int64_t p0 = counts[p] * k / nc, p1 = counts[p] * (k + 1) / nc;
+            pieces.push_back(in.narrow(saxis, sdispl[p] + p0, p1 - p0));
+          }
+          const int64_t m0 = numelem * k / nc, m1 = numelem * (k + 1) / nc;
+          Tensor part = raw_alltoall(at::cat(pieces, saxis), gaxis, saxis, m1 - m0);
+          if (m1 > m0) out.narrow(saxis, m0, m1 - m0).copy_(part);
+        }
+        return r.from_comm(out);
+      }
       if (max_len * rest > limit && rest > 0 && rest <= limit) {
         g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
         const int64_t nc = (max_len * rest + limit - 1) / limit;
@@ -543,6 +636,31 @@ Tensor Communicator::raw_reduce_scatter(const Tensor& input, int64_t op_, int64_
     const int64_t es = static_cast<int64_t>(in.element_size());
     const int64_t limit = slab_limit_bytes(r, cx());
     const int64_t in_bytes = in.numel() * es;
+    if (in_bytes > limit && in.numel() > 0 && static_cast<int64_t>(size_) * a3.after * es > limit &&
+        static_cast<int64_t>(size_) * es <= limit) {
+      // one row per destination does not fit: split the trailing dimensions first
+      g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
+      Tensor in3 = in.view({a3.before, a3.axis, a3.after});
+      Tensor out = at::empty(out_shape, in.options());
+      Tensor out3 = out.view({a3.before, numelem, a3.after});
+      const bool has_acc = accumulate.has_value() && accumulate->defined();
+      Tensor acc3;
+      if (has_acc) {
+        TORCH_CHECK(accumulate->sizes().vec() == out_shape && accumulate->scalar_type() == input.scalar_type() &&
+                        accumulate->device() == input.device(),
+                    "mpi4torch_b200: Reduce_scatter: the accumulate tensor must have the result's shape, dtype and device");
+        acc3 = r.to_comm(*accumulate).view({a3.before, numelem, a3.after});
+      }
+      const int64_t na = limit / (es * static_cast<int64_t>(size_));
+      for (int64_t c0 = 0; c0 < a3.after; c0 += na) {
+        const int64_t n = std::min(na, a3.after - c0);
+        Tensor part = raw_reduce_scatter(in3.narrow(2, c0, n).contiguous(), op_, 1, numelem, scale, has_scale,
+                                         has_acc ? c10::optional<Tensor>(acc3.narrow(2, c0, n).contiguous())
+                                                 : c10::optional<Tensor>());
+        out3.narrow(2, c0, n).copy_(part);
+      }
+      return r.from_comm(out);
+    }
     if (in_bytes > limit && in.numel() > 0 && static_cast<int64_t>(size_) * a3.after * es <= limit) {
       g_slab_chunked_calls.fetch_add(1, std::memory_order_relaxed);
       Tensor in3 = in.view({a3.before, a3.axis, a3.after});

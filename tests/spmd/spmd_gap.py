@@ -310,6 +310,39 @@ class TestErrorsAndMisc(unittest.TestCase):
             r0 = sum(q + 3 for q in range(R))
             self.assertTrue(torch.equal(xin.grad[:, col:col + counts[p]], wp[r0:r0 + R + 3]))
             col += counts[p]
+        # trailing dimensions larger than the limit (one row does not fit): Allgather, Reduce_scatter, Scatter, Alltoall
+        wide = (torch.arange(float((R + 1) * 40), dtype=torch.double, device=DEVICE) + 7.0 * R).reshape(R + 1, 40)
+        gw = comm.Allgather(wide, 0)
+        offw = sum(p + 1 for p in range(R))
+        self.assertEqual(gw.shape[0], sum(p + 1 for p in range(P)))
+        self.assertTrue(torch.equal(gw[offw:offw + R + 1], wide))
+        rsw_in = torch.arange(float(2 * P * 40), dtype=torch.double, device=DEVICE).reshape(2 * P, 40) * (R + 1)
+        acc = torch.full((2, 40), 0.5, dtype=torch.double, device=DEVICE)
+        rsw = comm.Reduce_scatterFused(rsw_in, m4t.MPI_SUM, 0, 2, 2.0, acc)
+        want_w = torch.arange(float(2 * P * 40), dtype=torch.double, device=DEVICE).reshape(2 * P, 40)[2 * R:2 * R + 2]
+        self.assertTrue(torch.allclose(rsw, 0.5 + 2.0 * want_w * (P * (P + 1) / 2), rtol=1e-12, atol=0))
+        scw_src = torch.arange(float(sum(counts) * 40), dtype=torch.double, device=DEVICE).reshape(sum(counts), 40)
+        scw = comm.Scatter(scw_src if R == 0 else torch.zeros(1, dtype=torch.double, device=DEVICE), 0, counts[R], 0)
+        self.assertTrue(torch.equal(scw, scw_src[lo:lo + counts[R]]))
+        a2w_in = (torch.arange(float(2 * sum(counts) * 9), dtype=torch.double, device=DEVICE) + 1000.0 * R
+                  ).reshape(2, sum(counts), 9)
+        a2w = comm.Alltoall(a2w_in, 0, 1, counts[R])
+        for p in range(P):
+            want_p = (torch.arange(float(2 * sum(counts) * 9), dtype=torch.double, device=DEVICE) + 1000.0 * p
+                      ).reshape(2, sum(counts), 9)[:, lo:lo + counts[R]]
+            self.assertTrue(torch.equal(a2w[2 * p:2 * p + 2], want_p))
+        # same-axis Alltoall (re-partition of one global axis), uneven on both sides, with its gradient
+        have = [p % 4 + 2 for p in range(P)]
+        newc = list(reversed(have))
+        g0 = sum(have[:R])
+        rp_in = (torch.arange(float(have[R] * 3), dtype=torch.double, device=DEVICE).reshape(have[R], 3) + 3.0 * g0
+                 ).requires_grad_()
+        rp = comm.Alltoall(rp_in, 0, 0, newc[R])
+        n0 = sum(newc[:R])
+        self.assertTrue(torch.equal(rp.detach(), torch.arange(float(newc[R] * 3), dtype=torch.double, device=DEVICE
+                                                              ).reshape(newc[R], 3) + 3.0 * n0))
+        (rp * (rp.detach() + 1.0)).sum().backward()
+        self.assertTrue(torch.equal(rp_in.grad, rp_in.detach() + 1.0))
         forced = int(os.environ.get("M4T_SLAB_CHUNK_BYTES", "0"))
         if 0 < forced <= 64 and P > 1:
             self.assertGreater(m4t._C.slab_chunked_calls(), before)

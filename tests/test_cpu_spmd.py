@@ -12,10 +12,11 @@ def test_spmd_suite_cpu(nprocs):
     assert f"SPMD suite np={nprocs}" in res.stdout and "ok=True" in res.stdout
 
 
-@pytest.mark.parametrize("nprocs,limit", [(3, 64), (5, 1000)])
+@pytest.mark.parametrize("nprocs,limit", [(2, 24), (3, 64), (5, 1000)])
 def test_spmd_suites_with_every_slab_op_moved_in_pieces(nprocs, limit):
-    """Gather / Allgather / Reduce_scatter larger than a staging half are moved in pieces instead of raising (the CUDA
-    backend's limit is 2 GiB; M4T_SLAB_CHUNK_BYTES lowers it so that practically every call of the suites chunks)."""
+    """Gather / Allgather / Reduce_scatter / Scatter / Alltoall larger than a staging half are moved in pieces instead of
+    raising (the CUDA backend's limit is 2 GiB; M4T_SLAB_CHUNK_BYTES lowers it so that practically every call of the
+    suites chunks - along the leading dimensions, along the axis, along the trailing dimensions at 24 bytes)."""
     res = run_spmd(nprocs, ["tests/spmd/run_all.py", "spmd_[cgsp]*.py"], device="cpu", timeout=900,
                    extra_env={"M4T_SLAB_CHUNK_BYTES": str(limit)})
     assert res.returncode == 0, f"np={nprocs}\nSTDOUT:\n{res.stdout[-4000:]}\nSTDERR:\n{res.stderr[-8000:]}"
