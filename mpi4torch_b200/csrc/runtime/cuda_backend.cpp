@@ -151,8 +151,13 @@ void CudaBackend::chain(cudaStream_t s) {
     return;
   }
   if (have_last_ && last_stream_ != s) {
-    M4T_CUDA(cudaEventRecord(chain_event_, last_stream_));
-    M4T_CUDA(cudaStreamWaitEvent(s, chain_event_, 0));
+    // the previous stream may have been destroyed by its owner in the meantime: its work has then been
+    // completed or abandoned, and there is nothing left to order against
+    if (cudaEventRecord(chain_event_, last_stream_) == cudaSuccess) {
+      M4T_CUDA(cudaStreamWaitEvent(s, chain_event_, 0));
+    } else {
+      cudaGetLastError();
+    }
   }
   last_stream_ = s;
   have_last_ = true;
