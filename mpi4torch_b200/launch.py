@@ -146,8 +146,23 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     ap.add_argument("--tag-output", action="store_true", help="prefix every output line with its rank")
     ap.add_argument("-m", dest="module", default=None, help="run a module (python -m) instead of a script")
     ap.add_argument("rest", nargs=argparse.REMAINDER, help="script and its arguments")
+    argv = list(sys.argv[1:] if argv is None else argv)
+    tail: list = []
+    i = 0
+    while i < len(argv):  # walk the launcher's own options; a `-m` among the script's arguments is not ours
+        a = argv[i]
+        if a in ("-np", "-n", "--nproc", "--timeout"):
+            i += 2
+        elif a == "--tag-output" or a.startswith(("--nproc=", "--timeout=")):
+            i += 1
+        elif a == "-m" and i + 1 < len(argv):
+            # like `python -m mod args...`: everything after the module name belongs to the module, options included
+            argv, tail = argv[:i + 2], argv[i + 2:]
+            break
+        else:
+            break
     args = ap.parse_args(argv)
-    rest = list(args.rest)
+    rest = list(args.rest) + tail
     if rest and rest[0] == "--":
         rest = rest[1:]
     if args.module:

@@ -133,3 +133,52 @@ def test_numa_helpers_parse_sysfs_lists():
     # on a single-node box there is nothing to prefer; on a multi-node box the node of CPU 0 contains CPU 0
     node = affinity._numa_node_of({0})
     assert node is None or isinstance(node, int)
+
+
+def test_info_lists_every_environment_variable_the_sources_read():
+    """mpi4torch_b200.info.KNOBS is the documented list of knobs: it must name exactly the M4T_* variables that the
+    C++/CUDA sources read through env_i64 / getenv and the Python package reads through os.environ."""
+    import re
+    from pathlib import Path
+
+    from mpi4torch_b200 import info
+
+    pkg = Path(info.__file__).parent
+    read = set()
+    for path in list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")):
+        read.update(re.findall(r'(?:env_i64|getenv)\(\s*"(M4T_[A-Z0-9_]+)"', path.read_text()))
+    for path in pkg.rglob("*.py"):
+        if path.name == "info.py":
+            continue
+        read.update(re.findall(r'environ(?:\.get\(|\[)\s*"(M4T_[A-Z0-9_]+)"', path.read_text()))
+    assert read, "the scan found nothing: pattern out of date"
+    assert read - set(info.KNOBS) == set(), f"undocumented knobs: {sorted(read - set(info.KNOBS))}"
+    assert set(info.KNOBS) - read == set(), f"documented but never read: {sorted(set(info.KNOBS) - read)}"
+    # the CLI runs without a GPU and without initialising the communicator
+    assert info.main(["--json"]) == 0
+
+
+def test_launcher_passes_options_after_dash_m_to_the_module(tmp_path):
+    """`launch -np 2 -m module --flag` hands --flag to the module (as `python -m` does), and a `-m` among a script's
+    own arguments is left alone."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root, M4T_CUDA="0")
+    res = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", "-m", "mpi4torch_b200.info", "--world",
+                          "--json"], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(line) == 1  # rank 0 only
+    d = json.loads(line[0])
+    assert d["world"]["size"] == 2 and "posix-shm" in d["world"]["transport"]
+    script = tmp_path / "echo.py"
+    script.write_text("import sys, os\nif os.environ['RANK'] == '0': print('ARGS', sys.argv[1:])\n")
+    res = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", str(script), "-m", "x", "--timeout", "3"],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ARGS ['-m', 'x', '--timeout', '3']" in res.stdout
