@@ -86,19 +86,77 @@ def _bootstrap() -> None:
         os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     want_cuda = os.environ.get("M4T_CUDA", "1") != "0" and torch.cuda.is_available()
     device = 0
+    world = int(os.environ.get("WORLD_SIZE", os.environ.get("M4T_WORLD_SIZE", "1")))
     if want_cuda:
         ndev = torch.cuda.device_count()
         local_rank = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
-        world = int(os.environ.get("WORLD_SIZE", "1"))
         if ndev == 0 or (world > 1 and int(os.environ.get("LOCAL_WORLD_SIZE", world)) > ndev):
             want_cuda = False  # more ranks than GPUs: CPU backend + host staging only
         else:
             device = local_rank % ndev
             torch.cuda.set_device(device)
+    if _spans_nodes(world):
+        # more than one node: the communicator lives on a TCP mesh, CUDA tensors are staged through host memory
+        # (what the reference does on an MPI without CUDA support); the NVLink backend needs one node
+        _connect_mesh(world)
+        want_cuda = False
     _C.init_world(want_cuda, device)
 
 
+def _spans_nodes(world: int) -> bool:
+    """One node = shared-memory control plane + NVLink heap; several nodes (LOCAL_WORLD_SIZE < WORLD_SIZE, as torchrun
+    and this package's launcher export them) = TCP mesh.  ``M4T_NET=1`` forces the mesh on one node (tests), ``0``
+    forbids it."""
+    forced = os.environ.get("M4T_NET", "")
+    if forced in ("0", "1"):
+        return forced == "1" and world > 1
+    return world > 1 and int(os.environ.get("LOCAL_WORLD_SIZE", world)) < world
+
+
+def _connect_mesh(world: int) -> None:
+    """Rendezvous for the TCP mesh: every rank publishes ``host:port`` of its listening socket in the job's key-value
+    store (the one torchrun's agent or this package's launcher hosts at MASTER_ADDR:MASTER_PORT; without either, rank 0
+    hosts it) and connects to the others natively.  Replaces ``mpirun``'s wire-up across nodes."""
+    import socket
+    from datetime import timedelta
+
+    from torch.distributed import TCPStore
+
+    rank = int(os.environ.get("RANK", os.environ.get("M4T_RANK", "0")))
+    host = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(os.environ.get("MASTER_PORT", "29500"))
+    timeout = float(os.environ.get("M4T_TIMEOUT_S", "300"))
+    hosted = os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "") == "True" or os.environ.get("M4T_STORE_HOSTED", "0") == "1"
+    store = TCPStore(host, port, None, rank == 0 and not hosted, timedelta(seconds=timeout), wait_for_workers=False)
+    mine = os.environ.get("M4T_NET_IFADDR", "")
+    if not mine:
+        try:  # the address this host uses to reach the master is one the other nodes can reach too
+            with socket.socket(socket.AF_INET, socket.SOCK_DGRAM) as s:
+                s.connect((host, port))
+                mine = s.getsockname()[0]
+        except OSError:
+            mine = socket.gethostname()
+    # one job name for all nodes (it seeds the communicator ids that keep frames of different communicators apart)
+    os.environ.setdefault("M4T_JOB_ID", f"mn{port}")
+    listen_port = _C.net_listen()
+    prefix = "m4t/" + os.environ["M4T_JOB_ID"] + "/addr/"
+    store.set(prefix + str(rank), f"{mine}:{listen_port}")
+    addrs = [store.get(prefix + str(p)).decode() for p in range(world)]
+    _C.net_connect(rank, world, addrs)
+    # keep the store alive until every rank has read every address (rank 0 may be its host)
+    store.add(prefix + "done", 1)
+    if rank == 0 and not hosted:
+        import time
+
+        t0 = time.monotonic()
+        while int(store.add(prefix + "done", 0)) < world and time.monotonic() - t0 < timeout:
+            time.sleep(0.01)
+    global _mesh_store
+    _mesh_store = store
+
+
 _bootstrapped = False
+_mesh_store = None  # the rendezvous store client (kept so that a store hosted by rank 0 outlives start-up)
 
 
 def _ensure_world() -> None:

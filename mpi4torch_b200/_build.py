@@ -26,6 +26,8 @@ _SOURCES = [
     "runtime/control.cpp",
     "runtime/plan.cpp",
     "runtime/cpu_backend.cpp",
+    "runtime/net_link.cpp",
+    "runtime/net_backend.cpp",
     "runtime/symm_heap.cpp",
     "runtime/cuda_backend.cpp",
     "runtime/world.cpp",

@@ -40,6 +40,24 @@ void init_world(bool want_cuda, int64_t device) {
   }
 }
 
+// Multi-node start-up, driven from Python (mpi4torch_b200/__init__.py::_bootstrap): every rank opens its listening
+// socket, the addresses travel through the launcher's store, then the mesh is connected.
+int g_listen_fd = -1;
+
+int64_t net_listen() {
+  int port = 0;
+  g_listen_fd = NetEngine::listen_any(&port);
+  return port;
+}
+
+void net_connect(int64_t rank, int64_t size, const std::vector<std::string>& addrs) {
+  M4T_CHECK(g_listen_fd >= 0, "net_connect() without net_listen()");
+  const double timeout_s = static_cast<double>(env_i64("M4T_TIMEOUT_S", 300));
+  auto engine = std::make_shared<NetEngine>(static_cast<int>(rank), static_cast<int>(size), g_listen_fd, addrs, timeout_s);
+  g_listen_fd = -1;
+  World::set_network(std::move(engine));
+}
+
 void deactivate_cuda_aware_mpi_support() {
   // Reference :54-59 forces host staging for CUDA tensors; same effect here.
   World::instance().set_host_staging(true);
@@ -99,6 +117,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("init_world", &init_world, py::arg("want_cuda"), py::arg("device") = 0,
         "Attach to the job (collective) and optionally bring up the CUDA backend on `device`.");
   m.def("finalize", [] { World::finalize(); });
+  m.def("net_listen", &net_listen, "Opens this rank's listening socket for the multi-node TCP mesh; returns the port");
+  m.def("net_connect", &net_connect, py::arg("rank"), py::arg("size"), py::arg("addrs"),
+        "Connects the TCP mesh (addrs[p] = 'host:port' of rank p); the world communicator is then created on it");
+  m.def("over_network", [] { return World::instance().ctx()->over_network(); });
   m.def("world_initialised", [] { return World::initialised(); });
   m.def("deactivate_cuda_aware_mpi_support", &deactivate_cuda_aware_mpi_support);
   m.def("activate_nvlink_transport", &activate_nvlink_transport);

@@ -54,7 +54,7 @@ struct Route {
 
   Route(World& w, CommContext& cx, const Tensor& t) : device(t.device()) {
     if (t.is_cpu()) {
-      be = &cx.cpu();
+      be = &cx.host();
     } else if (t.is_cuda()) {
       if (!w.host_staging() && cx.cuda_ready()) {
         CudaBackend* cb = cx.cuda();
@@ -65,7 +65,7 @@ struct Route {
         be = cb;
       } else {
         staged = true;
-        be = &cx.cpu();
+        be = &cx.host();
       }
     } else {
       TORCH_CHECK(false, "mpi4torch_b200: unsupported device ", t.device());
@@ -109,7 +109,7 @@ std::atomic<int64_t> g_slab_chunked_calls{0};  // how often a slab collective ha
 int64_t slab_limit_bytes(const Route& r, CommContext& cx) {
   static const int64_t forced = env_i64("M4T_SLAB_CHUNK_BYTES", 0);
   int64_t limit = std::numeric_limits<int64_t>::max();
-  if (!r.staged && r.be != &cx.cpu() && cx.cuda_ready()) limit = cx.cuda()->half_bytes();
+  if (!r.staged && r.be != &cx.host() && cx.cuda_ready()) limit = cx.cuda()->half_bytes();
   if (forced > 0) limit = std::min(limit, forced);
   return limit;
 }
@@ -147,7 +147,7 @@ c10::intrusive_ptr<Communicator> Communicator::Split(int64_t color, int64_t key)
   // one metadata round: everybody learns everybody's (color, key)
   int64_t mine[2] = {color, key};
   std::vector<int64_t> all(static_cast<size_t>(size_) * 2);
-  cx().control().allgather_i64(mine, 2, all.data());
+  cx().allgather_i64(mine, 2, all.data());
   std::vector<std::pair<int64_t, int64_t>> members;  // (key, old rank)
   // a negative colour (MPI_UNDEFINED) still takes part in the exchange and gets
   // a communicator that contains only itself (MPI_COMM_SELF)
@@ -160,7 +160,16 @@ c10::intrusive_ptr<Communicator> Communicator::Split(int64_t color, int64_t key)
   const uint64_t split_id = cx().next_split_id();  // identical on all ranks: Split is collective
   const std::string job = cx().job_id() + "_s" + std::to_string(split_id) +
                           (color >= 0 ? "c" + std::to_string(color) : "r" + std::to_string(rank_));
-  auto child = std::make_shared<CommContext>(new_rank, static_cast<int>(members.size()), job);
+  std::shared_ptr<CommContext> child;
+  if (cx().over_network()) {
+    // sub-communicator on the same TCP mesh: its own id keeps its frames apart from every other communicator's
+    std::vector<int> world_ranks;
+    for (const auto& m : members) world_ranks.push_back(cx().net()->members()[static_cast<size_t>(m.second)]);
+    auto link = std::make_shared<NetLink>(cx().net()->engine_ptr(), net_comm_id(job), std::move(world_ranks), new_rank);
+    child = std::make_shared<CommContext>(std::move(link), job);
+  } else {
+    child = std::make_shared<CommContext>(new_rank, static_cast<int>(members.size()), job);
+  }
   if (cx().cuda_ready()) {
     // same device, smaller arenas than the world communicator's
     child->init_cuda(cx().cuda()->device(), env_i64("M4T_SUB_STAGE_MB", 256), env_i64("M4T_SUB_SYMM_MB", 0));
@@ -182,12 +191,13 @@ c10::intrusive_ptr<Communicator> comm_world() { return c10::make_intrusive<Commu
 
 void Communicator::Barrier() {
   std::lock_guard<std::recursive_mutex> g(world_->mutex());
-  cx().control().barrier();
+  cx().barrier();
 }
 
 std::string Communicator::Describe() const {
   std::ostringstream o;
-  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << cx().job_id() << " | cpu: posix-shm";
+  o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << cx().job_id()
+    << (cx().over_network() ? " | host: tcp mesh (job spans nodes; CUDA tensors are staged through host memory)" : " | cpu: posix-shm");
   if (cx().cuda_ready()) o << " | " << cx().cuda()->describe();
   if (world_->host_staging()) o << " | host staging forced";
   return o.str();
@@ -294,7 +304,7 @@ void Communicator::exchange_meta(const int64_t* mine, int words, int64_t* all) {
     for (int64_t p = 0; p < size_; ++p) std::copy(mine, mine + words, all + p * words);
     return;
   }
-  cx().control().allgather_i64(mine, words, all);
+  cx().allgather_i64(mine, words, all);
 }
 
 Tensor Communicator::raw_gather(const Tensor& input, int64_t axis_, int64_t root, bool all) {
@@ -796,7 +806,7 @@ Tensor Communicator::raw_wait(const std::vector<Tensor>& handle) {
     stream = c10::cuda::getCurrentCUDAStream(buf.device().index()).stream();
     be = cx().cuda();
   } else {
-    be = &cx().cpu();
+    be = &cx().host();
   }
   be->wait(req, stream);
   if (kind == 0) return handle[2];

@@ -1,0 +1,354 @@
+#include "net_backend.h"
+
+#include <cstring>
+
+#include "host_kernels.h"
+
+namespace m4t {
+
+namespace {
+constexpr int64_t kDirectBytes = 64 * 1024;  // below: every rank receives every contribution
+constexpr int kDescWords = 8;                // src_off, n[3], ss[3], run
+
+void push_desc(std::vector<int64_t>& v, const SlabJob& j) {
+  v.push_back(j.src_off);
+  for (int i = 0; i < 3; ++i) v.push_back(j.n[i]);
+  for (int i = 0; i < 3; ++i) v.push_back(j.ss[i]);
+  v.push_back(j.run);
+}
+
+SlabJob read_desc(const int64_t* w) {
+  SlabJob j;
+  j.src_off = w[0];
+  for (int i = 0; i < 3; ++i) j.n[i] = w[1 + i];
+  for (int i = 0; i < 3; ++i) j.ss[i] = w[4 + i];
+  j.run = w[7];
+  return j;
+}
+
+// rows of a box, packed contiguously in loop order (i0, i1, i2)
+void pack_box(const SlabJob& j, const char* src, char* dst, int64_t es) {
+  const size_t run_bytes = static_cast<size_t>(j.run * es);
+  for (int64_t i0 = 0; i0 < j.n[0]; ++i0)
+    for (int64_t i1 = 0; i1 < j.n[1]; ++i1)
+      for (int64_t i2 = 0; i2 < j.n[2]; ++i2) {
+        std::memcpy(dst, src + (j.src_off + i0 * j.ss[0] + i1 * j.ss[1] + i2 * j.ss[2]) * es, run_bytes);
+        dst += run_bytes;
+      }
+}
+
+void unpack_box(const SlabJob& j, const char* src, char* dst, int64_t es) {
+  const size_t run_bytes = static_cast<size_t>(j.run * es);
+  for (int64_t i0 = 0; i0 < j.n[0]; ++i0)
+    for (int64_t i1 = 0; i1 < j.n[1]; ++i1)
+      for (int64_t i2 = 0; i2 < j.n[2]; ++i2) {
+        std::memcpy(dst + (j.dst_off + i0 * j.ds[0] + i1 * j.ds[1] + i2 * j.ds[2]) * es, src, run_bytes);
+        src += run_bytes;
+      }
+}
+
+// Serves the box requests of every peer out of `in` and returns the packed answers (kept alive by the caller until
+// the sends are complete).  reqs[p] = descriptor words received from p.
+void serve_requests(NetLink& link, int64_t data_tag, const std::vector<std::vector<char>>& reqs, const char* in, int64_t es,
+                    std::vector<std::vector<char>>& answers, std::vector<uint64_t>& ops) {
+  const int P = link.size(), r = link.rank();
+  answers.assign(static_cast<size_t>(P), {});
+  for (int p = 0; p < P; ++p) {
+    if (p == r || reqs[static_cast<size_t>(p)].empty()) continue;
+    const auto* w = reinterpret_cast<const int64_t*>(reqs[static_cast<size_t>(p)].data());
+    const size_t njobs = reqs[static_cast<size_t>(p)].size() / (kDescWords * sizeof(int64_t));
+    size_t total = 0;
+    for (size_t k = 0; k < njobs; ++k) total += static_cast<size_t>(read_desc(w + k * kDescWords).elems() * es);
+    auto& buf = answers[static_cast<size_t>(p)];
+    buf.resize(total);
+    char* dst = buf.data();
+    for (size_t k = 0; k < njobs; ++k) {
+      const SlabJob j = read_desc(w + k * kDescWords);
+      pack_box(j, in, dst, es);
+      dst += j.elems() * es;
+    }
+    ops.push_back(link.send(p, kNetColl, data_tag, buf.data(), buf.size()));
+  }
+}
+}  // namespace
+
+void NetBackend::allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi, void*) {
+  check_op_dtype(op, dt);
+  const int P = size(), r = rank();
+  const int64_t es = dtype_size(dt);
+  const size_t bytes = static_cast<size_t>(n * es);
+  if (P == 1) {
+    const void* srcs[1] = {in};
+    M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, 1, out, 0, n, &epi);
+    return;
+  }
+  const int64_t tag = link_->next_seq() * 4;
+  NetEngine& eng = link_->engine();
+  const void* srcs[kMaxRanks];
+  std::vector<uint64_t> ops;
+  if (static_cast<int64_t>(bytes) <= kDirectBytes || n < P) {
+    std::vector<char> tmp(bytes * static_cast<size_t>(P - 1));
+    for (int p = 0, k = 0; p < P; ++p) {
+      if (p == r) {
+        srcs[p] = in;
+        continue;
+      }
+      char* slot = tmp.data() + bytes * static_cast<size_t>(k++);
+      srcs[p] = slot;
+      ops.push_back(link_->recv(p, kNetColl, tag, slot, bytes));
+    }
+    for (int p = 0; p < P; ++p)
+      if (p != r) ops.push_back(link_->send(p, kNetColl, tag, in, bytes));
+    eng.wait_all(ops);
+    M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, P, out, 0, n, &epi);
+    return;
+  }
+  // reduce-scatter by direct exchange (rank p reduces slice p, sources in rank order exactly like the shared-memory
+  // backend), then all-gather of the finished slices; every rank sends and receives (P-1)/P of the message twice
+  auto lo = [&](int p) { return n * p / P; };
+  const int64_t mylo = lo(r), mylen = lo(r + 1) - lo(r);
+  std::vector<char> tmp(static_cast<size_t>(mylen * es) * static_cast<size_t>(P - 1));
+  std::vector<char> res(static_cast<size_t>(mylen * es));
+  for (int p = 0, k = 0; p < P; ++p) {
+    if (p == r) {
+      srcs[p] = static_cast<const char*>(in) + mylo * es;
+      continue;
+    }
+    char* slot = tmp.data() + static_cast<size_t>(mylen * es) * static_cast<size_t>(k++);
+    srcs[p] = slot;
+    ops.push_back(link_->recv(p, kNetColl, tag, slot, static_cast<size_t>(mylen * es)));
+  }
+  for (int p = 0; p < P; ++p)
+    if (p != r)
+      ops.push_back(link_->send(p, kNetColl, tag, static_cast<const char*>(in) + lo(p) * es,
+                                static_cast<size_t>((lo(p + 1) - lo(p)) * es)));
+  eng.wait_all(ops);
+  ops.clear();
+  Epilogue e1;
+  e1.scale = epi.scale;
+  e1.has_scale = epi.has_scale;
+  M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, P, res.data(), 0, mylen, &e1);
+  // phase 2 (accumulate fused while the slices land)
+  std::vector<char> land;
+  if (epi.accumulate) land.resize(bytes);
+  char* dst = epi.accumulate ? land.data() : static_cast<char*>(out);
+  for (int p = 0; p < P; ++p)
+    if (p != r) ops.push_back(link_->recv(p, kNetColl, tag + 1, dst + lo(p) * es, static_cast<size_t>((lo(p + 1) - lo(p)) * es)));
+  for (int p = 0; p < P; ++p)
+    if (p != r) ops.push_back(link_->send(p, kNetColl, tag + 1, res.data(), res.size()));
+  if (mylen) std::memcpy(dst + mylo * es, res.data(), res.size());
+  eng.wait_all(ops);
+  if (epi.accumulate) {
+    M4T_DISPATCH_DTYPE_OP(dt, ReduceOp::SUM, CpuAccumulateCopy, land.data(), epi.accumulate, out, 0, n);
+  }
+}
+
+void NetBackend::bcast(void* buf, int64_t n, DType dt, int root, void*) {
+  const int P = size(), r = rank();
+  M4T_CHECK(root >= 0 && root < P, "Bcast_: root " << root << " out of range");
+  if (P == 1) return;
+  const size_t bytes = static_cast<size_t>(n * dtype_size(dt));
+  const int64_t tag = link_->next_seq() * 4;
+  NetEngine& eng = link_->engine();
+  const int v = (r - root + P) % P;  // binomial tree on ranks relative to the root
+  int mask = 1;
+  while (mask < P) {
+    if (v & mask) {
+      eng.wait(link_->recv((v - mask + root) % P, kNetColl, tag, buf, bytes));
+      break;
+    }
+    mask <<= 1;
+  }
+  mask >>= 1;
+  std::vector<uint64_t> ops;
+  while (mask > 0) {
+    if (v + mask < P) ops.push_back(link_->send((v + mask + root) % P, kNetColl, tag, buf, bytes));
+    mask >>= 1;
+  }
+  eng.wait_all(ops);
+}
+
+void NetBackend::reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void*) {
+  check_op_dtype(op, dt);
+  const int P = size(), r = rank();
+  M4T_CHECK(root >= 0 && root < P, "Reduce_: root " << root << " out of range");
+  const size_t bytes = static_cast<size_t>(n * dtype_size(dt));
+  if (P == 1) {
+    const void* srcs[1] = {buf};
+    M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, 1, buf, 0, n, nullptr);
+    return;
+  }
+  const int64_t tag = link_->next_seq() * 4;
+  NetEngine& eng = link_->engine();
+  if (r != root) {
+    eng.wait(link_->send(root, kNetColl, tag, buf, bytes));
+    if (bytes) std::memset(buf, 0, bytes);  // reference csrc/extension.cpp:443-447
+    return;
+  }
+  // the root combines the contributions in rank order (same result as the shared-memory backend)
+  std::vector<char> tmp(bytes * static_cast<size_t>(P - 1));
+  const void* srcs[kMaxRanks];
+  std::vector<uint64_t> ops;
+  for (int p = 0, k = 0; p < P; ++p) {
+    if (p == r) {
+      srcs[p] = buf;
+      continue;
+    }
+    char* slot = tmp.data() + bytes * static_cast<size_t>(k++);
+    srcs[p] = slot;
+    ops.push_back(link_->recv(p, kNetColl, tag, slot, bytes));
+  }
+  eng.wait_all(ops);
+  M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, P, buf, 0, n, nullptr);
+}
+
+void NetBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt, void*) {
+  const int P = size(), r = rank();
+  const int64_t es = dtype_size(dt);
+  const char* cin = static_cast<const char*>(in);
+  char* cout = static_cast<char*>(out);
+  if (P == 1) {
+    for (const auto& j : plan.jobs) copy_rows(j, cin, cout, es);
+    return;
+  }
+  const int64_t seq = link_->next_seq();
+  const int64_t req_tag = seq * 4, data_tag = seq * 4 + 1;
+  NetEngine& eng = link_->engine();
+  // what I want from whom
+  std::vector<std::vector<int64_t>> want(static_cast<size_t>(P));
+  std::vector<std::vector<const SlabJob*>> mine(static_cast<size_t>(P));
+  for (const auto& j : plan.jobs) {
+    if (j.peer == r) continue;
+    push_desc(want[static_cast<size_t>(j.peer)], j);
+    mine[static_cast<size_t>(j.peer)].push_back(&j);
+  }
+  std::vector<uint64_t> req_recv(static_cast<size_t>(P), 0), sends;
+  for (int p = 0; p < P; ++p)
+    if (p != r) req_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, req_tag, nullptr, SIZE_MAX);
+  for (int p = 0; p < P; ++p)
+    if (p != r)
+      sends.push_back(link_->send(p, kNetColl, req_tag, want[static_cast<size_t>(p)].data(),
+                                  want[static_cast<size_t>(p)].size() * sizeof(int64_t)));
+  // answers I expect
+  std::vector<std::vector<char>> got(static_cast<size_t>(P));
+  std::vector<uint64_t> data_recv(static_cast<size_t>(P), 0);
+  for (int p = 0; p < P; ++p) {
+    if (p == r || mine[static_cast<size_t>(p)].empty()) continue;
+    size_t total = 0;
+    for (const SlabJob* j : mine[static_cast<size_t>(p)]) total += static_cast<size_t>(j->elems() * es);
+    got[static_cast<size_t>(p)].resize(total);
+    data_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, data_tag, got[static_cast<size_t>(p)].data(), total);
+  }
+  for (const auto& j : plan.jobs)
+    if (j.peer == r) copy_rows(j, cin, cout, es);
+  std::vector<std::vector<char>> reqs(static_cast<size_t>(P));
+  for (int p = 0; p < P; ++p)
+    if (p != r) eng.wait(req_recv[static_cast<size_t>(p)], &reqs[static_cast<size_t>(p)]);
+  std::vector<std::vector<char>> answers;
+  serve_requests(*link_, data_tag, reqs, cin, es, answers, sends);
+  for (int p = 0; p < P; ++p) {
+    if (!data_recv[static_cast<size_t>(p)]) continue;
+    eng.wait(data_recv[static_cast<size_t>(p)]);
+    const char* src = got[static_cast<size_t>(p)].data();
+    for (const SlabJob* j : mine[static_cast<size_t>(p)]) {
+      unpack_box(*j, src, cout, es);
+      src += j->elems() * es;
+    }
+  }
+  eng.wait_all(sends);
+}
+
+void NetBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,
+                             void*) {
+  check_op_dtype(op, dt);
+  const int P = size(), r = rank();
+  const int64_t es = dtype_size(dt);
+  const char* cin = static_cast<const char*>(in);
+  const char* srcs[kMaxRanks];
+  if (P == 1) {
+    srcs[0] = cin;
+    if (plan.out_elems > 0) {
+      M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceBox, plan.box, srcs, 1, static_cast<char*>(out), &epi);
+    }
+    return;
+  }
+  const int64_t seq = link_->next_seq();
+  const int64_t req_tag = seq * 4, data_tag = seq * 4 + 1;
+  NetEngine& eng = link_->engine();
+  std::vector<int64_t> want;
+  if (plan.out_elems > 0) push_desc(want, plan.box);
+  std::vector<uint64_t> req_recv(static_cast<size_t>(P), 0), sends;
+  for (int p = 0; p < P; ++p)
+    if (p != r) req_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, req_tag, nullptr, SIZE_MAX);
+  for (int p = 0; p < P; ++p)
+    if (p != r) sends.push_back(link_->send(p, kNetColl, req_tag, want.data(), want.size() * sizeof(int64_t)));
+  const size_t box_bytes = plan.out_elems > 0 ? static_cast<size_t>(plan.box.elems() * es) : 0;
+  std::vector<std::vector<char>> got(static_cast<size_t>(P));
+  std::vector<uint64_t> data_recv(static_cast<size_t>(P), 0);
+  if (box_bytes) {
+    for (int p = 0; p < P; ++p) {
+      got[static_cast<size_t>(p)].resize(box_bytes);
+      if (p != r) data_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, data_tag, got[static_cast<size_t>(p)].data(), box_bytes);
+    }
+    pack_box(plan.box, cin, got[static_cast<size_t>(r)].data(), es);
+  }
+  std::vector<std::vector<char>> reqs(static_cast<size_t>(P));
+  for (int p = 0; p < P; ++p)
+    if (p != r) eng.wait(req_recv[static_cast<size_t>(p)], &reqs[static_cast<size_t>(p)]);
+  std::vector<std::vector<char>> answers;
+  serve_requests(*link_, data_tag, reqs, cin, es, answers, sends);
+  if (box_bytes) {
+    for (int p = 0; p < P; ++p) {
+      if (p != r) eng.wait(data_recv[static_cast<size_t>(p)]);
+      srcs[p] = got[static_cast<size_t>(p)].data();
+    }
+    SlabJob packed = plan.box;  // sources are the packed answers, the destination keeps the plan's strides
+    packed.src_off = 0;
+    packed.ss[2] = packed.run;
+    packed.ss[1] = packed.n[2] * packed.run;
+    packed.ss[0] = packed.n[1] * packed.n[2] * packed.run;
+    M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceBox, packed, srcs, P, static_cast<char*>(out), &epi);
+  }
+  eng.wait_all(sends);
+}
+
+int64_t NetBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag, void*) {
+  M4T_CHECK(dest >= 0 && dest < size(), "Isend: destination rank " << dest << " out of range");
+  // buffered (the engine keeps a copy): a handle that is dropped without Wait must not leave the engine reading
+  // freed memory, and like the shared-memory backend the send then completes locally
+  const uint64_t op = link_->engine().post_send(link_->members()[static_cast<size_t>(dest)], link_->comm_id(), kNetP2p, tag,
+                                                buf, static_cast<size_t>(bytes), /*copy=*/true);
+  const int64_t id = next_request_++;
+  requests_[id] = op;
+  return id;
+}
+
+int64_t NetBackend::irecv(void* buf, int64_t bytes, int source, int64_t tag, void*) {
+  M4T_CHECK(source >= 0 && source < size(), "Irecv: source rank " << source << " out of range");
+  // received into an engine buffer and copied out by Wait (a dropped handle never leaves a dangling target)
+  const uint64_t op = link_->recv(source, kNetP2p, tag, nullptr, static_cast<size_t>(bytes));
+  const int64_t id = next_request_++;
+  requests_[id] = op;
+  recv_bufs_[id] = buf;
+  return id;
+}
+
+void NetBackend::wait(int64_t request, void*) {
+  auto it = requests_.find(request);
+  M4T_CHECK(it != requests_.end(), "Wait: unknown or already completed request " << request
+                                       << " (a WaitHandle may only be waited on once)");
+  const uint64_t op = it->second;
+  requests_.erase(it);
+  auto rb = recv_bufs_.find(request);
+  if (rb == recv_bufs_.end()) {
+    link_->engine().wait(op);
+    return;
+  }
+  void* dst = rb->second;
+  recv_bufs_.erase(rb);
+  std::vector<char> data;
+  const size_t n = link_->engine().wait(op, &data);
+  if (n) std::memcpy(dst, data.data(), n);
+}
+
+}  // namespace m4t

@@ -1,0 +1,48 @@
+// Host backend over the TCP mesh (jobs that span nodes).  Same contract as CpuBackend, different transport:
+//   Allreduce   small: every rank receives every contribution and reduces in rank order; large: ring reduce-scatter +
+//               ring all-gather (each rank moves 2(P-1)/P of the message), epilogue applied to the finished vector
+//   Bcast_      binomial tree from the root
+//   Reduce_     binomial tree to the root, non-root buffers zero-filled
+//   slab plans  request / response: a rank sends the box descriptors of its plan to the peers that hold the data, they
+//               pack the rows and answer; the plans themselves (plan.cpp) are the ones the other backends execute
+//   Isend/Irecv the engine's posted sends / receives with the user tag (FIFO per source and tag, unexpected messages
+//               are buffered)
+// Host-blocking like MPI on host buffers (reference csrc/extension.cpp:61-104); CUDA tensors reach it through the
+// API layer's host staging.
+#pragma once
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "backend.h"
+#include "net_link.h"
+
+namespace m4t {
+
+class NetBackend final : public Backend {
+ public:
+  explicit NetBackend(std::shared_ptr<NetLink> link) : link_(std::move(link)) {}
+
+  const char* name() const override { return "tcp"; }
+  int rank() const override { return link_->rank(); }
+  int size() const override { return link_->size(); }
+
+  void allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                 void* stream) override;
+  void bcast(void* buf, int64_t n, DType dt, int root, void* stream) override;
+  void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override;
+  void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override;
+  void reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,
+                   void* stream) override;
+  int64_t isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) override;
+  int64_t irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) override;
+  void wait(int64_t request, void* stream) override;
+
+ private:
+  std::shared_ptr<NetLink> link_;
+  std::unordered_map<int64_t, uint64_t> requests_;  // request id -> engine operation
+  std::unordered_map<int64_t, void*> recv_bufs_;    // receive requests: where Wait copies the message
+  int64_t next_request_ = 1;
+};
+
+}  // namespace m4t

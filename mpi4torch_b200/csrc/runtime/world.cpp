@@ -7,6 +7,7 @@ namespace m4t {
 namespace {
 World* g_world = nullptr;
 std::mutex g_world_mu;
+std::shared_ptr<NetEngine> g_engine;  // set by set_network() for jobs that span nodes
 }  // namespace
 
 CommContext::CommContext(int rank, int size, const std::string& job_id) : job_id_(job_id) {
@@ -14,19 +15,41 @@ CommContext::CommContext(int rank, int size, const std::string& job_id) : job_id
   cpu_ = std::make_unique<CpuBackend>(*ctl_);
 }
 
+CommContext::CommContext(std::shared_ptr<NetLink> link, const std::string& job_id) : job_id_(job_id), net_(std::move(link)) {
+  // a private one-rank segment keeps the shared-memory classes valid; nothing is exchanged through it
+  ctl_ = std::make_unique<Control>(0, 1, job_id + "_n" + std::to_string(net_->engine().rank()));
+  cpu_ = std::make_unique<CpuBackend>(*ctl_);
+  netbe_ = std::make_unique<NetBackend>(net_);
+}
+
 CommContext::~CommContext() { shutdown(); }
 
 void CommContext::shutdown() {
   if (!ctl_) return;
-  // every member reaches this point before anybody unmaps / unlinks shared segments
+  // every member reaches this point before anybody unmaps / unlinks shared segments (or closes its sockets)
+  if (net_) net_->quiesce();
   ctl_->quiesce(static_cast<double>(env_i64("M4T_EXIT_TIMEOUT_S", 10)));
   cuda_.reset();
+  netbe_.reset();
+  net_.reset();
   cpu_.reset();
   ctl_.reset();
 }
 
+void CommContext::barrier() {
+  if (net_) net_->barrier();
+  else ctl_->barrier();
+}
+
+void CommContext::allgather_i64(const int64_t* mine, int k, int64_t* all) {
+  if (net_) net_->allgather_i64(mine, k, all);
+  else ctl_->allgather_i64(mine, k, all);
+}
+
 void CommContext::init_cuda(int device, int64_t stage_mb, int64_t symm_mb) {
   if (cuda_) return;
+  M4T_CHECK(!net_, "the NVLink backend needs all ranks on one node; this job spans nodes (CUDA tensors are staged "
+                   "through host memory and the TCP transport)");
   cuda_ = std::make_unique<CudaBackend>(*ctl_, device, stage_mb, symm_mb);
 }
 
@@ -34,7 +57,17 @@ void CommContext::shutdown_cuda() { cuda_.reset(); }
 
 World::World() {
   env_ = world_env_from_environment();
-  ctx_ = std::make_shared<CommContext>(env_.rank, env_.size, env_.job_id);
+  if (g_engine) {
+    M4T_CHECK(g_engine->rank() == env_.rank && g_engine->size() == env_.size,
+              "the TCP mesh was built for rank " << g_engine->rank() << "/" << g_engine->size() << " but the environment says "
+                                                 << env_.rank << "/" << env_.size);
+    std::vector<int> members(static_cast<size_t>(env_.size));
+    for (int p = 0; p < env_.size; ++p) members[static_cast<size_t>(p)] = p;
+    auto link = std::make_shared<NetLink>(g_engine, net_comm_id(env_.job_id + "_world"), std::move(members), env_.rank);
+    ctx_ = std::make_shared<CommContext>(std::move(link), env_.job_id);
+  } else {
+    ctx_ = std::make_shared<CommContext>(env_.rank, env_.size, env_.job_id);
+  }
 }
 
 World::~World() {
@@ -50,6 +83,12 @@ void World::release_child(const CommContext* c) {
       children_.erase(it);
       return;
     }
+}
+
+void World::set_network(std::shared_ptr<NetEngine> engine) {
+  std::lock_guard<std::mutex> g(g_world_mu);
+  M4T_CHECK(!g_world, "the TCP mesh must be set up before the world communicator exists");
+  g_engine = std::move(engine);
 }
 
 World& World::instance() {
@@ -69,6 +108,7 @@ void World::finalize() {
     delete g_world;
     g_world = nullptr;
   }
+  g_engine.reset();
 }
 
 void World::init_cuda(int device) {

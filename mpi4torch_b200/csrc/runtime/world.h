@@ -10,6 +10,8 @@
 #include "backend.h"
 #include "control.h"
 #include "cpu_backend.h"
+#include "net_backend.h"
+#include "net_link.h"
 
 namespace m4t {
 
@@ -24,12 +26,22 @@ class CudaBackend;
 class CommContext {
  public:
   CommContext(int rank, int size, const std::string& job_id);
+  // Job that spans nodes: the communicator lives on the TCP mesh (net_link.h).  The shared-memory control segment
+  // then only holds this process (nothing is shared through it) and there is no CUDA backend.
+  CommContext(std::shared_ptr<NetLink> link, const std::string& job_id);
   ~CommContext();
-  int rank() const { return ctl_->rank(); }
-  int size() const { return ctl_->size(); }
+  int rank() const { return net_ ? net_->rank() : ctl_->rank(); }
+  int size() const { return net_ ? net_->size() : ctl_->size(); }
   const std::string& job_id() const { return job_id_; }
   Control& control() { return *ctl_; }
   CpuBackend& cpu() { return *cpu_; }
+  // the backend that moves host tensors: POSIX shared memory on one node, TCP across nodes
+  Backend& host() { return net_ ? static_cast<Backend&>(*netbe_) : static_cast<Backend&>(*cpu_); }
+  bool over_network() const { return net_ != nullptr; }
+  const std::shared_ptr<NetLink>& net() const { return net_; }
+  // host control operations of the communicator (shared-memory flags or TCP messages)
+  void barrier();
+  void allgather_i64(const int64_t* mine, int k, int64_t* all);
   // Collective over the context's ranks.  stage_mb / symm_mb < 0 = environment defaults.
   void init_cuda(int device, int64_t stage_mb = -1, int64_t symm_mb = -1);
   void shutdown_cuda();
@@ -47,6 +59,8 @@ class CommContext {
   std::unique_ptr<Control> ctl_;
   std::unique_ptr<CpuBackend> cpu_;
   std::unique_ptr<CudaBackend> cuda_;
+  std::shared_ptr<NetLink> net_;
+  std::unique_ptr<NetBackend> netbe_;
   uint64_t split_seq_ = 0;
 };
 
@@ -55,6 +69,9 @@ class World {
   // Lazily created from the environment (RANK / WORLD_SIZE / LOCAL_RANK / M4T_JOB_ID).
   static World& instance();
   static bool initialised();
+  // Multi-node start-up (before the first instance()): the mesh this process is part of.  The world communicator is
+  // then created on it instead of on a shared-memory segment.
+  static void set_network(std::shared_ptr<NetEngine> engine);
   // Tears the world down (idempotent); called from Python's atexit.
   static void finalize();
 

@@ -64,6 +64,10 @@ KNOBS: Dict[str, Tuple[str, str]] = {
     "M4T_DEBUG_SEGV": ("0", "1 installs a SIGSEGV handler that prints a native backtrace"),
     "M4T_NVTX": ("1", "0 drops the per-op NVTX ranges"),
     "M4T_NUMA_BIND": ("1", "0 leaves CPU affinity / memory policy alone (utils.bind_to_gpu_numa)"),
+    # ---- jobs that span nodes (TCP mesh)
+    "M4T_NET": ("", "1 forces the TCP mesh on one node (tests), 0 forbids it; default: when LOCAL_WORLD_SIZE < WORLD_SIZE"),
+    "M4T_NET_IFADDR": ("", "address other nodes should use to reach this rank (default: the one that routes to MASTER_ADDR)"),
+    "M4T_STORE_HOSTED": ("0", "1 = a launcher hosts the rendezvous store at MASTER_ADDR:MASTER_PORT (else rank 0 does)"),
     # ---- rendezvous (normally set by the launcher or torchrun)
     "M4T_RANK": ("", "rank when RANK is not set"),
     "M4T_WORLD_SIZE": ("", "world size when WORLD_SIZE is not set"),

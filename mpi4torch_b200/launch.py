@@ -1,4 +1,5 @@
-"""SPMD launcher: ``python -m mpi4torch_b200.launch -np N script.py [args...]``.
+"""SPMD launcher: ``python -m mpi4torch_b200.launch -np N script.py [args...]``; across nodes, once per node:
+``python -m mpi4torch_b200.launch -np N --nnodes M --node-rank K --master-addr HOST --master-port PORT script.py``.
 
 Replaces ``mpirun -np N python script.py`` (reference ``README.md:53-56``,
 ``.github/workflows/test.yml:64-84``): starts N ranks on this node, one OS
@@ -7,6 +8,11 @@ process each, wires them with environment variables only
 ``MASTER_ADDR / MASTER_PORT`` so ``torch.distributed`` baselines can rendezvous
 too), supervises them, and tears the whole job down as soon as one rank fails.
 The library itself never spawns processes.
+
+With ``--nnodes M`` every node runs one launcher with its ``--node-rank``; ranks are numbered node by node
+(``RANK = node_rank * N + LOCAL_RANK``, ``WORLD_SIZE = M * N``), node 0's launcher hosts the key-value store at
+``--master-addr:--master-port`` through which the ranks exchange the addresses of their TCP mesh sockets
+(``mpirun``'s wire-up across hosts; ``torchrun --nnodes`` works as well - the library then uses the agent's store).
 """
 from __future__ import annotations
 
@@ -44,19 +50,43 @@ def launch(
     env: Optional[dict] = None,
     tag_output: bool = False,
     cwd: Optional[str] = None,
+    nnodes: int = 1,
+    node_rank: int = 0,
+    master_addr: Optional[str] = None,
+    master_port: Optional[int] = None,
 ) -> int:
-    """Run ``cmd`` as ``nprocs`` ranks; returns the job's exit code (0 = all ranks ok)."""
+    """Run ``cmd`` as ``nprocs`` ranks on this node; returns the job's exit code (0 = all ranks ok).
+
+    ``nnodes > 1``: this node's share of a job of ``nnodes * nprocs`` ranks (see the module docstring)."""
     if nprocs < 1:
         raise ValueError("nprocs must be >= 1")
-    job_id = "j" + uuid.uuid4().hex[:12]
+    if nnodes < 1 or not 0 <= node_rank < nnodes:
+        raise ValueError("need 0 <= node_rank < nnodes")
     base = dict(os.environ if env is None else env)
+    store = None
+    if nnodes > 1:
+        if not master_addr or not master_port:
+            raise ValueError("--master-addr and --master-port are required with --nnodes > 1")
+        job_id = f"mn{master_port}"  # the same on every node
+        if node_rank == 0:
+            from datetime import timedelta
+
+            from torch.distributed import TCPStore
+
+            # node 0's launcher hosts the rendezvous store; it lives as long as the job
+            store = TCPStore(master_addr, int(master_port), None, True, timedelta(seconds=300), wait_for_workers=False)
+        base["M4T_STORE_HOSTED"] = "1"
+        base["GROUP_RANK"] = str(node_rank)
+    else:
+        job_id = "j" + uuid.uuid4().hex[:12]
+        master_addr, master_port = "127.0.0.1", _free_port()
     base.update(
         {
-            "WORLD_SIZE": str(nprocs),
+            "WORLD_SIZE": str(nprocs * nnodes),
             "LOCAL_WORLD_SIZE": str(nprocs),
             "M4T_JOB_ID": job_id,
-            "MASTER_ADDR": "127.0.0.1",
-            "MASTER_PORT": str(_free_port()),
+            "MASTER_ADDR": str(master_addr),
+            "MASTER_PORT": str(master_port),
         }
     )
     if nprocs > 1 and "OMP_NUM_THREADS" not in base:
@@ -73,7 +103,7 @@ def launch(
     try:
         for rank in range(nprocs):
             e = dict(base)
-            e["RANK"] = str(rank)
+            e["RANK"] = str(node_rank * nprocs + rank)
             e["LOCAL_RANK"] = str(rank)
             kwargs = {}
             if tag_output:
@@ -122,6 +152,7 @@ def launch(
             if p.poll() is None:
                 p.kill()
         _cleanup_shm(job_id)
+        del store
 
 
 def _terminate(procs: List[subprocess.Popen], pending: set) -> None:
@@ -144,6 +175,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     ap.add_argument("-np", "-n", "--nproc", dest="np", type=int, required=True, help="number of ranks")
     ap.add_argument("--timeout", type=float, default=None, help="kill the job after this many seconds")
     ap.add_argument("--tag-output", action="store_true", help="prefix every output line with its rank")
+    ap.add_argument("--nnodes", type=int, default=1, help="number of nodes of the job (one launcher per node)")
+    ap.add_argument("--node-rank", type=int, default=0, help="this node's index, 0 <= node-rank < nnodes")
+    ap.add_argument("--master-addr", default=None, help="address of node 0 (with --nnodes > 1)")
+    ap.add_argument("--master-port", type=int, default=None, help="port of the rendezvous store on node 0")
     ap.add_argument("-m", dest="module", default=None, help="run a module (python -m) instead of a script")
     ap.add_argument("rest", nargs=argparse.REMAINDER, help="script and its arguments")
     argv = list(sys.argv[1:] if argv is None else argv)
@@ -151,9 +186,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     i = 0
     while i < len(argv):  # walk the launcher's own options; a `-m` among the script's arguments is not ours
         a = argv[i]
-        if a in ("-np", "-n", "--nproc", "--timeout"):
+        if a in ("-np", "-n", "--nproc", "--timeout", "--nnodes", "--node-rank", "--master-addr", "--master-port"):
             i += 2
-        elif a == "--tag-output" or a.startswith(("--nproc=", "--timeout=")):
+        elif a == "--tag-output" or a.startswith(("--nproc=", "--timeout=", "--nnodes=", "--node-rank=", "--master-addr=",
+                                                   "--master-port=")):
             i += 1
         elif a == "-m" and i + 1 < len(argv):
             # like `python -m mod args...`: everything after the module name belongs to the module, options included
@@ -171,7 +207,8 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         if not rest:
             ap.error("no script given")
         cmd = [sys.executable] + rest if rest[0].endswith(".py") else rest
-    return launch(args.np, cmd, timeout=args.timeout, tag_output=args.tag_output)
+    return launch(args.np, cmd, timeout=args.timeout, tag_output=args.tag_output, nnodes=args.nnodes,
+                  node_rank=args.node_rank, master_addr=args.master_addr, master_port=args.master_port)
 
 
 if __name__ == "__main__":

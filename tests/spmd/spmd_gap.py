@@ -360,6 +360,8 @@ class TestErrorsAndMisc(unittest.TestCase):
         shim = os.path.join(root, "baseline", "mpi_shim")
         if not os.path.exists(os.path.join(shim, "lib", "libmpi.so")) or "MASTER_PORT" not in os.environ:
             self.skipTest("baseline/mpi_shim is not built (make -C baseline/mpi_shim)")
+        if int(os.environ.get("LOCAL_WORLD_SIZE", P)) < P:
+            self.skipTest("the bundled MPI shim is a single-node MPI; this job spans nodes")
         sys.path.insert(0, os.path.join(shim, "python"))
         try:
             import mpi4py.MPI as MPI

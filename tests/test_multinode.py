@@ -1,0 +1,119 @@
+"""Jobs that span nodes: the TCP mesh transport (csrc/runtime/net_link.cpp, net_backend.cpp).
+
+The reference reaches other nodes through MPI itself; here a job whose LOCAL_WORLD_SIZE is smaller than its WORLD_SIZE
+moves its communicators onto a mesh of TCP connections.  Several "nodes" are simulated on this host: one launcher per
+node against a common --master-addr/--master-port, or M4T_NET=1 to force the mesh inside one launcher.  The whole SPMD
+test set (collectives, uneven shapes, non-blocking p2p, JoinDummies, Split, parallelism helpers) runs unchanged."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT, run_spmd
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _env():
+    env = dict(os.environ)
+    env["PYTHONPATH"] = str(ROOT) + os.pathsep + env.get("PYTHONPATH", "")
+    env["M4T_CUDA"] = "0"
+    env["M4T_TEST_DEVICE"] = "cpu"
+    env.setdefault("M4T_TIMEOUT_S", "120")
+    return env
+
+
+@pytest.mark.parametrize("nprocs", [2, 5])
+def test_spmd_suites_over_the_tcp_mesh(nprocs):
+    res = run_spmd(nprocs, ["tests/spmd/run_all.py"], device="cpu", timeout=900, extra_env={"M4T_NET": "1"})
+    assert res.returncode == 0, f"np={nprocs}\nSTDOUT:\n{res.stdout[-4000:]}\nSTDERR:\n{res.stderr[-8000:]}"
+    assert f"SPMD suite np={nprocs}" in res.stdout and "ok=True" in res.stdout
+
+
+def test_two_nodes_two_ranks_each_one_launcher_per_node():
+    """2 x 2 ranks: node 0's launcher hosts the rendezvous store, both launchers number their ranks node by node, and
+    the full SPMD test set passes at world size 4."""
+    port = _free_port()
+    base = [sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", "--nnodes", "2", "--master-addr", "127.0.0.1",
+            "--master-port", str(port), "--timeout", "600"]
+    node1 = subprocess.Popen(base + ["--node-rank", "1", "tests/spmd/run_all.py"], env=_env(), cwd=str(ROOT),
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        node0 = subprocess.run(base + ["--node-rank", "0", "tests/spmd/run_all.py"], env=_env(), cwd=str(ROOT),
+                               capture_output=True, text=True, timeout=700)
+        out1, err1 = node1.communicate(timeout=120)
+    finally:
+        if node1.poll() is None:
+            node1.kill()
+    assert node0.returncode == 0, node0.stderr[-4000:]
+    assert node1.returncode == 0, err1[-4000:]
+    assert "SPMD suite np=4" in node0.stdout and "ok=True" in node0.stdout
+
+
+def test_describe_and_info_report_the_mesh():
+    res = subprocess.run([sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", "-m", "mpi4torch_b200.info", "--world",
+                          "--json"], env=dict(_env(), M4T_NET="1"), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+
+    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["world"]["size"] == 2 and "tcp mesh" in d["world"]["transport"] and d["world"]["cuda_backend"] is False
+
+
+def test_a_dead_peer_raises_instead_of_hanging(tmp_path):
+    """A rank that dies closes its sockets: whoever waits for it raises at once (the shared-memory control plane has
+    the abort flag and bounded waits for this; MPI jobs usually hang or are killed by mpirun)."""
+    script = tmp_path / "die.py"
+    script.write_text(
+        "import os, sys, time, torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD\n"
+        "c.Barrier()\n"
+        "if c.rank == 1:\n"
+        "    os._exit(3)\n"
+        "t0 = time.time()\n"
+        "try:\n"
+        "    c.Allreduce(torch.ones(4), m.MPI_SUM)\n"
+        "except RuntimeError as e:\n"
+        "    print('RAISED', round(time.time() - t0, 2), str(e)[:200], flush=True)\n"
+        "    sys.exit(5)\n")
+    res = run_spmd(3, [str(script)], device="cpu", timeout=120, extra_env={"M4T_NET": "1"})
+    assert res.returncode != 0
+    assert "RAISED" in res.stdout and "closed its connection" in res.stdout
+
+
+def test_large_messages_both_directions_and_sub_communicators_over_tcp(tmp_path):
+    """64 MiB exchanged both ways at once between every pair (the progress loop must drain while it sends), a 32 MiB
+    Allreduce with the fused epilogue, and collectives on two disjoint sub-communicators interleaved with the world's."""
+    script = tmp_path / "big.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R, P = c.rank, c.size\n"
+        "n = 16 << 20\n"
+        "x = torch.full((n,), float(R + 1))\n"
+        "hs = [c.Isend(x, p, 7) for p in range(P) if p != R]\n"
+        "for p in range(P):\n"
+        "    if p == R: continue\n"
+        "    y = c.Recv(torch.empty(n), p, 7)\n"
+        "    assert float(y[0]) == p + 1 and float(y[-1]) == p + 1\n"
+        "for h in hs: c.Wait(h)\n"
+        "acc = torch.ones(8 << 20)\n"
+        "z = c.AllreduceFused(torch.full((8 << 20,), float(R)), m.MPI_SUM, 0.5, acc)\n"
+        "assert float(z[0]) == 1 + 0.5 * sum(range(P)) and float(z[-1]) == float(z[0])\n"
+        "sub = c.Split(R % 2, R)\n"
+        "a = sub.Allreduce(torch.tensor([float(R)]), m.MPI_SUM)\n"
+        "b = c.Allreduce(torch.tensor([1.0]), m.MPI_SUM)\n"
+        "g = sub.Allgather(torch.tensor([float(R)]), 0)\n"
+        "assert float(a) == sum(r for r in range(P) if r % 2 == R % 2) and float(b) == P\n"
+        "assert g.tolist() == [float(r) for r in range(P) if r % 2 == R % 2]\n"
+        "sub.Free()\n"
+        "c.Barrier()\n"
+        "if R == 0: print('BIG OK', flush=True)\n")
+    res = run_spmd(4, [str(script)], device="cpu", timeout=600, extra_env={"M4T_NET": "1"})
+    assert res.returncode == 0, res.stderr[-4000:]
+    assert "BIG OK" in res.stdout
