@@ -7,6 +7,11 @@
 namespace m4t {
 
 namespace {
+// grow-only scratch: large collectives reuse the same pages instead of faulting fresh ones in on every call
+void grow(NetBuffer& b, size_t n) {
+  if (b.size() < n) b.allocate(n + n / 4);
+}
+
 constexpr int64_t kDirectBytes = 64 * 1024;  // below: every rank receives every contribution
 constexpr int kDescWords = 8;                // src_off, n[3], ss[3], run
 
@@ -49,10 +54,11 @@ void unpack_box(const SlabJob& j, const char* src, char* dst, int64_t es) {
 
 // Serves the box requests of every peer out of `in` and returns the packed answers (kept alive by the caller until
 // the sends are complete).  reqs[p] = descriptor words received from p.
-void serve_requests(NetLink& link, int64_t data_tag, const std::vector<std::vector<char>>& reqs, const char* in, int64_t es,
-                    std::vector<std::vector<char>>& answers, std::vector<uint64_t>& ops) {
+void serve_requests(NetLink& link, int64_t data_tag, const std::vector<NetBuffer>& reqs, const char* in, int64_t es,
+                    std::vector<NetBuffer>& answers, std::vector<uint64_t>& ops) {
   const int P = link.size(), r = link.rank();
-  answers.assign(static_cast<size_t>(P), {});
+  answers.clear();
+  answers.resize(static_cast<size_t>(P));
   for (int p = 0; p < P; ++p) {
     if (p == r || reqs[static_cast<size_t>(p)].empty()) continue;
     const auto* w = reinterpret_cast<const int64_t*>(reqs[static_cast<size_t>(p)].data());
@@ -60,7 +66,7 @@ void serve_requests(NetLink& link, int64_t data_tag, const std::vector<std::vect
     size_t total = 0;
     for (size_t k = 0; k < njobs; ++k) total += static_cast<size_t>(read_desc(w + k * kDescWords).elems() * es);
     auto& buf = answers[static_cast<size_t>(p)];
-    buf.resize(total);
+    buf.allocate(total);
     char* dst = buf.data();
     for (size_t k = 0; k < njobs; ++k) {
       const SlabJob j = read_desc(w + k * kDescWords);
@@ -87,7 +93,8 @@ void NetBackend::allreduce(const void* in, void* out, int64_t n, DType dt, Reduc
   const void* srcs[kMaxRanks];
   std::vector<uint64_t> ops;
   if (static_cast<int64_t>(bytes) <= kDirectBytes || n < P) {
-    std::vector<char> tmp(bytes * static_cast<size_t>(P - 1));
+    NetBuffer tmp;
+    tmp.allocate(bytes * static_cast<size_t>(P - 1));
     for (int p = 0, k = 0; p < P; ++p) {
       if (p == r) {
         srcs[p] = in;
@@ -107,8 +114,11 @@ void NetBackend::allreduce(const void* in, void* out, int64_t n, DType dt, Reduc
   // backend), then all-gather of the finished slices; every rank sends and receives (P-1)/P of the message twice
   auto lo = [&](int p) { return n * p / P; };
   const int64_t mylo = lo(r), mylen = lo(r + 1) - lo(r);
-  std::vector<char> tmp(static_cast<size_t>(mylen * es) * static_cast<size_t>(P - 1));
-  std::vector<char> res(static_cast<size_t>(mylen * es));
+  NetBuffer& tmp = scratch_[0];
+  NetBuffer& res = scratch_[1];
+  grow(tmp, static_cast<size_t>(mylen * es) * static_cast<size_t>(P - 1));
+  grow(res, static_cast<size_t>(mylen * es));
+  const size_t res_bytes = static_cast<size_t>(mylen * es);
   for (int p = 0, k = 0; p < P; ++p) {
     if (p == r) {
       srcs[p] = static_cast<const char*>(in) + mylo * es;
@@ -129,14 +139,14 @@ void NetBackend::allreduce(const void* in, void* out, int64_t n, DType dt, Reduc
   e1.has_scale = epi.has_scale;
   M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, P, res.data(), 0, mylen, &e1);
   // phase 2 (accumulate fused while the slices land)
-  std::vector<char> land;
-  if (epi.accumulate) land.resize(bytes);
+  NetBuffer& land = scratch_[2];
+  if (epi.accumulate) grow(land, bytes);
   char* dst = epi.accumulate ? land.data() : static_cast<char*>(out);
   for (int p = 0; p < P; ++p)
     if (p != r) ops.push_back(link_->recv(p, kNetColl, tag + 1, dst + lo(p) * es, static_cast<size_t>((lo(p + 1) - lo(p)) * es)));
   for (int p = 0; p < P; ++p)
-    if (p != r) ops.push_back(link_->send(p, kNetColl, tag + 1, res.data(), res.size()));
-  if (mylen) std::memcpy(dst + mylo * es, res.data(), res.size());
+    if (p != r) ops.push_back(link_->send(p, kNetColl, tag + 1, res.data(), res_bytes));
+  if (mylen) std::memcpy(dst + mylo * es, res.data(), res_bytes);
   eng.wait_all(ops);
   if (epi.accumulate) {
     M4T_DISPATCH_DTYPE_OP(dt, ReduceOp::SUM, CpuAccumulateCopy, land.data(), epi.accumulate, out, 0, n);
@@ -186,7 +196,8 @@ void NetBackend::reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, v
     return;
   }
   // the root combines the contributions in rank order (same result as the shared-memory backend)
-  std::vector<char> tmp(bytes * static_cast<size_t>(P - 1));
+  NetBuffer tmp;
+  tmp.allocate(bytes * static_cast<size_t>(P - 1));
   const void* srcs[kMaxRanks];
   std::vector<uint64_t> ops;
   for (int p = 0, k = 0; p < P; ++p) {
@@ -230,21 +241,21 @@ void NetBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt,
       sends.push_back(link_->send(p, kNetColl, req_tag, want[static_cast<size_t>(p)].data(),
                                   want[static_cast<size_t>(p)].size() * sizeof(int64_t)));
   // answers I expect
-  std::vector<std::vector<char>> got(static_cast<size_t>(P));
+  std::vector<NetBuffer> got(static_cast<size_t>(P));
   std::vector<uint64_t> data_recv(static_cast<size_t>(P), 0);
   for (int p = 0; p < P; ++p) {
     if (p == r || mine[static_cast<size_t>(p)].empty()) continue;
     size_t total = 0;
     for (const SlabJob* j : mine[static_cast<size_t>(p)]) total += static_cast<size_t>(j->elems() * es);
-    got[static_cast<size_t>(p)].resize(total);
+    got[static_cast<size_t>(p)].allocate(total);
     data_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, data_tag, got[static_cast<size_t>(p)].data(), total);
   }
   for (const auto& j : plan.jobs)
     if (j.peer == r) copy_rows(j, cin, cout, es);
-  std::vector<std::vector<char>> reqs(static_cast<size_t>(P));
+  std::vector<NetBuffer> reqs(static_cast<size_t>(P));
   for (int p = 0; p < P; ++p)
     if (p != r) eng.wait(req_recv[static_cast<size_t>(p)], &reqs[static_cast<size_t>(p)]);
-  std::vector<std::vector<char>> answers;
+  std::vector<NetBuffer> answers;
   serve_requests(*link_, data_tag, reqs, cin, es, answers, sends);
   for (int p = 0; p < P; ++p) {
     if (!data_recv[static_cast<size_t>(p)]) continue;
@@ -283,19 +294,19 @@ void NetBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out, 
   for (int p = 0; p < P; ++p)
     if (p != r) sends.push_back(link_->send(p, kNetColl, req_tag, want.data(), want.size() * sizeof(int64_t)));
   const size_t box_bytes = plan.out_elems > 0 ? static_cast<size_t>(plan.box.elems() * es) : 0;
-  std::vector<std::vector<char>> got(static_cast<size_t>(P));
+  std::vector<NetBuffer> got(static_cast<size_t>(P));
   std::vector<uint64_t> data_recv(static_cast<size_t>(P), 0);
   if (box_bytes) {
     for (int p = 0; p < P; ++p) {
-      got[static_cast<size_t>(p)].resize(box_bytes);
+      got[static_cast<size_t>(p)].allocate(box_bytes);
       if (p != r) data_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, data_tag, got[static_cast<size_t>(p)].data(), box_bytes);
     }
     pack_box(plan.box, cin, got[static_cast<size_t>(r)].data(), es);
   }
-  std::vector<std::vector<char>> reqs(static_cast<size_t>(P));
+  std::vector<NetBuffer> reqs(static_cast<size_t>(P));
   for (int p = 0; p < P; ++p)
     if (p != r) eng.wait(req_recv[static_cast<size_t>(p)], &reqs[static_cast<size_t>(p)]);
-  std::vector<std::vector<char>> answers;
+  std::vector<NetBuffer> answers;
   serve_requests(*link_, data_tag, reqs, cin, es, answers, sends);
   if (box_bytes) {
     for (int p = 0; p < P; ++p) {
@@ -346,7 +357,7 @@ void NetBackend::wait(int64_t request, void*) {
   }
   void* dst = rb->second;
   recv_bufs_.erase(rb);
-  std::vector<char> data;
+  NetBuffer data;
   const size_t n = link_->engine().wait(op, &data);
   if (n) std::memcpy(dst, data.data(), n);
 }

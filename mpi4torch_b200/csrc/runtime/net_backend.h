@@ -43,6 +43,7 @@ class NetBackend final : public Backend {
   std::unordered_map<int64_t, uint64_t> requests_;  // request id -> engine operation
   std::unordered_map<int64_t, void*> recv_bufs_;    // receive requests: where Wait copies the message
   int64_t next_request_ = 1;
+  NetBuffer scratch_[3];  // grow-only temporaries of the large-message Allreduce
 };
 
 }  // namespace m4t

@@ -222,7 +222,7 @@ uint64_t NetEngine::post_send(int peer, uint32_t comm, uint32_t kind, int64_t ta
         fail("message truncated: " + std::to_string(bytes) + " bytes (tag " + std::to_string(tag) + ") into a " +
              std::to_string(r.cap) + "-byte receive buffer");
       r.bytes = bytes;
-      if (r.engine_buffer) r.owned.assign(static_cast<const char*>(data), static_cast<const char*>(data) + bytes);
+      if (r.engine_buffer) r.owned.assign(data, bytes);
       else if (bytes) std::memcpy(r.data, data, bytes);
       r.done = true;
       pr.posted.erase(it);
@@ -230,13 +230,13 @@ uint64_t NetEngine::post_send(int peer, uint32_t comm, uint32_t kind, int64_t ta
     }
     Unexpected u;
     u.h = h;
-    u.data.assign(static_cast<const char*>(data), static_cast<const char*>(data) + bytes);
+    u.data.assign(data, bytes);
     u.complete = true;
     pr.ux.push_back(std::move(u));
     return id;
   }
   if (pr.closed) fail("rank " + std::to_string(peer) + " has closed its connection");
-  if (copy && bytes) o.owned.assign(static_cast<const char*>(data), static_cast<const char*>(data) + bytes);
+  if (copy && bytes) o.owned.assign(data, bytes);
   ops_[id] = std::move(o);
   const char* src = (copy && bytes) ? ops_.at(id).owned.data() : static_cast<const char*>(data);
   pr.sendq.push_back(SendItem{h, src, 0, id});
@@ -297,7 +297,7 @@ void NetEngine::frame_started(int p) {
       fail("message truncated: " + std::to_string(h.bytes) + " bytes sent by rank " + std::to_string(p) + " (tag " +
            std::to_string(h.tag) + ") into a " + std::to_string(o.cap) + "-byte receive buffer");
     if (o.engine_buffer) {
-      o.owned.resize(h.bytes);
+      o.owned.allocate(h.bytes);
       o.data = o.owned.data();
     }
     o.bytes = h.bytes;
@@ -310,7 +310,7 @@ void NetEngine::frame_started(int p) {
   pr.ux.emplace_back();
   Unexpected& u = pr.ux.back();
   u.h = h;
-  u.data.resize(h.bytes);
+  u.data.allocate(h.bytes);
   pr.in_ux = &u;
   pr.in_dst = u.data.data();
   if (h.bytes == 0) frame_finished(p);
@@ -437,7 +437,7 @@ bool NetEngine::test(uint64_t op) {
   return it->second.done;
 }
 
-size_t NetEngine::wait(uint64_t op, std::vector<char>* owned) {
+size_t NetEngine::wait(uint64_t op, NetBuffer* owned) {
   auto it = ops_.find(op);
   M4T_CHECK(it != ops_.end(), "tcp transport: unknown or already completed operation");
   uint64_t start = 0;

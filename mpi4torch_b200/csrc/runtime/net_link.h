@@ -13,6 +13,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <deque>
 #include <list>
 #include <memory>
@@ -27,6 +28,24 @@ namespace m4t {
 constexpr uint32_t kNetCtrl = 1;  // barrier / metadata words
 constexpr uint32_t kNetColl = 2;  // collective payload
 constexpr uint32_t kNetP2p = 3;   // user Isend / Irecv
+
+// Byte buffer without value-initialisation (a std::vector<char> would zero-fill - and page-fault - every message).
+struct NetBuffer {
+  std::unique_ptr<char[]> ptr;
+  size_t bytes = 0;
+  void allocate(size_t n) {
+    ptr.reset(n ? new char[n] : nullptr);
+    bytes = n;
+  }
+  void assign(const void* src, size_t n) {
+    allocate(n);
+    if (n) std::memcpy(ptr.get(), src, n);
+  }
+  char* data() { return ptr.get(); }
+  const char* data() const { return ptr.get(); }
+  size_t size() const { return bytes; }
+  bool empty() const { return bytes == 0; }
+};
 
 class NetEngine {
  public:
@@ -51,7 +70,7 @@ class NetEngine {
   // data == nullptr: the engine allocates the buffer (any size up to cap), fetch it through wait()'s `owned`.
   uint64_t post_recv(int peer, uint32_t comm, uint32_t kind, int64_t tag, void* data, size_t cap);
   // Progresses until the operation is complete; returns the message size; forgets the operation.
-  size_t wait(uint64_t op, std::vector<char>* owned = nullptr);
+  size_t wait(uint64_t op, NetBuffer* owned = nullptr);
   void wait_all(const std::vector<uint64_t>& ops);
   // true if the operation is complete (makes one non-blocking progress pass first)
   bool test(uint64_t op);
@@ -71,7 +90,7 @@ class NetEngine {
     int64_t tag = 0;
     char* data = nullptr;
     size_t cap = 0, bytes = 0;
-    std::vector<char> owned;
+    NetBuffer owned;
   };
   struct SendItem {
     Header h;
@@ -81,7 +100,7 @@ class NetEngine {
   };
   struct Unexpected {
     Header h;
-    std::vector<char> data;
+    NetBuffer data;
     bool complete = false;
     uint64_t claimed = 0;  // posted receive waiting for the rest of this frame
   };
