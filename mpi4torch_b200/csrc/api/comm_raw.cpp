@@ -197,7 +197,10 @@ void Communicator::Barrier() {
 std::string Communicator::Describe() const {
   std::ostringstream o;
   o << "mpi4torch_b200 communicator rank " << rank_ << "/" << size_ << " job " << cx().job_id()
-    << (cx().over_network() ? " | host: tcp mesh (job spans nodes; CUDA tensors are staged through host memory)" : " | cpu: posix-shm");
+    << (cx().over_network() ? (cx().hierarchical() ? " | host: tcp mesh + shared memory inside the node (hierarchical Allreduce)"
+                                                    : " | host: tcp mesh")
+                            : " | cpu: posix-shm");
+  if (cx().over_network()) o << " (job spans nodes; CUDA tensors are staged through host memory)";
   if (cx().cuda_ready()) o << " | " << cx().cuda()->describe();
   if (world_->host_staging()) o << " | host staging forced";
   return o.str();

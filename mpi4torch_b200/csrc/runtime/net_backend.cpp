@@ -2,6 +2,7 @@
 
 #include <cstring>
 
+#include "cpu_backend.h"
 #include "host_kernels.h"
 
 namespace m4t {
@@ -360,6 +361,77 @@ void NetBackend::wait(int64_t request, void*) {
   NetBuffer data;
   const size_t n = link_->engine().wait(op, &data);
   if (n) std::memcpy(dst, data.data(), n);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+
+namespace {
+template <DType DT> void widen_to_f32(const void* src, float* dst, int64_t n) {
+  using E = Elem<DT>;
+  const auto* s = static_cast<const typename E::storage*>(src);
+  for (int64_t i = 0; i < n; ++i) dst[i] = E::load(s[i]);
+}
+// out = round(val [+ acc]): the one rounding of the 16-bit float contract
+template <DType DT> void narrow_from_f32(const float* val, const void* acc, void* out, int64_t n) {
+  using E = Elem<DT>;
+  const auto* a = static_cast<const typename E::storage*>(acc);
+  auto* o = static_cast<typename E::storage*>(out);
+  if (a)
+    for (int64_t i = 0; i < n; ++i) o[i] = E::store(val[i] + E::load(a[i]));
+  else
+    for (int64_t i = 0; i < n; ++i) o[i] = E::store(val[i]);
+}
+}  // namespace
+
+void HierBackend::allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi, void*) {
+  check_op_dtype(op, dt);
+  const int L = local_.size(), l = local_.rank();
+  if (dt == DType::BF16 || dt == DType::F16) {
+    // 16-bit floats accumulate in fp32 and are rounded ONCE (the contract of every backend): the three steps run on an
+    // fp32 copy, the result is narrowed at the end together with the accumulate operand
+    grow(wide_in_, static_cast<size_t>(n) * sizeof(float));
+    grow(wide_out_, static_cast<size_t>(n) * sizeof(float));
+    auto* wi = reinterpret_cast<float*>(wide_in_.data());
+    auto* wo = reinterpret_cast<float*>(wide_out_.data());
+    if (dt == DType::BF16) widen_to_f32<DType::BF16>(in, wi, n);
+    else widen_to_f32<DType::F16>(in, wi, n);
+    Epilogue e32;
+    e32.scale = epi.scale;
+    e32.has_scale = epi.has_scale;
+    allreduce(wi, wo, n, DType::F32, op, e32, nullptr);
+    if (dt == DType::BF16) narrow_from_f32<DType::BF16>(wo, epi.accumulate, out, n);
+    else narrow_from_f32<DType::F16>(wo, epi.accumulate, out, n);
+    return;
+  }
+  const int64_t es = dtype_size(dt);
+  Epilogue scale_only;
+  scale_only.scale = epi.scale;
+  scale_only.has_scale = epi.has_scale;
+  if (n < 4 * L || n * es <= 4096) {
+    // latency-bound: one shared-memory Allreduce, then every rank reduces the (tiny) vector along its rail
+    grow(part_, static_cast<size_t>(n * es));
+    local_.allreduce(in, part_.data(), n, dt, op, Epilogue{}, nullptr);
+    rail_.allreduce(part_.data(), out, n, dt, op, epi, nullptr);
+    return;
+  }
+  std::vector<int64_t> counts(static_cast<size_t>(L));
+  for (int i = 0; i < L; ++i) counts[static_cast<size_t>(i)] = n * (i + 1) / L - n * i / L;
+  const int64_t mine = counts[static_cast<size_t>(l)];
+  grow(part_, static_cast<size_t>(mine * es));
+  // 1. inside the node: local rank i receives the node's sum of slice i
+  const ReducePlan rs = plan_reduce_scatter(l, L, 1, 1, counts);
+  local_.reduce_pull(rs, in, part_.data(), dt, op, Epilogue{}, nullptr);
+  // 2. between the nodes: the ranks with the same local index combine their slices (scale fused)
+  rail_.allreduce(part_.data(), part_.data(), mine, dt, op, scale_only, nullptr);
+  // 3. inside the node: every local rank collects all finished slices (accumulate fused afterwards)
+  const PullPlan ag = plan_gather(l, L, 0, 1, 1, counts, /*all=*/true);
+  if (epi.accumulate) {
+    grow(land_, static_cast<size_t>(n * es));
+    local_.pull(ag, part_.data(), land_.data(), dt, nullptr);
+    M4T_DISPATCH_DTYPE_OP(dt, ReduceOp::SUM, CpuAccumulateCopy, land_.data(), epi.accumulate, out, 0, n);
+  } else {
+    local_.pull(ag, part_.data(), out, dt, nullptr);
+  }
 }
 
 }  // namespace m4t

@@ -46,4 +46,49 @@ class NetBackend final : public Backend {
   NetBuffer scratch_[3];  // grow-only temporaries of the large-message Allreduce
 };
 
+// Host backend of a job that spans nodes with the same number of ranks on each: Allreduce is done in three steps -
+// reduce-scatter inside the node through shared memory (local rank i ends up with slice i), Allreduce of that slice
+// between the ranks that have the same local index on every node (one TCP "rail" per local rank, so all of a node's
+// ranks drive the network at the same time and only 1/L of the message crosses it per rank), all-gather inside the
+// node.  Every other operation goes to the flat mesh backend.  The same structure is what a device path would use
+// (NVLink inside the node instead of shared memory).
+class CpuBackend;
+class HierBackend final : public Backend {
+ public:
+  HierBackend(CpuBackend& local, NetBackend& flat, std::shared_ptr<NetLink> rail)
+      : local_(local), flat_(flat), rail_link_(std::move(rail)), rail_(rail_link_) {}
+
+  const char* name() const override { return "shm+tcp"; }
+  int rank() const override { return flat_.rank(); }
+  int size() const override { return flat_.size(); }
+
+  void allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
+                 void* stream) override;
+  void bcast(void* buf, int64_t n, DType dt, int root, void* stream) override { flat_.bcast(buf, n, dt, root, stream); }
+  void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override {
+    flat_.reduce(buf, n, dt, op, root, stream);
+  }
+  void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override {
+    flat_.pull(plan, in, out, dt, stream);
+  }
+  void reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,
+                   void* stream) override {
+    flat_.reduce_pull(plan, in, out, dt, op, epi, stream);
+  }
+  int64_t isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) override {
+    return flat_.isend(buf, bytes, dest, tag, stream);
+  }
+  int64_t irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) override {
+    return flat_.irecv(buf, bytes, source, tag, stream);
+  }
+  void wait(int64_t request, void* stream) override { flat_.wait(request, stream); }
+
+ private:
+  CpuBackend& local_;
+  NetBackend& flat_;
+  std::shared_ptr<NetLink> rail_link_;
+  NetBackend rail_;
+  NetBuffer part_, land_, wide_in_, wide_out_;
+};
+
 }  // namespace m4t

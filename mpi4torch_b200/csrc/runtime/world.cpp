@@ -15,11 +15,33 @@ CommContext::CommContext(int rank, int size, const std::string& job_id) : job_id
   cpu_ = std::make_unique<CpuBackend>(*ctl_);
 }
 
-CommContext::CommContext(std::shared_ptr<NetLink> link, const std::string& job_id) : job_id_(job_id), net_(std::move(link)) {
-  // a private one-rank segment keeps the shared-memory classes valid; nothing is exchanged through it
-  ctl_ = std::make_unique<Control>(0, 1, job_id + "_n" + std::to_string(net_->engine().rank()));
-  cpu_ = std::make_unique<CpuBackend>(*ctl_);
+CommContext::CommContext(std::shared_ptr<NetLink> link, const std::string& job_id, int local_rank, int local_size)
+    : job_id_(job_id), net_(std::move(link)) {
   netbe_ = std::make_unique<NetBackend>(net_);
+  // do all nodes hold `local_size` consecutive ranks?  (every rank checks the same numbers)
+  const int P = net_->size(), r = net_->rank();
+  bool uniform = local_size > 1 && local_size < P && P % local_size == 0 && r % local_size == local_rank;
+  {
+    const int64_t mine[2] = {local_size, uniform ? 1 : 0};
+    std::vector<int64_t> all(static_cast<size_t>(P) * 2);
+    net_->allgather_i64(mine, 2, all.data());
+    for (int p = 0; p < P; ++p) uniform = uniform && all[static_cast<size_t>(p) * 2] == local_size && all[static_cast<size_t>(p) * 2 + 1] == 1;
+  }
+  if (uniform) {
+    // the ranks of this node share a control segment and arenas; one TCP rail per local index connects the nodes
+    const int node = r / local_size, nodes = P / local_size;
+    ctl_ = std::make_unique<Control>(local_rank, local_size, job_id + "_node" + std::to_string(node));
+    cpu_ = std::make_unique<CpuBackend>(*ctl_);
+    std::vector<int> rail;
+    for (int k = 0; k < nodes; ++k) rail.push_back(net_->members()[static_cast<size_t>(k * local_size + local_rank)]);
+    auto rail_link = std::make_shared<NetLink>(net_->engine_ptr(), net_comm_id(job_id + "_rail" + std::to_string(local_rank)),
+                                               std::move(rail), node);
+    hier_ = std::make_unique<HierBackend>(*cpu_, *netbe_, std::move(rail_link));
+  } else {
+    // a private one-rank segment keeps the shared-memory classes valid; nothing is exchanged through it
+    ctl_ = std::make_unique<Control>(0, 1, job_id + "_n" + std::to_string(net_->engine().rank()));
+    cpu_ = std::make_unique<CpuBackend>(*ctl_);
+  }
 }
 
 CommContext::~CommContext() { shutdown(); }
@@ -30,6 +52,7 @@ void CommContext::shutdown() {
   if (net_) net_->quiesce();
   ctl_->quiesce(static_cast<double>(env_i64("M4T_EXIT_TIMEOUT_S", 10)));
   cuda_.reset();
+  hier_.reset();
   netbe_.reset();
   net_.reset();
   cpu_.reset();
@@ -64,7 +87,15 @@ World::World() {
     std::vector<int> members(static_cast<size_t>(env_.size));
     for (int p = 0; p < env_.size; ++p) members[static_cast<size_t>(p)] = p;
     auto link = std::make_shared<NetLink>(g_engine, net_comm_id(env_.job_id + "_world"), std::move(members), env_.rank);
-    ctx_ = std::make_shared<CommContext>(std::move(link), env_.job_id);
+    // ranks per node: LOCAL_WORLD_SIZE as the launchers export it (M4T_NET_LOCAL_SIZE overrides: simulated nodes)
+    int64_t local_size = env_i64("M4T_NET_LOCAL_SIZE", 0);
+    int local_rank = env_.local_rank;
+    if (local_size > 0) {
+      local_rank = env_.rank % static_cast<int>(local_size);
+    } else {
+      local_size = env_i64("LOCAL_WORLD_SIZE", 1);
+    }
+    ctx_ = std::make_shared<CommContext>(std::move(link), env_.job_id, local_rank, static_cast<int>(local_size));
   } else {
     ctx_ = std::make_shared<CommContext>(env_.rank, env_.size, env_.job_id);
   }

@@ -28,7 +28,9 @@ class CommContext {
   CommContext(int rank, int size, const std::string& job_id);
   // Job that spans nodes: the communicator lives on the TCP mesh (net_link.h).  The shared-memory control segment
   // then only holds this process (nothing is shared through it) and there is no CUDA backend.
-  CommContext(std::shared_ptr<NetLink> link, const std::string& job_id);
+  // With local_size > 1 (the same number of ranks on every node, ranks numbered node by node) the ranks of one node
+  // additionally share a control segment and Allreduce becomes hierarchical (HierBackend, net_backend.h).
+  CommContext(std::shared_ptr<NetLink> link, const std::string& job_id, int local_rank = 0, int local_size = 1);
   ~CommContext();
   int rank() const { return net_ ? net_->rank() : ctl_->rank(); }
   int size() const { return net_ ? net_->size() : ctl_->size(); }
@@ -36,7 +38,11 @@ class CommContext {
   Control& control() { return *ctl_; }
   CpuBackend& cpu() { return *cpu_; }
   // the backend that moves host tensors: POSIX shared memory on one node, TCP across nodes
-  Backend& host() { return net_ ? static_cast<Backend&>(*netbe_) : static_cast<Backend&>(*cpu_); }
+  Backend& host() {
+    if (hier_) return *hier_;
+    return net_ ? static_cast<Backend&>(*netbe_) : static_cast<Backend&>(*cpu_);
+  }
+  bool hierarchical() const { return hier_ != nullptr; }
   bool over_network() const { return net_ != nullptr; }
   const std::shared_ptr<NetLink>& net() const { return net_; }
   // host control operations of the communicator (shared-memory flags or TCP messages)
@@ -61,6 +67,7 @@ class CommContext {
   std::unique_ptr<CudaBackend> cuda_;
   std::shared_ptr<NetLink> net_;
   std::unique_ptr<NetBackend> netbe_;
+  std::unique_ptr<HierBackend> hier_;
   uint64_t split_seq_ = 0;
 };
 

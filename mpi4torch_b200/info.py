@@ -67,6 +67,7 @@ KNOBS: Dict[str, Tuple[str, str]] = {
     # ---- jobs that span nodes (TCP mesh)
     "M4T_NET": ("", "1 forces the TCP mesh on one node (tests), 0 forbids it; default: when LOCAL_WORLD_SIZE < WORLD_SIZE"),
     "M4T_NET_IFADDR": ("", "address other nodes should use to reach this rank (default: the one that routes to MASTER_ADDR)"),
+    "M4T_NET_LOCAL_SIZE": ("", "ranks per node for the hierarchical Allreduce (default LOCAL_WORLD_SIZE; tests simulate nodes with it)"),
     "M4T_STORE_HOSTED": ("0", "1 = a launcher hosts the rendezvous store at MASTER_ADDR:MASTER_PORT (else rank 0 does)"),
     # ---- rendezvous (normally set by the launcher or torchrun)
     "M4T_RANK": ("", "rank when RANK is not set"),

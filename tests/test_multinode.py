@@ -36,6 +36,48 @@ def test_spmd_suites_over_the_tcp_mesh(nprocs):
     assert f"SPMD suite np={nprocs}" in res.stdout and "ok=True" in res.stdout
 
 
+@pytest.mark.parametrize("nprocs,per_node", [(4, 2), (6, 3)])
+def test_spmd_suites_with_hierarchical_allreduce(nprocs, per_node):
+    """Simulated nodes of `per_node` ranks: Allreduce = shared-memory reduce-scatter inside the node, one TCP rail per
+    local rank between the nodes, shared-memory all-gather (HierBackend); 16-bit floats still round once."""
+    res = run_spmd(nprocs, ["tests/spmd/run_all.py"], device="cpu", timeout=900,
+                   extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
+    assert res.returncode == 0, f"np={nprocs}\nSTDOUT:\n{res.stdout[-4000:]}\nSTDERR:\n{res.stderr[-8000:]}"
+    assert f"SPMD suite np={nprocs}" in res.stdout and "ok=True" in res.stdout
+
+
+def test_hierarchical_allreduce_values_all_sizes_and_dtypes(tmp_path):
+    script = tmp_path / "hier.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R, P = c.rank, c.size\n"
+        "assert 'hierarchical' in c.describe(), c.describe()\n"
+        "for n in (1, 3, 7, 100, 4096, 100003, 1 << 20):\n"
+        "    for dt in (torch.float64, torch.float32, torch.int32, torch.bfloat16, torch.float16):\n"
+        "        x = (torch.arange(n) % 13 + R).to(dt)\n"
+        "        ref = sum(((torch.arange(n) % 13 + r).to(torch.float64)) for r in range(P))\n"
+        "        tol = dict(rtol=2 ** -7, atol=0) if dt in (torch.bfloat16, torch.float16) else dict(rtol=1e-12, atol=0)\n"
+        "        assert torch.allclose(c.Allreduce(x, m.MPI_SUM).double(), ref, **tol), (n, dt)\n"
+        "        if dt == torch.int32: continue\n"
+        "        z = c.AllreduceFused(x, m.MPI_SUM, 0.5, torch.ones(n, dtype=dt))\n"
+        "        assert torch.allclose(z.double(), 1 + 0.5 * ref, **tol), (n, dt)\n"
+        "    assert float(c.Allreduce(torch.full((n,), float(R)), m.MPI_MAX).min()) == P - 1\n"
+        "    la = c.Allreduce((torch.arange(n) % (R + 2) == 0).float() * 3, m.MPI_LAND)\n"
+        "    ref = torch.ones(n, dtype=torch.bool)\n"
+        "    for r in range(P): ref &= (torch.arange(n) % (r + 2) == 0)\n"
+        "    assert torch.equal(la.bool(), ref)\n"
+        "x = torch.ones(5, requires_grad=True)\n"
+        "c.Allreduce(x * (R + 1), m.MPI_SUM).sum().backward()\n"
+        "assert float(x.grad[0]) == P * (R + 1)\n"
+        "c.Barrier()\n"
+        "if R == 0: print('HIER OK', flush=True)\n")
+    for nprocs, per_node in ((6, 2), (8, 4)):
+        res = run_spmd(nprocs, [str(script)], device="cpu", timeout=600,
+                       extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
+        assert res.returncode == 0, res.stderr[-4000:]
+        assert "HIER OK" in res.stdout
+
+
 def test_two_nodes_two_ranks_each_one_launcher_per_node():
     """2 x 2 ranks: node 0's launcher hosts the rendezvous store, both launchers number their ranks node by node, and
     the full SPMD test set passes at world size 4."""
