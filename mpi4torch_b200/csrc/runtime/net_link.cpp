@@ -268,20 +268,6 @@ uint64_t NetEngine::post_recv(int peer, uint32_t comm, uint32_t kind, int64_t ta
   return id;
 }
 
-void NetEngine::cancel_recv(uint64_t op) {
-  auto it = ops_.find(op);
-  if (it == ops_.end()) return;
-  Peer& pr = peers_[static_cast<size_t>(it->second.peer)];
-  pr.posted.remove(op);
-  for (auto& u : pr.ux)
-    if (u.claimed == op) u.claimed = 0;
-  if (pr.in_active && pr.in_op == op) {
-    // the frame is being written into the caller's buffer: cannot be abandoned half way
-    fail("cannot cancel a receive whose message is already arriving");
-  }
-  ops_.erase(it);
-}
-
 void NetEngine::frame_started(int p) {
   Peer& pr = peers_[static_cast<size_t>(p)];
   const Header& h = pr.in_h;
@@ -428,13 +414,6 @@ void NetEngine::check_peer_alive(const Op& o) const {
   if (o.peer != rank_ && peers_[static_cast<size_t>(o.peer)].closed && !o.done)
     fail("rank " + std::to_string(o.peer) + " closed its connection (the process ended or raised) while this rank was " +
          (o.is_recv ? "waiting for a message from it" : "sending to it"));
-}
-
-bool NetEngine::test(uint64_t op) {
-  progress(0);
-  auto it = ops_.find(op);
-  M4T_CHECK(it != ops_.end(), "tcp transport: unknown operation");
-  return it->second.done;
 }
 
 size_t NetEngine::wait(uint64_t op, NetBuffer* owned) {

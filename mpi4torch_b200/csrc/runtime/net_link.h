@@ -72,10 +72,6 @@ class NetEngine {
   // Progresses until the operation is complete; returns the message size; forgets the operation.
   size_t wait(uint64_t op, NetBuffer* owned = nullptr);
   void wait_all(const std::vector<uint64_t>& ops);
-  // true if the operation is complete (makes one non-blocking progress pass first)
-  bool test(uint64_t op);
-  // Drops a posted receive that will never be matched (error paths).
-  void cancel_recv(uint64_t op);
 
  private:
   struct Header {
