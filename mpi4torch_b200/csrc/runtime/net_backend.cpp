@@ -365,6 +365,25 @@ void NetBackend::wait(int64_t request, void*) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 
+int64_t HierBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) {
+  M4T_CHECK(dest >= 0 && dest < size(), "Isend: destination rank " << dest << " out of range");
+  const int L = local_.size(), node = rank() / L;
+  if (dest / L == node) return (local_.isend(buf, bytes, dest % L, tag, stream) << 1) | 1;
+  return flat_.isend(buf, bytes, dest, tag, stream) << 1;
+}
+
+int64_t HierBackend::irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) {
+  M4T_CHECK(source >= 0 && source < size(), "Irecv: source rank " << source << " out of range");
+  const int L = local_.size(), node = rank() / L;
+  if (source / L == node) return (local_.irecv(buf, bytes, source % L, tag, stream) << 1) | 1;
+  return flat_.irecv(buf, bytes, source, tag, stream) << 1;
+}
+
+void HierBackend::wait(int64_t request, void* stream) {
+  if (request & 1) local_.wait(request >> 1, stream);
+  else flat_.wait(request >> 1, stream);
+}
+
 namespace {
 template <DType DT> void widen_to_f32(const void* src, float* dst, int64_t n) {
   using E = Elem<DT>;

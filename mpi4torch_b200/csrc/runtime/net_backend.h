@@ -75,13 +75,11 @@ class HierBackend final : public Backend {
                    void* stream) override {
     flat_.reduce_pull(plan, in, out, dt, op, epi, stream);
   }
-  int64_t isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) override {
-    return flat_.isend(buf, bytes, dest, tag, stream);
-  }
-  int64_t irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) override {
-    return flat_.irecv(buf, bytes, source, tag, stream);
-  }
-  void wait(int64_t request, void* stream) override { flat_.wait(request, stream); }
+  // point-to-point: a peer on this node is reached through the node's shared memory, any other through the mesh (a
+  // given source always takes the same route, so per-source FIFO order holds); the low bit of the id says which
+  int64_t isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) override;
+  int64_t irecv(void* buf, int64_t bytes, int source, int64_t tag, void* stream) override;
+  void wait(int64_t request, void* stream) override;
 
  private:
   CpuBackend& local_;
