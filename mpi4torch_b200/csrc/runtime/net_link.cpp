@@ -420,9 +420,13 @@ size_t NetEngine::wait(uint64_t op, NetBuffer* owned) {
   auto it = ops_.find(op);
   M4T_CHECK(it != ops_.end(), "tcp transport: unknown or already completed operation");
   uint64_t start = 0;
+  int spins = 0;
   while (!it->second.done) {
     check_peer_alive(it->second);
-    progress(50);
+    // answers of a peer that is already inside the matching call arrive within microseconds: look a few times without
+    // sleeping before paying a scheduler wake-up
+    progress(spins < 200 ? 0 : 50);
+    ++spins;
     if (!it->second.done) {
       if (start == 0) start = now_ns();
       if (static_cast<double>(now_ns() - start) > timeout_s_ * 1e9)
