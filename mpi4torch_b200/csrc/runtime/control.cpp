@@ -120,6 +120,7 @@ Control::~Control() {
 
 void Control::backoff(uint64_t& spins) {
   ++spins;
+  if (idle_hook_ && !in_quiesce_ && (spins & 0x3f) == 0) idle_hook_();
   if (spins < 2000) {
 #if defined(__x86_64__)
     __builtin_ia32_pause();
@@ -168,6 +169,7 @@ void Control::barrier() {
 
 bool Control::quiesce(double timeout_s) noexcept {
   if (!cb_ || size_ <= 1) return true;
+  in_quiesce_ = true;  // noexcept path: the idle hook (which may raise) stays out of it
   cb_->departing.fetch_add(1, std::memory_order_acq_rel);
   const uint64_t start = now_ns();
   uint64_t spins = 0;

@@ -12,6 +12,7 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -109,6 +110,10 @@ class Control {
 
   uint64_t next_host_seq() { return ++host_seq_; }
 
+  // Called now and then while a wait on this segment spins.  A job that spans nodes installs the TCP engine's progress
+  // here: a rank that waits for a neighbour on its node must keep moving the bytes it still owes to other nodes.
+  void set_idle_hook(std::function<void()> hook) { idle_hook_ = std::move(hook); }
+
  private:
   void backoff(uint64_t& spins);
   void check_abort_timeout(uint64_t start_ns, const char* what);
@@ -122,6 +127,8 @@ class Control {
   uint64_t host_seq_ = 0;
   uint64_t fd_round_ = 0;
   double timeout_s_;
+  std::function<void()> idle_hook_;
+  bool in_quiesce_ = false;
 };
 
 uint64_t now_ns();

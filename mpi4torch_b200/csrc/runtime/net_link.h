@@ -72,6 +72,8 @@ class NetEngine {
   // Progresses until the operation is complete; returns the message size; forgets the operation.
   size_t wait(uint64_t op, NetBuffer* owned = nullptr);
   void wait_all(const std::vector<uint64_t>& ops);
+  // One non-blocking progress pass (pending sends leave, arriving frames are taken in); for waits outside the engine.
+  void poke() { progress(0); }
 
  private:
   struct Header {

@@ -31,6 +31,14 @@ CommContext::CommContext(std::shared_ptr<NetLink> link, const std::string& job_i
     // the ranks of this node share a control segment and arenas; one TCP rail per local index connects the nodes
     const int node = r / local_size, nodes = P / local_size;
     ctl_ = std::make_unique<Control>(local_rank, local_size, job_id + "_node" + std::to_string(node));
+    {
+      // a rank that spins on its node's shared memory keeps its TCP traffic moving (a buffered Isend to another node
+      // must not stall because its sender entered a node-local wait)
+      std::weak_ptr<NetEngine> eng = net_->engine_ptr();
+      ctl_->set_idle_hook([eng] {
+        if (auto e = eng.lock()) e->poke();
+      });
+    }
     cpu_ = std::make_unique<CpuBackend>(*ctl_);
     std::vector<int> rail;
     for (int k = 0; k < nodes; ++k) rail.push_back(net_->members()[static_cast<size_t>(k * local_size + local_rank)]);

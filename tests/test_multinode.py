@@ -159,3 +159,31 @@ def test_large_messages_both_directions_and_sub_communicators_over_tcp(tmp_path)
     res = run_spmd(4, [str(script)], device="cpu", timeout=600, extra_env={"M4T_NET": "1"})
     assert res.returncode == 0, res.stderr[-4000:]
     assert "BIG OK" in res.stdout
+
+
+def test_node_local_waits_keep_the_network_moving(tmp_path):
+    """Rank 0 posts a large buffered Isend to another node and enters an Allreduce, whose first step waits for rank 1 on
+    the node's shared memory; rank 1 only arrives after a chain of messages that ends at the receiver of that Isend.
+    The shared-memory wait must keep pushing rank 0's bytes (Control's idle hook), otherwise the job deadlocks."""
+    script = tmp_path / "chain.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R = c.rank\n"
+        "n = 16 << 20\n"
+        "if R == 0:\n"
+        "    h = c.Isend(torch.ones(n), 2, 5)\n"
+        "elif R == 2:\n"
+        "    c.Recv(torch.empty(n), 0, 5); c.Send(torch.ones(3), 3, 6)\n"
+        "elif R == 3:\n"
+        "    c.Recv(torch.empty(3), 2, 6); c.Send(torch.ones(3), 1, 7)\n"
+        "elif R == 1:\n"
+        "    c.Recv(torch.empty(3), 3, 7)\n"
+        "z = c.Allreduce(torch.ones(1 << 16), m.MPI_SUM)\n"
+        "if R == 0: c.Wait(h)\n"
+        "assert float(z[0]) == 4\n"
+        "c.Barrier()\n"
+        "if R == 0: print('CHAIN OK', flush=True)\n")
+    res = run_spmd(4, [str(script)], device="cpu", timeout=120,
+                   extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": "2", "M4T_TIMEOUT_S": "30"})
+    assert res.returncode == 0, res.stderr[-4000:]
+    assert "CHAIN OK" in res.stdout
