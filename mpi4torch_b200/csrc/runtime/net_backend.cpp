@@ -64,6 +64,13 @@ void serve_requests(NetLink& link, int64_t data_tag, const std::vector<NetBuffer
     if (p == r || reqs[static_cast<size_t>(p)].empty()) continue;
     const auto* w = reinterpret_cast<const int64_t*>(reqs[static_cast<size_t>(p)].data());
     const size_t njobs = reqs[static_cast<size_t>(p)].size() / (kDescWords * sizeof(int64_t));
+    if (njobs == 1) {
+      const SlabJob j = read_desc(w);
+      if (j.rows() == 1) {  // one contiguous run: straight out of the input, no packing
+        ops.push_back(link.send(p, kNetColl, data_tag, in + j.src_off * es, static_cast<size_t>(j.run * es)));
+        continue;
+      }
+    }
     size_t total = 0;
     for (size_t k = 0; k < njobs; ++k) total += static_cast<size_t>(read_desc(w + k * kDescWords).elems() * es);
     auto& buf = answers[static_cast<size_t>(p)];
@@ -244,10 +251,18 @@ void NetBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt,
   // answers I expect
   std::vector<NetBuffer> got(static_cast<size_t>(P));
   std::vector<uint64_t> data_recv(static_cast<size_t>(P), 0);
+  std::vector<bool> direct(static_cast<size_t>(P), false);
   for (int p = 0; p < P; ++p) {
     if (p == r || mine[static_cast<size_t>(p)].empty()) continue;
+    const auto& js = mine[static_cast<size_t>(p)];
+    if (js.size() == 1 && js[0]->rows() == 1) {  // one contiguous run: straight into the output
+      data_recv[static_cast<size_t>(p)] =
+          link_->recv(p, kNetColl, data_tag, cout + js[0]->dst_off * es, static_cast<size_t>(js[0]->run * es));
+      direct[static_cast<size_t>(p)] = true;
+      continue;
+    }
     size_t total = 0;
-    for (const SlabJob* j : mine[static_cast<size_t>(p)]) total += static_cast<size_t>(j->elems() * es);
+    for (const SlabJob* j : js) total += static_cast<size_t>(j->elems() * es);
     got[static_cast<size_t>(p)].allocate(total);
     data_recv[static_cast<size_t>(p)] = link_->recv(p, kNetColl, data_tag, got[static_cast<size_t>(p)].data(), total);
   }
@@ -261,6 +276,7 @@ void NetBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt,
   for (int p = 0; p < P; ++p) {
     if (!data_recv[static_cast<size_t>(p)]) continue;
     eng.wait(data_recv[static_cast<size_t>(p)]);
+    if (direct[static_cast<size_t>(p)]) continue;
     const char* src = got[static_cast<size_t>(p)].data();
     for (const SlabJob* j : mine[static_cast<size_t>(p)]) {
       unpack_box(*j, src, cout, es);
