@@ -381,6 +381,23 @@ void NetBackend::wait(int64_t request, void*) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 
+void HierBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) {
+  const int L = local_.size(), node = rank() / L;
+  PullPlan near = plan, far = plan;  // same sizes, disjoint job lists (they fill disjoint parts of the output)
+  near.jobs.clear();
+  far.jobs.clear();
+  for (const auto& j : plan.jobs) {
+    if (j.peer / L == node) {
+      near.jobs.push_back(j);
+      near.jobs.back().peer = j.peer % L;
+    } else {
+      far.jobs.push_back(j);
+    }
+  }
+  local_.pull(near, in, out, dt, stream);
+  flat_.pull(far, in, out, dt, stream);
+}
+
 int64_t HierBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) {
   M4T_CHECK(dest >= 0 && dest < size(), "Isend: destination rank " << dest << " out of range");
   const int L = local_.size(), node = rank() / L;

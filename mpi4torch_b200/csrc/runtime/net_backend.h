@@ -68,9 +68,8 @@ class HierBackend final : public Backend {
   void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override {
     flat_.reduce(buf, n, dt, op, root, stream);
   }
-  void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override {
-    flat_.pull(plan, in, out, dt, stream);
-  }
+  // slab plans: boxes held by ranks of this node are read through the node's shared memory, the others over the mesh
+  void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override;
   void reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,
                    void* stream) override {
     flat_.reduce_pull(plan, in, out, dt, op, epi, stream);
