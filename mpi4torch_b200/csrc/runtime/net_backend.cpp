@@ -381,6 +381,24 @@ void NetBackend::wait(int64_t request, void*) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 
+namespace {
+template <DType DT> void widen_to_f32(const void* src, float* dst, int64_t n) {
+  using E = Elem<DT>;
+  const auto* s = static_cast<const typename E::storage*>(src);
+  for (int64_t i = 0; i < n; ++i) dst[i] = E::load(s[i]);
+}
+// out = round(val [+ acc]): the one rounding of the 16-bit float contract
+template <DType DT> void narrow_from_f32(const float* val, const void* acc, void* out, int64_t n) {
+  using E = Elem<DT>;
+  const auto* a = static_cast<const typename E::storage*>(acc);
+  auto* o = static_cast<typename E::storage*>(out);
+  if (a)
+    for (int64_t i = 0; i < n; ++i) o[i] = E::store(val[i] + E::load(a[i]));
+  else
+    for (int64_t i = 0; i < n; ++i) o[i] = E::store(val[i]);
+}
+}  // namespace
+
 void HierBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) {
   const int L = local_.size(), node = rank() / L;
   PullPlan near = plan, far = plan;  // same sizes, disjoint job lists (they fill disjoint parts of the output)
@@ -417,23 +435,33 @@ void HierBackend::wait(int64_t request, void* stream) {
   else flat_.wait(request >> 1, stream);
 }
 
-namespace {
-template <DType DT> void widen_to_f32(const void* src, float* dst, int64_t n) {
-  using E = Elem<DT>;
-  const auto* s = static_cast<const typename E::storage*>(src);
-  for (int64_t i = 0; i < n; ++i) dst[i] = E::load(s[i]);
+void HierBackend::bcast(void* buf, int64_t n, DType dt, int root, void*) {
+  M4T_CHECK(root >= 0 && root < size(), "Bcast_: root " << root << " out of range");
+  const int L = local_.size(), l = local_.rank();
+  // the root's rail carries the buffer to one rank per node, shared memory spreads it inside each node
+  if (l == root % L) rail_.bcast(buf, n, dt, root / L, nullptr);
+  local_.bcast(buf, n, dt, root % L, nullptr);
 }
-// out = round(val [+ acc]): the one rounding of the 16-bit float contract
-template <DType DT> void narrow_from_f32(const float* val, const void* acc, void* out, int64_t n) {
-  using E = Elem<DT>;
-  const auto* a = static_cast<const typename E::storage*>(acc);
-  auto* o = static_cast<typename E::storage*>(out);
-  if (a)
-    for (int64_t i = 0; i < n; ++i) o[i] = E::store(val[i] + E::load(a[i]));
-  else
-    for (int64_t i = 0; i < n; ++i) o[i] = E::store(val[i]);
+
+void HierBackend::reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void*) {
+  check_op_dtype(op, dt);
+  M4T_CHECK(root >= 0 && root < size(), "Reduce_: root " << root << " out of range");
+  const int L = local_.size(), l = local_.rank();
+  if (dt == DType::BF16 || dt == DType::F16) {
+    // two reduction levels: run them on an fp32 copy so that the result is rounded once
+    grow(wide_in_, static_cast<size_t>(n) * sizeof(float));
+    auto* w = reinterpret_cast<float*>(wide_in_.data());
+    if (dt == DType::BF16) widen_to_f32<DType::BF16>(buf, w, n);
+    else widen_to_f32<DType::F16>(buf, w, n);
+    reduce(w, n, DType::F32, op, root, nullptr);
+    if (dt == DType::BF16) narrow_from_f32<DType::BF16>(w, nullptr, buf, n);
+    else narrow_from_f32<DType::F16>(w, nullptr, buf, n);
+    return;
+  }
+  // inside the node to the rank on the root's rail (the others are zero-filled), then along that rail to the root
+  local_.reduce(buf, n, dt, op, root % L, nullptr);
+  if (l == root % L) rail_.reduce(buf, n, dt, op, root / L, nullptr);
 }
-}  // namespace
 
 void HierBackend::allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi, void*) {
   check_op_dtype(op, dt);

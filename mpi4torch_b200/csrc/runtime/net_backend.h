@@ -64,10 +64,9 @@ class HierBackend final : public Backend {
 
   void allreduce(const void* in, void* out, int64_t n, DType dt, ReduceOp op, const Epilogue& epi,
                  void* stream) override;
-  void bcast(void* buf, int64_t n, DType dt, int root, void* stream) override { flat_.bcast(buf, n, dt, root, stream); }
-  void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override {
-    flat_.reduce(buf, n, dt, op, root, stream);
-  }
+  // rooted operations: along the root's rail between the nodes, through shared memory inside each node
+  void bcast(void* buf, int64_t n, DType dt, int root, void* stream) override;
+  void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override;
   // slab plans: boxes held by ranks of this node are read through the node's shared memory, the others over the mesh
   void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override;
   void reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,

@@ -78,6 +78,31 @@ def test_hierarchical_allreduce_values_all_sizes_and_dtypes(tmp_path):
         assert "HIER OK" in res.stdout
 
 
+def test_hierarchical_rooted_operations_every_root(tmp_path):
+    """Bcast_ / Reduce_ along the root's rail and through the nodes' shared memory, for every root, 3 ranks per node."""
+    script = tmp_path / "rooted.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R, P = c.rank, c.size\n"
+        "for root in range(P):\n"
+        "    for dt in (torch.float64, torch.bfloat16, torch.int64):\n"
+        "        for n in (1, 1000, 300001):\n"
+        "            x = (torch.arange(n) % 7 + R).to(dt)\n"
+        "            y = c.Reduce_(x.clone(), m.MPI_SUM, root)\n"
+        "            ref = sum((torch.arange(n) % 7 + r).double() for r in range(P))\n"
+        "            if R == root:\n"
+        "                assert torch.allclose(y.double(), ref, rtol=2 ** -7 if dt == torch.bfloat16 else 0, atol=0), (root, dt, n)\n"
+        "            else:\n"
+        "                assert float(y.double().abs().sum()) == 0\n"
+        "            b = c.Bcast_((torch.arange(n) % 5 + (7 if R == root else 0)).to(dt), root)\n"
+        "            assert torch.equal(b, (torch.arange(n) % 5 + 7).to(dt))\n"
+        "c.Barrier()\n"
+        "if R == 0: print('ROOTED OK', flush=True)\n")
+    res = run_spmd(6, [str(script)], device="cpu", timeout=600, extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": "3"})
+    assert res.returncode == 0, res.stderr[-4000:]
+    assert "ROOTED OK" in res.stdout
+
+
 def test_two_nodes_two_ranks_each_one_launcher_per_node():
     """2 x 2 ranks: node 0's launcher hosts the rendezvous store, both launchers number their ranks node by node, and
     the full SPMD test set passes at world size 4."""
