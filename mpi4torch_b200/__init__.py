@@ -96,10 +96,14 @@ def _bootstrap() -> None:
             device = local_rank % ndev
             torch.cuda.set_device(device)
     if _spans_nodes(world):
-        # more than one node: the communicator lives on a TCP mesh, CUDA tensors are staged through host memory
-        # (what the reference does on an MPI without CUDA support); the NVLink backend needs one node
+        # more than one node: the world communicator lives on a TCP mesh and stages CUDA tensors through host memory
+        # (what the reference does on an MPI without CUDA support); the NVLink backend needs one node - sub-communicators
+        # whose members share a node (comm.Split by node) get it
         _connect_mesh(world)
-        want_cuda = False
+        _C.init_world(False, device)
+        if want_cuda:
+            _C.set_node_cuda_device(device)
+        return
     _C.init_world(want_cuda, device)
 
 

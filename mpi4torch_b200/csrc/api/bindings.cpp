@@ -121,6 +121,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("net_connect", &net_connect, py::arg("rank"), py::arg("size"), py::arg("addrs"),
         "Connects the TCP mesh (addrs[p] = 'host:port' of rank p); the world communicator is then created on it");
   m.def("over_network", [] { return World::instance().ctx()->over_network(); });
+  m.def("set_node_cuda_device", [](int64_t device) { World::instance().set_node_cuda_device(static_cast<int>(device)); },
+        "Job that spans nodes: the device node-local sub-communicators bind their NVLink backend to");
   m.def("world_initialised", [] { return World::initialised(); });
   m.def("deactivate_cuda_aware_mpi_support", &deactivate_cuda_aware_mpi_support);
   m.def("activate_nvlink_transport", &activate_nvlink_transport);

@@ -162,15 +162,26 @@ c10::intrusive_ptr<Communicator> Communicator::Split(int64_t color, int64_t key)
                           (color >= 0 ? "c" + std::to_string(color) : "r" + std::to_string(rank_));
   std::shared_ptr<CommContext> child;
   if (cx().over_network()) {
-    // sub-communicator on the same TCP mesh: its own id keeps its frames apart from every other communicator's
     std::vector<int> world_ranks;
     for (const auto& m : members) world_ranks.push_back(cx().net()->members()[static_cast<size_t>(m.second)]);
-    auto link = std::make_shared<NetLink>(cx().net()->engine_ptr(), net_comm_id(job), std::move(world_ranks), new_rank);
-    child = std::make_shared<CommContext>(std::move(link), job);
+    const int per_node = world_->ctx()->ranks_per_node();
+    bool one_node = per_node > 0;
+    for (int w : world_ranks) one_node = one_node && w / per_node == world_ranks[0] / per_node;
+    if (one_node) {
+      // all members live on one node: an ordinary shared-memory communicator - and, with a GPU per rank, the NVLink
+      // backend (tensor parallelism inside the node, the world communicator across nodes)
+      child = std::make_shared<CommContext>(new_rank, static_cast<int>(members.size()), job);
+      if (world_->node_cuda_device() >= 0 && members.size() > 1)
+        child->init_cuda(world_->node_cuda_device(), env_i64("M4T_SUB_STAGE_MB", 256), env_i64("M4T_SUB_SYMM_MB", 0));
+    } else {
+      // sub-communicator on the same TCP mesh: its own id keeps its frames apart from every other communicator's
+      auto link = std::make_shared<NetLink>(cx().net()->engine_ptr(), net_comm_id(job), std::move(world_ranks), new_rank);
+      child = std::make_shared<CommContext>(std::move(link), job);
+    }
   } else {
     child = std::make_shared<CommContext>(new_rank, static_cast<int>(members.size()), job);
   }
-  if (cx().cuda_ready()) {
+  if (!cx().over_network() && cx().cuda_ready()) {
     // same device, smaller arenas than the world communicator's
     child->init_cuda(cx().cuda()->device(), env_i64("M4T_SUB_STAGE_MB", 256), env_i64("M4T_SUB_SYMM_MB", 0));
   }

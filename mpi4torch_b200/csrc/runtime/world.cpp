@@ -28,6 +28,7 @@ CommContext::CommContext(std::shared_ptr<NetLink> link, const std::string& job_i
     for (int p = 0; p < P; ++p) uniform = uniform && all[static_cast<size_t>(p) * 2] == local_size && all[static_cast<size_t>(p) * 2 + 1] == 1;
   }
   if (uniform) {
+    ranks_per_node_ = local_size;
     // the ranks of this node share a control segment and arenas; one TCP rail per local index connects the nodes
     const int node = r / local_size, nodes = P / local_size;
     ctl_ = std::make_unique<Control>(local_rank, local_size, job_id + "_node" + std::to_string(node));

@@ -43,6 +43,8 @@ class CommContext {
     return net_ ? static_cast<Backend&>(*netbe_) : static_cast<Backend&>(*cpu_);
   }
   bool hierarchical() const { return hier_ != nullptr; }
+  // ranks per node when every node holds the same number of consecutive world ranks, else 0
+  int ranks_per_node() const { return ranks_per_node_; }
   bool over_network() const { return net_ != nullptr; }
   const std::shared_ptr<NetLink>& net() const { return net_; }
   // host control operations of the communicator (shared-memory flags or TCP messages)
@@ -68,6 +70,7 @@ class CommContext {
   std::shared_ptr<NetLink> net_;
   std::unique_ptr<NetBackend> netbe_;
   std::unique_ptr<HierBackend> hier_;
+  int ranks_per_node_ = 0;
   uint64_t split_seq_ = 0;
 };
 
@@ -107,6 +110,10 @@ class World {
   // Runtime toggle mirroring deactivate_cuda_aware_mpi_support() (reference
   // csrc/extension.cpp:54-59): CUDA tensors are staged through host memory and
   // the CPU shared-memory backend.
+  // Device this rank would use for NVLink communicators (-1: none).  In a job that spans nodes the world communicator
+  // has no CUDA backend, but a sub-communicator whose members all live on one node gets one.
+  void set_node_cuda_device(int device) { node_cuda_device_ = device; }
+  int node_cuda_device() const { return node_cuda_device_; }
   void set_host_staging(bool on) { host_staging_ = on; }
   bool host_staging() const { return host_staging_; }
 
@@ -121,6 +128,7 @@ class World {
   std::shared_ptr<CommContext> ctx_;
   std::vector<std::shared_ptr<CommContext>> children_;
   bool host_staging_ = false;
+  int node_cuda_device_ = -1;
   std::recursive_mutex mu_;
 };
 

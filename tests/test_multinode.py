@@ -103,6 +103,39 @@ def test_hierarchical_rooted_operations_every_root(tmp_path):
     assert "ROOTED OK" in res.stdout
 
 
+def test_sub_communicators_inside_a_node_use_shared_memory(tmp_path):
+    """comm.Split by node gives an ordinary single-node communicator (shared memory; with a GPU per rank the NVLink
+    backend), a split across nodes stays on the mesh; composing both by hand equals the world Allreduce, gradients
+    included."""
+    script = tmp_path / "nodesplit.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R, P = c.rank, c.size\n"
+        "L = 2\n"
+        "node = c.Split(R // L, R)\n"
+        "rail = c.Split(R % L, R)\n"
+        "assert 'posix-shm' in node.describe(), node.describe()\n"
+        "assert 'tcp mesh' in rail.describe(), rail.describe()\n"
+        "x = torch.tensor([float(R)], requires_grad=True)\n"
+        "b = rail.Allreduce(node.Allreduce(x, m.MPI_SUM), m.MPI_SUM)\n"
+        "b.backward()\n"
+        "assert float(b.detach()) == sum(range(P)) and float(x.grad) == P\n"
+        "g = node.Allgather(torch.tensor([float(R)]), 0)\n"
+        "assert g.tolist() == [float(r) for r in range(P) if r // L == R // L]\n"
+        "sub2 = node.Split(0, -R)\n"
+        "assert 'posix-shm' in sub2.describe() and sub2.rank == node.size - 1 - node.rank\n"
+        "h = node.Isend(torch.tensor([float(R)]), (node.rank + 1) % node.size, 3)\n"
+        "y = node.Recv(torch.empty(1), (node.rank - 1) % node.size, 3); node.Wait(h)\n"
+        "assert float(y) == (R // L) * L + (node.rank - 1) % node.size\n"
+        "sub2.Free(); node.Free(); rail.Free()\n"
+        "c.Barrier()\n"
+        "if R == 0: print('NODE SPLIT OK', flush=True)\n")
+    for nprocs in (4, 6):
+        res = run_spmd(nprocs, [str(script)], device="cpu", timeout=300, extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": "2"})
+        assert res.returncode == 0, res.stderr[-4000:]
+        assert "NODE SPLIT OK" in res.stdout
+
+
 def test_two_nodes_two_ranks_each_one_launcher_per_node():
     """2 x 2 ranks: node 0's launcher hosts the rendezvous store, both launchers number their ranks node by node, and
     the full SPMD test set passes at world size 4."""
