@@ -416,6 +416,55 @@ void HierBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt
   flat_.pull(far, in, out, dt, stream);
 }
 
+void HierBackend::reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,
+                              void* stream) {
+  check_op_dtype(op, dt);
+  const int L = local_.size(), l = local_.rank(), P = size(), N = P / L, node = rank() / L;
+  bool uniform = static_cast<int>(plan.numelem.size()) == P && plan.numelem[0] > 0;
+  for (int p = 1; uniform && p < P; ++p) uniform = plan.numelem[static_cast<size_t>(p)] == plan.numelem[0];
+  if (!uniform) {
+    flat_.reduce_pull(plan, in, out, dt, op, epi, stream);
+    return;
+  }
+  const int64_t c = plan.numelem[0], before = plan.before, after = plan.after;
+  if (dt == DType::BF16 || dt == DType::F16) {
+    // two reduction levels: on an fp32 copy, rounded once (together with the accumulate operand)
+    const int64_t n_in = before * c * P * after, n_out = before * c * after;
+    grow(wide_in_, static_cast<size_t>(n_in) * sizeof(float));
+    grow(wide_out_, static_cast<size_t>(n_out) * sizeof(float));
+    auto* wi = reinterpret_cast<float*>(wide_in_.data());
+    auto* wo = reinterpret_cast<float*>(wide_out_.data());
+    if (dt == DType::BF16) widen_to_f32<DType::BF16>(in, wi, n_in);
+    else widen_to_f32<DType::F16>(in, wi, n_in);
+    Epilogue e32;
+    e32.scale = epi.scale;
+    e32.has_scale = epi.has_scale;
+    reduce_pull(plan, wi, wo, DType::F32, op, e32, nullptr);
+    if (dt == DType::BF16) narrow_from_f32<DType::BF16>(wo, epi.accumulate, out, n_out);
+    else narrow_from_f32<DType::F16>(wo, epi.accumulate, out, n_out);
+    return;
+  }
+  const int64_t es = dtype_size(dt);
+  // 1. inside the node: local rank l gets the node's sums of the slices of ranks l, L+l, ... as [before, N*c, after]
+  ReducePlan near;
+  near.stage_elems = before * c * P * after;
+  near.out_elems = near.max_out_elems = before * c * N * after;
+  near.box.peer = -1;
+  near.box.src_off = static_cast<int64_t>(l) * c * after;
+  near.box.n[1] = before;
+  near.box.ss[1] = c * P * after;
+  near.box.ds[1] = c * N * after;
+  near.box.n[2] = N;
+  near.box.ss[2] = static_cast<int64_t>(L) * c * after;
+  near.box.ds[2] = c * after;
+  near.box.run = c * after;
+  grow(part_, static_cast<size_t>(near.out_elems * es));
+  local_.reduce_pull(near, in, part_.data(), dt, op, Epilogue{}, nullptr);
+  // 2. along the rail: reduce-scatter of those N slices, node k keeps slice k (scale / accumulate fused)
+  const ReducePlan far = plan_reduce_scatter(node, N, before, after, std::vector<int64_t>(static_cast<size_t>(N), c));
+  rail_.reduce_pull(far, part_.data(), out, dt, op, epi, nullptr);
+}
+
 int64_t HierBackend::isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) {
   M4T_CHECK(dest >= 0 && dest < size(), "Isend: destination rank " << dest << " out of range");
   const int L = local_.size(), node = rank() / L;

@@ -69,10 +69,11 @@ class HierBackend final : public Backend {
   void reduce(void* buf, int64_t n, DType dt, ReduceOp op, int root, void* stream) override;
   // slab plans: boxes held by ranks of this node are read through the node's shared memory, the others over the mesh
   void pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) override;
+  // Reduce_scatter with the same count on every rank: the node first sums, through shared memory, the slices of the
+  // destinations on each rail (local rank l collects those of ranks l, L+l, 2L+l, ...), then a reduce-scatter along the
+  // rail finishes them; other shapes use the flat mesh
   void reduce_pull(const ReducePlan& plan, const void* in, void* out, DType dt, ReduceOp op, const Epilogue& epi,
-                   void* stream) override {
-    flat_.reduce_pull(plan, in, out, dt, op, epi, stream);
-  }
+                   void* stream) override;
   // point-to-point: a peer on this node is reached through the node's shared memory, any other through the mesh (a
   // given source always takes the same route, so per-source FIFO order holds); the low bit of the id says which
   int64_t isend(const void* buf, int64_t bytes, int dest, int64_t tag, void* stream) override;

@@ -242,6 +242,9 @@ ReducePlan plan_reduce_scatter(int rank, int size, int64_t before, int64_t after
   j.ds[2] = numelem[rank] * after;
   j.run = numelem[rank] * after;
   if (plan.out_elems > 0) normalize_job(j);
+  plan.before = before;
+  plan.after = after;
+  plan.numelem.assign(numelem.begin(), numelem.begin() + size);
   return plan;
 }
 

@@ -42,6 +42,9 @@ struct ReducePlan {
   int64_t stage_elems = 0;   // identical on all ranks
   int64_t out_elems = 0;
   int64_t max_out_elems = 0;  // max over ranks (rank-independent grid sizing)
+  // the request the plan was built from (transports that re-plan in stages - the hierarchical host backend - read it)
+  int64_t before = 1, after = 1;
+  std::vector<int64_t> numelem;
 };
 
 // Drops unit loops and folds loops that continue the contiguous run.

@@ -136,6 +136,39 @@ def test_sub_communicators_inside_a_node_use_shared_memory(tmp_path):
         assert "NODE SPLIT OK" in res.stdout
 
 
+def test_hierarchical_reduce_scatter_uniform_counts(tmp_path):
+    """Reduce_scatter with the same count on every rank: node-level sums of each rail's slices through shared memory,
+    then a reduce-scatter along the rail; every dtype class, leading / trailing dimensions, fused epilogue, gradient."""
+    script = tmp_path / "hrs.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R, P = c.rank, c.size\n"
+        "assert 'hierarchical' in c.describe()\n"
+        "for dt in (torch.float64, torch.float32, torch.bfloat16, torch.int64):\n"
+        "    for (before, cnt, after) in ((1, 1, 1), (3, 2, 5), (1, 1000, 1), (2, 257, 33)):\n"
+        "        def full(r): return ((torch.arange(before * cnt * P * after) % 11 + r).reshape(before, cnt * P, after)).to(dt)\n"
+        "        ref = sum(full(r).double() for r in range(P))[:, R * cnt:(R + 1) * cnt, :]\n"
+        "        y = c.Reduce_scatter(full(R), m.MPI_SUM, 1, cnt)\n"
+        "        tol = dict(rtol=2 ** -7, atol=0) if dt == torch.bfloat16 else dict(rtol=0, atol=0)\n"
+        "        assert y.shape == ref.shape and torch.allclose(y.double(), ref, **tol), (dt, before, cnt, after)\n"
+        "        if dt == torch.int64: continue\n"
+        "        acc = torch.full(ref.shape, 2.0, dtype=dt)\n"
+        "        z = c.Reduce_scatterFused(full(R), m.MPI_SUM, 1, cnt, 0.25, acc)\n"
+        "        assert torch.allclose(z.double(), 2.0 + 0.25 * ref, **tol), (dt, before, cnt, after, 'fused')\n"
+        "    mx = c.Reduce_scatter(torch.full((P * 3,), float(R)), m.MPI_MAX, 0, 3); assert mx.tolist() == [P - 1.0] * 3\n"
+        "x = torch.ones(P * 4, requires_grad=True)\n"
+        "(c.Reduce_scatter(x * (R + 1), m.MPI_SUM, 0, 4) * (R + 1)).sum().backward()\n"
+        "assert x.grad.tolist() == [float((R + 1) * (d + 1)) for d in range(P) for _ in range(4)]\n"
+        "c.Barrier()\n"
+        "if R == 0: print(\"HIER RS OK\")\n"
+    )
+    for nprocs, per_node in ((4, 2), (6, 3), (8, 2)):
+        res = run_spmd(nprocs, [str(script)], device="cpu", timeout=300,
+                       extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
+        assert res.returncode == 0, res.stderr[-4000:]
+        assert "HIER RS OK" in res.stdout
+
+
 def test_two_nodes_two_ranks_each_one_launcher_per_node():
     """2 x 2 ranks: node 0's launcher hosts the rendezvous store, both launchers number their ranks node by node, and
     the full SPMD test set passes at world size 4."""
