@@ -146,7 +146,7 @@ def _connect_mesh(world: int) -> None:
     prefix = "m4t/" + os.environ["M4T_JOB_ID"] + "/addr/"
     store.set(prefix + str(rank), f"{mine}:{listen_port}")
     addrs = [store.get(prefix + str(p)).decode() for p in range(world)]
-    _C.net_connect(rank, world, addrs)
+    _C.net_connect(rank, world, addrs, os.environ["M4T_JOB_ID"])
     # keep the store alive until every rank has read every address (rank 0 may be its host)
     store.add(prefix + "done", 1)
     if rank == 0 and not hosted:

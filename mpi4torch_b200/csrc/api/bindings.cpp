@@ -50,10 +50,11 @@ int64_t net_listen() {
   return port;
 }
 
-void net_connect(int64_t rank, int64_t size, const std::vector<std::string>& addrs) {
+void net_connect(int64_t rank, int64_t size, const std::vector<std::string>& addrs, const std::string& job) {
   M4T_CHECK(g_listen_fd >= 0, "net_connect() without net_listen()");
   const double timeout_s = static_cast<double>(env_i64("M4T_TIMEOUT_S", 300));
-  auto engine = std::make_shared<NetEngine>(static_cast<int>(rank), static_cast<int>(size), g_listen_fd, addrs, timeout_s);
+  auto engine = std::make_shared<NetEngine>(static_cast<int>(rank), static_cast<int>(size), g_listen_fd, addrs, timeout_s,
+                                            net_comm_id(job));
   g_listen_fd = -1;
   World::set_network(std::move(engine));
 }
@@ -118,7 +119,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         "Attach to the job (collective) and optionally bring up the CUDA backend on `device`.");
   m.def("finalize", [] { World::finalize(); });
   m.def("net_listen", &net_listen, "Opens this rank's listening socket for the multi-node TCP mesh; returns the port");
-  m.def("net_connect", &net_connect, py::arg("rank"), py::arg("size"), py::arg("addrs"),
+  m.def("net_connect", &net_connect, py::arg("rank"), py::arg("size"), py::arg("addrs"), py::arg("job") = "",
         "Connects the TCP mesh (addrs[p] = 'host:port' of rank p); the world communicator is then created on it");
   m.def("over_network", [] { return World::instance().ctx()->over_network(); });
   m.def("set_node_cuda_device", [](int64_t device) { World::instance().set_node_cuda_device(static_cast<int>(device)); },

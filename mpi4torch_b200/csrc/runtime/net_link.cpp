@@ -137,17 +137,20 @@ int NetEngine::listen_any(int* port_out) {
   return fd;
 }
 
-NetEngine::NetEngine(int rank, int size, int listen_fd, const std::vector<std::string>& addrs, double timeout_s)
+NetEngine::NetEngine(int rank, int size, int listen_fd, const std::vector<std::string>& addrs, double timeout_s,
+                     uint32_t job_key)
     : rank_(rank), size_(size), timeout_s_(timeout_s), peers_(static_cast<size_t>(size)) {
   M4T_CHECK(static_cast<int>(addrs.size()) == size, "need one address per rank");
   const uint64_t deadline = now_ns() + static_cast<uint64_t>(timeout_s * 1e9);
   struct Hello {
     uint32_t magic;
     int32_t rank;
+    uint32_t job_key;
+    uint32_t reserved;
   };
   for (int p = 0; p < rank; ++p) {
     const int fd = connect_to(addrs[static_cast<size_t>(p)], deadline);
-    Hello h{kNetMagic, rank};
+    Hello h{kNetMagic, rank, job_key, 0};
     write_full(fd, &h, sizeof(h), deadline);
     peers_[static_cast<size_t>(p)].fd = fd;
   }
@@ -162,9 +165,20 @@ NetEngine::NetEngine(int rank, int size, int listen_fd, const std::vector<std::s
       if (fd >= 0) break;
     }
     Hello h{};
-    read_full(fd, &h, sizeof(h), deadline);
-    M4T_CHECK(h.magic == kNetMagic && h.rank > rank && h.rank < size && peers_[static_cast<size_t>(h.rank)].fd < 0,
-              "unexpected greeting on the mesh socket (another job on this port?)");
+    bool ok = true;
+    try {
+      read_full(fd, &h, sizeof(h), std::min<uint64_t>(deadline, now_ns() + 5000000000ull));
+    } catch (const std::exception&) {
+      ok = false;  // a connection that never greets (port scanner, health check)
+    }
+    ok = ok && h.magic == kNetMagic && h.job_key == job_key && h.rank > rank && h.rank < size &&
+         peers_[static_cast<size_t>(h.rank)].fd < 0;
+    if (!ok) {  // not one of ours: turn it away and keep waiting for the real peer
+      ::close(fd);
+      --k;
+      M4T_CHECK(now_ns() < deadline, "timed out waiting for the higher ranks to connect");
+      continue;
+    }
     peers_[static_cast<size_t>(h.rank)].fd = fd;
   }
   ::close(listen_fd);

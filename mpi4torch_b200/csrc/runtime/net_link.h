@@ -54,7 +54,8 @@ class NetEngine {
 
   // Builds the mesh: addrs[p] = "host:port" of rank p's listening socket.  Ranks connect to every lower rank and
   // accept from every higher one.  Takes ownership of listen_fd (closed once the mesh stands).
-  NetEngine(int rank, int size, int listen_fd, const std::vector<std::string>& addrs, double timeout_s);
+  // `job_key`: greetings carrying another key (a different job, a port scanner) are turned away.
+  NetEngine(int rank, int size, int listen_fd, const std::vector<std::string>& addrs, double timeout_s, uint32_t job_key = 0);
   ~NetEngine();
   NetEngine(const NetEngine&) = delete;
   NetEngine& operator=(const NetEngine&) = delete;
