@@ -401,6 +401,39 @@ template <DType DT> void narrow_from_f32(const float* val, const void* acc, void
 
 void HierBackend::pull(const PullPlan& plan, const void* in, void* out, DType dt, void* stream) {
   const int L = local_.size(), node = rank() / L;
+  const int P = size(), N = P / L, l = local_.rank();
+  bool uniform_allgather = plan.replicated_output && static_cast<int>(plan.axis_len.size()) == P && plan.axis_len[0] > 0 &&
+                           plan.before > 0 && plan.after > 0;
+  for (int p = 1; uniform_allgather && p < P; ++p) uniform_allgather = plan.axis_len[static_cast<size_t>(p)] == plan.axis_len[0];
+  if (uniform_allgather) {
+    // Allgather with the same length on every rank: along the rail first (each rank fetches N-1 slices over the network
+    // instead of (N-1) L), then the node's ranks exchange what their rails brought through shared memory
+    const int64_t c = plan.axis_len[0], before = plan.before, after = plan.after, es = dtype_size(dt);
+    const PullPlan far = plan_gather(node, N, 0, before, after, std::vector<int64_t>(static_cast<size_t>(N), c), /*all=*/true);
+    grow(part_, static_cast<size_t>(before * c * N * after * es));
+    rail_.pull(far, in, part_.data(), dt, nullptr);  // [before, N*c, after]: slice k = rank (k, l)
+    PullPlan near;
+    near.stage_elems = near.max_stage_elems = before * c * N * after;
+    near.out_elems = near.max_out_elems = before * c * P * after;
+    near.replicated_output = true;
+    for (int q = 0; q < L; ++q) {
+      SlabJob j;  // local rank q's rail buffer: slice k goes to global rank k*L + q
+      j.peer = (l + q) % L;
+      const int src = j.peer;
+      j.src_off = 0;
+      j.dst_off = static_cast<int64_t>(src) * c * after;
+      j.n[1] = before;
+      j.ss[1] = c * N * after;
+      j.ds[1] = c * P * after;
+      j.n[2] = N;
+      j.ss[2] = c * after;
+      j.ds[2] = static_cast<int64_t>(L) * c * after;
+      j.run = c * after;
+      near.jobs.push_back(j);
+    }
+    local_.pull(near, part_.data(), out, dt, nullptr);
+    return;
+  }
   PullPlan near = plan, far = plan;  // same sizes, disjoint job lists (they fill disjoint parts of the output)
   near.jobs.clear();
   far.jobs.clear();

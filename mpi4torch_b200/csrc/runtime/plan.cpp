@@ -113,6 +113,11 @@ PullPlan plan_gather(int rank, int size, int root, int64_t before, int64_t after
     }
   }
   rotate_jobs(plan, rank, size);
+  if (all) {
+    plan.before = before;
+    plan.after = after;
+    plan.axis_len.assign(axis_len.begin(), axis_len.begin() + size);
+  }
   return plan;
 }
 

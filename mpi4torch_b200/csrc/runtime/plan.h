@@ -34,6 +34,9 @@ struct PullPlan {
   int64_t max_stage_elems = 0;  // max over ranks of stage_elems (symmetric heap sizing)
   int64_t max_out_elems = 0;    // max over ranks of out_elems (rank-independent grid sizing)
   bool replicated_output = false;  // every rank receives the identical gathered tensor (Allgather)
+  // Allgather only: the request the plan was built from (the hierarchical host backend re-plans it in two stages)
+  int64_t before = 1, after = 1;
+  std::vector<int64_t> axis_len;
 };
 
 // out = reduce over all peers p of staged_p[box]; all peers share one box shape.

@@ -169,6 +169,35 @@ def test_hierarchical_reduce_scatter_uniform_counts(tmp_path):
         assert "HIER RS OK" in res.stdout
 
 
+def test_hierarchical_allgather_uniform_lengths(tmp_path):
+    """Allgather with the same length on every rank: along the rail first, then the node's ranks exchange what their
+    rails brought through shared memory; layouts with leading / trailing dimensions, several dtypes, the gradient."""
+    script = tmp_path / "hag.py"
+    script.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD; R, P = c.rank, c.size\n"
+        "assert 'hierarchical' in c.describe()\n"
+        "for dt in (torch.float64, torch.bfloat16, torch.int32, torch.bool):\n"
+        "    for (before, cnt, after) in ((1, 1, 1), (3, 2, 5), (1, 1000, 1), (2, 257, 33)):\n"
+        "        def part(r): return ((torch.arange(before * cnt * after) % 7 + r) % (2 if dt == torch.bool else 1000)).reshape(before, cnt, after).to(dt)\n"
+        "        y = c.Allgather(part(R), 1)\n"
+        "        ref = torch.cat([part(r) for r in range(P)], dim=1)\n"
+        "        assert torch.equal(y, ref), (dt, before, cnt, after)\n"
+        "x = torch.ones(2, 3, requires_grad=True)\n"
+        "g = c.Allgather(x * (R + 1), 0)\n"
+        "(g * torch.arange(float(2 * P * 3)).reshape(2 * P, 3)).sum().backward()\n"
+        "w = torch.arange(float(2 * P * 3)).reshape(2 * P, 3)[2 * R:2 * R + 2]\n"
+        "assert torch.equal(x.grad, w * P * (R + 1))\n"
+        "c.Barrier()\n"
+        "if R == 0: print(\"HIER AG OK\", flush=True)\n"
+    )
+    for nprocs, per_node in ((4, 2), (6, 3), (8, 2)):
+        res = run_spmd(nprocs, [str(script)], device="cpu", timeout=300,
+                       extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
+        assert res.returncode == 0, res.stderr[-4000:]
+        assert "HIER AG OK" in res.stdout
+
+
 def test_two_nodes_two_ranks_each_one_launcher_per_node():
     """2 x 2 ranks: node 0's launcher hosts the rendezvous store, both launchers number their ranks node by node, and
     the full SPMD test set passes at world size 4."""
