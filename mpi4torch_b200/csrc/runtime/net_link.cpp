@@ -403,9 +403,10 @@ void NetEngine::pump_out(int p) {
 }
 
 void NetEngine::progress(int timeout_ms) {
-  std::vector<pollfd> fds;
-  std::vector<int> who;
-  fds.reserve(static_cast<size_t>(size_));
+  auto& fds = poll_fds_;  // members: the busy part of wait() calls this hundreds of times per message
+  auto& who = poll_who_;
+  fds.clear();
+  who.clear();
   for (int p = 0; p < size_; ++p) {
     Peer& pr = peers_[static_cast<size_t>(p)];
     if (p == rank_ || pr.fd < 0 || pr.closed) continue;

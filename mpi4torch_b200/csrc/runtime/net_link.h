@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstring>
 #include <deque>
+#include <poll.h>
 #include <list>
 #include <memory>
 #include <string>
@@ -133,6 +134,8 @@ class NetEngine {
   std::vector<Peer> peers_;
   std::unordered_map<uint64_t, Op> ops_;
   uint64_t next_op_ = 1;
+  std::vector<struct pollfd> poll_fds_;
+  std::vector<int> poll_who_;
 };
 
 class NetLink {
