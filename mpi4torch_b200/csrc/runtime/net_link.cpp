@@ -515,13 +515,17 @@ void NetLink::bcast_i64(int64_t* data, int k, int root) {
   }
 }
 
-bool NetLink::quiesce() noexcept {
+bool NetLink::quiesce(double timeout_s) noexcept {
+  const double saved = eng_->timeout_s();
+  bool ok = true;
   try {
+    eng_->set_timeout_s(std::min(saved, timeout_s));
     barrier();
-    return true;
   } catch (...) {
-    return false;
+    ok = false;
   }
+  eng_->set_timeout_s(saved);
+  return ok;
 }
 
 }  // namespace m4t

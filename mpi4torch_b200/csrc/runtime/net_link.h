@@ -64,6 +64,7 @@ class NetEngine {
   int rank() const { return rank_; }
   int size() const { return size_; }
   double timeout_s() const { return timeout_s_; }
+  void set_timeout_s(double t) { timeout_s_ = t; }
 
   // `data` must stay valid until wait() returned for the operation, unless `copy` (the engine then keeps its own
   // copy until the bytes have left).  peer == rank() is a local hand-over.
@@ -161,8 +162,9 @@ class NetLink {
   void barrier();
   void allgather_i64(const int64_t* mine, int k, int64_t* all);
   void bcast_i64(int64_t* data, int k, int root);
-  // teardown handshake: a barrier that never throws
-  bool quiesce() noexcept;
+  // teardown handshake: a barrier that never throws and gives up after `timeout_s` (a rank that leaves early - an
+  // exception, sys.exit - must not keep its peers waiting for the full operation timeout)
+  bool quiesce(double timeout_s) noexcept;
 
  private:
   std::shared_ptr<NetEngine> eng_;

@@ -58,8 +58,12 @@ CommContext::~CommContext() { shutdown(); }
 void CommContext::shutdown() {
   if (!ctl_) return;
   // every member reaches this point before anybody unmaps / unlinks shared segments (or closes its sockets)
-  if (net_) net_->quiesce();
-  ctl_->quiesce(static_cast<double>(env_i64("M4T_EXIT_TIMEOUT_S", 10)));
+  // once one teardown handshake of this process has failed (a peer is gone or stuck) the remaining ones only get a
+  // moment: every further wait would just delay the exit of a job that is already broken
+  static bool handshake_failed = false;
+  const double exit_timeout = handshake_failed ? 0.2 : static_cast<double>(env_i64("M4T_EXIT_TIMEOUT_S", 10));
+  if (net_ && !net_->quiesce(exit_timeout)) handshake_failed = true;
+  if (!ctl_->quiesce(handshake_failed ? 0.2 : exit_timeout)) handshake_failed = true;
   cuda_.reset();
   hier_.reset();
   netbe_.reset();

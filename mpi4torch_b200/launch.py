@@ -13,6 +13,10 @@ With ``--nnodes M`` every node runs one launcher with its ``--node-rank``; ranks
 (``RANK = node_rank * N + LOCAL_RANK``, ``WORLD_SIZE = M * N``), node 0's launcher hosts the key-value store at
 ``--master-addr:--master-port`` through which the ranks exchange the addresses of their TCP mesh sockets
 (``mpirun``'s wire-up across hosts; ``torchrun --nnodes`` works as well - the library then uses the agent's store).
+
+``--hosts h0,h1,...`` does the "once per node" part itself, the way ``mpirun --host`` does: run on ``h0``, it starts the
+other nodes' launchers through a remote shell (``--rsh``, default ``ssh``; same working directory, ``PYTHONPATH`` and
+``M4T_*`` / ``OMP_NUM_THREADS`` variables) and tears them down with the job.
 """
 from __future__ import annotations
 
@@ -170,6 +174,53 @@ def _terminate(procs: List[subprocess.Popen], pending: set) -> None:
             procs[r].kill()
 
 
+def launch_on_hosts(hosts: Sequence[str], nprocs: int, cmd: Sequence[str], *, rsh: str = "ssh", timeout: Optional[float] = None,
+                    tag_output: bool = False, master_port: Optional[int] = None, master_addr: Optional[str] = None) -> int:
+    """``mpirun --host h0,h1,...``: this process is node 0 (it must run on ``hosts[0]``); the launchers of the other
+    nodes are started through ``rsh host <command>`` and stopped when the job ends.  Returns the job's exit code."""
+    import shlex
+
+    hosts = [h for h in hosts if h]
+    if len(hosts) < 2:
+        return launch(nprocs, cmd, timeout=timeout, tag_output=tag_output)
+    addr = master_addr or hosts[0]
+    port = int(master_port or _free_port())
+    forward = {k: v for k, v in os.environ.items() if k.startswith("M4T_") or k in ("PYTHONPATH", "OMP_NUM_THREADS")}
+    remotes: List[subprocess.Popen] = []
+    try:
+        for k, host in enumerate(hosts[1:], start=1):
+            inner = ["env"] + [f"{k_}={v}" for k_, v in forward.items()] + [
+                sys.executable, "-m", "mpi4torch_b200.launch", "-np", str(nprocs), "--nnodes", str(len(hosts)), "--node-rank", str(k),
+                "--master-addr", addr, "--master-port", str(port)]
+            if timeout is not None:
+                inner += ["--timeout", str(timeout)]
+            if tag_output:
+                inner += ["--tag-output"]
+            inner += list(cmd)
+            remote_cmd = "cd " + shlex.quote(os.getcwd()) + " && " + " ".join(shlex.quote(x) for x in inner)
+            remotes.append(subprocess.Popen(shlex.split(rsh) + [host, remote_cmd]))
+        rc = launch(nprocs, cmd, timeout=timeout, tag_output=tag_output, nnodes=len(hosts), node_rank=0, master_addr=addr,
+                    master_port=port)
+        deadline = time.monotonic() + 30.0
+        for p in remotes:
+            try:
+                r = p.wait(timeout=max(0.1, deadline - time.monotonic()))
+            except subprocess.TimeoutExpired:
+                r = 124
+            if r != 0 and rc == 0:
+                rc = r if r > 0 else 128 - r
+        return rc
+    finally:
+        for p in remotes:
+            if p.poll() is None:
+                p.terminate()
+        for p in remotes:
+            try:
+                p.wait(timeout=5.0)
+            except subprocess.TimeoutExpired:
+                p.kill()
+
+
 def main(argv: Optional[Sequence[str]] = None) -> int:
     ap = argparse.ArgumentParser(prog="python -m mpi4torch_b200.launch", description=__doc__.split("\n\n")[0])
     ap.add_argument("-np", "-n", "--nproc", dest="np", type=int, required=True, help="number of ranks")
@@ -179,6 +230,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     ap.add_argument("--node-rank", type=int, default=0, help="this node's index, 0 <= node-rank < nnodes")
     ap.add_argument("--master-addr", default=None, help="address of node 0 (with --nnodes > 1)")
     ap.add_argument("--master-port", type=int, default=None, help="port of the rendezvous store on node 0")
+    ap.add_argument("--hosts", default=None, help="comma-separated hosts, this one first: start the other nodes' launchers "
+                                                  "through --rsh (like mpirun --host)")
+    ap.add_argument("--rsh", default="ssh", help="remote shell used with --hosts (default: ssh)")
     ap.add_argument("-m", dest="module", default=None, help="run a module (python -m) instead of a script")
     ap.add_argument("rest", nargs=argparse.REMAINDER, help="script and its arguments")
     argv = list(sys.argv[1:] if argv is None else argv)
@@ -186,10 +240,11 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     i = 0
     while i < len(argv):  # walk the launcher's own options; a `-m` among the script's arguments is not ours
         a = argv[i]
-        if a in ("-np", "-n", "--nproc", "--timeout", "--nnodes", "--node-rank", "--master-addr", "--master-port"):
+        if a in ("-np", "-n", "--nproc", "--timeout", "--nnodes", "--node-rank", "--master-addr", "--master-port", "--hosts",
+                 "--rsh"):
             i += 2
         elif a == "--tag-output" or a.startswith(("--nproc=", "--timeout=", "--nnodes=", "--node-rank=", "--master-addr=",
-                                                   "--master-port=")):
+                                                   "--master-port=", "--hosts=", "--rsh=")):
             i += 1
         elif a == "-m" and i + 1 < len(argv):
             # like `python -m mod args...`: everything after the module name belongs to the module, options included
@@ -207,6 +262,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         if not rest:
             ap.error("no script given")
         cmd = [sys.executable] + rest if rest[0].endswith(".py") else rest
+    if args.hosts:
+        return launch_on_hosts(args.hosts.split(","), args.np, cmd, rsh=args.rsh, timeout=args.timeout, tag_output=args.tag_output,
+                               master_port=args.master_port, master_addr=args.master_addr)
     return launch(args.np, cmd, timeout=args.timeout, tag_output=args.tag_output, nnodes=args.nnodes,
                   node_rank=args.node_rank, master_addr=args.master_addr, master_port=args.master_port)
 

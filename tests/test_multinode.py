@@ -307,3 +307,34 @@ def test_node_local_waits_keep_the_network_moving(tmp_path):
                    extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": "2", "M4T_TIMEOUT_S": "30"})
     assert res.returncode == 0, res.stderr[-4000:]
     assert "CHAIN OK" in res.stdout
+
+
+def test_hosts_option_starts_the_other_nodes_through_a_remote_shell(tmp_path):
+    """`launch --hosts h0,h1 --rsh CMD` (mpirun --host): node 0 runs here, node 1's launcher is started through the remote
+    shell - a stand-in script that ignores the host and runs the command locally - and the failure of a remote rank
+    fails the job."""
+    rsh = tmp_path / "fake_ssh"
+    rsh.write_text("#!/bin/sh\nshift\nexec sh -c \"$*\"\n")
+    rsh.chmod(0o755)
+    ok = tmp_path / "ok.py"
+    ok.write_text(
+        "import torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD\n"
+        "y = c.Allreduce(torch.ones(3) * (c.rank + 1), m.MPI_SUM)\n"
+        "assert y.tolist() == [10.0] * 3 and c.size == 4\n"
+        "c.Barrier()\n"
+        "if c.rank == 3: print('LAST RANK OK', flush=True)\n")
+    base = [sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", "--hosts", "127.0.0.1,127.0.0.1", "--rsh", str(rsh),
+            "--timeout", "240"]
+    res = subprocess.run(base + [str(ok)], env=_env(), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-4000:]
+    assert "LAST RANK OK" in res.stdout  # printed by a rank of the remotely started node
+    bad = tmp_path / "bad.py"
+    bad.write_text(
+        "import sys, torch, mpi4torch_b200 as m\n"
+        "c = m.COMM_WORLD\n"
+        "c.Barrier()\n"
+        "if c.rank == 2: sys.exit(7)\n"
+        "c.Allreduce(torch.ones(1), m.MPI_SUM)\n")
+    res = subprocess.run(base + [str(bad)], env=_env(), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0
