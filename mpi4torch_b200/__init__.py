@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import atexit
 import os
+import sys
 from typing import List, Optional
 
 import torch
@@ -146,6 +147,9 @@ def _connect_mesh(world: int) -> None:
     prefix = "m4t/" + os.environ["M4T_JOB_ID"] + "/addr/"
     store.set(prefix + str(rank), f"{mine}:{listen_port}")
     addrs = [store.get(prefix + str(p)).decode() for p in range(world)]
+    if os.environ.get("M4T_DEBUG", "0") not in ("", "0"):
+        sys.stderr.write(f"[m4t:{rank}] tcp mesh: store {host}:{port} ({'hosted elsewhere' if hosted or rank else 'hosted here'}), "
+                         f"listening on {mine}:{listen_port}, peers {addrs}\n")
     _C.net_connect(rank, world, addrs, os.environ["M4T_JOB_ID"])
     # keep the store alive until every rank has read every address (rank 0 may be its host)
     store.add(prefix + "done", 1)
