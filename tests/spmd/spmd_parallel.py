@@ -361,5 +361,57 @@ class TestShardedOptimizer(unittest.TestCase):
             self.assertTrue(torch.equal(p.detach(), comm.Bcast_(p.detach().clone(), 0)))
 
 
+
+
+class TestNodeRails(unittest.TestCase):
+    """Two-level (node / rail) collectives composed from the primitives (parallel/hierarchical.py)."""
+
+    def _per_node(self):
+        for k in (3, 2):
+            if P % k == 0 and P > k:
+                return k
+        return 1 if P > 1 else P
+
+    def test_hierarchical_allreduce_equals_allreduce_and_is_differentiable(self):
+        from mpi4torch_b200.parallel import NodeRails, hierarchical_allreduce
+
+        rails = NodeRails(comm, per_node=self._per_node())
+        self.assertEqual(rails.node.size * rails.rail.size, P)
+        self.assertEqual((rails.node.rank, rails.rail.rank), (R % rails.per_node, R // rails.per_node))
+        for shape in ((1,), (7,), (5, 3), (2, 3, 4)):  # 7 and 15 are not multiples of the node size: padded internally
+            g = torch.Generator().manual_seed(40 + R)
+            x = torch.randn(*shape, generator=g, dtype=DT).to(DEVICE).requires_grad_()
+            y = hierarchical_allreduce(x, rails)
+            ref = comm.Allreduce(x.detach(), m4t.MPI_SUM)
+            self.assertEqual(y.shape, x.shape)
+            self.assertTrue(torch.allclose(y, ref, rtol=1e-12, atol=1e-12))
+            w = (torch.arange(float(x.numel()), dtype=DT).reshape(shape) + R).to(DEVICE)
+            (y * w).sum().backward()
+            # adjoint of a sum over ranks: the sum over ranks of the upstream gradients
+            self.assertTrue(torch.allclose(x.grad, comm.Allreduce(w, m4t.MPI_SUM), rtol=1e-12, atol=1e-12))
+        z = hierarchical_allreduce(torch.full((4,), float(R), dtype=DT, device=DEVICE), rails, m4t.MPI_MAX)
+        self.assertEqual(z.tolist(), [P - 1.0] * 4)
+        s = hierarchical_allreduce(torch.ones(6, dtype=DT, device=DEVICE), rails, m4t.MPI_SUM, scale=1.0 / P)
+        self.assertTrue(torch.allclose(s, torch.ones(6, dtype=DT, device=DEVICE)))
+        rails.free()
+
+    def test_hierarchical_gradient_sync_matches_the_flat_one(self):
+        from mpi4torch_b200.parallel import NodeRails, hierarchical_sync_gradients_
+
+        rails = NodeRails(comm, per_node=self._per_node())
+        torch.manual_seed(3)
+        a = torch.nn.Linear(5, 4).to(DT).to(DEVICE)
+        b = torch.nn.Linear(5, 4).to(DT).to(DEVICE)
+        b.load_state_dict(a.state_dict())
+        g = torch.Generator().manual_seed(70 + R)
+        x = torch.randn(9, 5, generator=g, dtype=DT).to(DEVICE)
+        a(x).square().sum().backward()
+        b(x).square().sum().backward()
+        sync_gradients_(a.parameters(), comm)
+        hierarchical_sync_gradients_(b.parameters(), rails)
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            self.assertTrue(torch.allclose(pa.grad, pb.grad, rtol=1e-12, atol=1e-12))
+        rails.free()
+
 if __name__ == "__main__":
     unittest.main()
