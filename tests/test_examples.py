@@ -53,3 +53,12 @@ def test_sharded_optimizer_example_cpu():
     losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
     assert len(losses) >= 3 and losses[-1] < 0.5 * losses[0], losses
     assert "optimizer state per rank" in res.stdout
+
+
+def test_multinode_two_level_example_on_simulated_nodes():
+    res = run_spmd(4, ["examples/multinode_two_level.py", "--device", "cpu", "--steps", "21"], device="cpu", timeout=300,
+                   extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": "2"})
+    assert res.returncode == 0, res.stderr[-4000:]
+    assert "4 ranks = 2 node(s) x 2; node: cpu: posix-shm" in res.stdout
+    losses = [float(v) for v in re.findall(r"loss ([0-9.]+)", res.stdout)]
+    assert len(losses) == 3 and losses[-1] < 0.5 * losses[0], losses
