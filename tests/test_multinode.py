@@ -338,3 +338,23 @@ def test_hosts_option_starts_the_other_nodes_through_a_remote_shell(tmp_path):
         "c.Allreduce(torch.ones(1), m.MPI_SUM)\n")
     res = subprocess.run(base + [str(bad)], env=_env(), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
     assert res.returncode != 0
+
+
+@pytest.mark.parametrize("nprocs,per_node,seed", [(4, 2, 1), (6, 3, 2), (5, 0, 4)])
+def test_random_operation_sequences_give_identical_results_on_every_transport(nprocs, per_node, seed):
+    """tests/spmd/fuzz_ops.py: a seeded random sequence of collectives, re-partitions, rings and sub-communicators with
+    exactly representable values.  Shared memory, the flat mesh, the hierarchical mode and the piece-wise slab paths
+    must produce bit-identical outputs on every rank."""
+    def digests(extra):
+        res = run_spmd(nprocs, ["tests/spmd/fuzz_ops.py", str(seed), "140"], device="cpu", timeout=600, extra_env=extra)
+        assert res.returncode == 0, res.stderr[-4000:]
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("FUZZ")]
+        assert len(line) == 1, res.stdout[-2000:]
+        return line[0]
+
+    want = digests({})
+    assert digests({"M4T_NET": "1"}) == want
+    assert digests({"M4T_SLAB_CHUNK_BYTES": "64"}) == want
+    if per_node:
+        assert digests({"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)}) == want
+        assert digests({"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node), "M4T_SLAB_CHUNK_BYTES": "200"}) == want
