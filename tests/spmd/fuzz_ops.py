@@ -31,10 +31,29 @@ def values(shape, dtype, salt):
 
 
 def absorb(name, t):
+    if t.requires_grad:  # on every rank, also where the result is empty: the adjoint is a collective
+        # also push a gradient through the op: the adjoint communication must agree across transports too
+        w = ((torch.arange(t.numel()) * 3 + R) % 5).reshape(t.shape).to(t.dtype)
+        leaf = LEAVES.pop()
+        (t * w).sum().backward()
+        g = leaf.grad if leaf.grad is not None else torch.zeros(0)
+        digest.update(b"grad")
+        digest.update(g.detach().to(torch.float64).contiguous().numpy().tobytes())
     t = t.detach().to(torch.float64).contiguous()
     digest.update(name.encode())
     digest.update(str(tuple(t.shape)).encode())
     digest.update(t.numpy().tobytes())
+
+
+LEAVES = []
+
+
+def leaf_values(shape, dtype, salt, with_grad):
+    x = values(shape, dtype, salt)
+    if with_grad and dtype == torch.float64:
+        x.requires_grad_()
+        LEAVES.append(x)
+    return x
 
 
 def rand_shape(axis_len=None, big=False):
@@ -52,7 +71,7 @@ for i in range(nops):
     big = rng.random() < 0.15
     if kind == "allreduce":
         op = rng.choice([m4t.MPI_SUM, m4t.MPI_MAX, m4t.MPI_MIN])
-        absorb(kind, comm.Allreduce(values(rand_shape(big=big), dt, i), op))
+        absorb(kind, comm.Allreduce(leaf_values(rand_shape(big=big), dt, i, op == m4t.MPI_SUM), op))
     elif kind == "bcast":
         absorb(kind, comm.Bcast_(values(rand_shape(big=big), dt, i), rng.randrange(P)))
     elif kind == "reduce":
@@ -62,7 +81,7 @@ for i in range(nops):
         ax = rng.randrange(len(shape))
         uneven = rng.random() < 0.5
         shape[ax] = (shape[ax] + (R % 3 if uneven else 0)) if not big else shape[ax]
-        x = values(shape, dt, i)
+        x = leaf_values(shape, dt, i, True)
         absorb(kind, comm.Allgather(x, ax) if kind == "allgather" else comm.Gather(x, ax, rng.randrange(P)))
     elif kind == "scatter":
         shape = rand_shape()
@@ -70,7 +89,13 @@ for i in range(nops):
         counts = [rng.randint(0, 3) for _ in range(P)]
         root = rng.randrange(P)
         shape[ax] = sum(counts)
-        src = values(shape, dt, i) if R == root else torch.zeros(1, dtype=dt)
+        if R == root:
+            src = leaf_values(shape, dt, i, True)
+        else:  # placeholder; it takes part in the adjoint Gather, so it is a leaf like root's tensor
+            src = torch.zeros(1, dtype=dt)
+            if dt == torch.float64:
+                src.requires_grad_()
+                LEAVES.append(src)
         absorb(kind, comm.Scatter(src, ax, counts[R], root))
     elif kind == "alltoall":
         shape = [rng.randint(1, 4) for _ in range(rng.randint(2, 3))]
@@ -78,20 +103,20 @@ for i in range(nops):
         counts = [rng.randint(0, 3) for _ in range(P)]
         shape[s] = sum(counts)
         shape[g] = shape[g] + R % 2
-        absorb(kind, comm.Alltoall(values(shape, dt, i), g, s, counts[R]))
+        absorb(kind, comm.Alltoall(leaf_values(shape, dt, i, True), g, s, counts[R]))
     elif kind == "repart":
         have = [rng.randint(0, 4) for _ in range(P)]
         total = sum(have)
         cuts = sorted(rng.randint(0, total) for _ in range(P - 1))
         want = [b - a for a, b in zip([0] + cuts, cuts + [total])]
-        absorb(kind, comm.Alltoall(values([have[R], 3], dt, i), 0, 0, want[R]))
+        absorb(kind, comm.Alltoall(leaf_values([have[R], 3], dt, i, True), 0, 0, want[R]))
     elif kind == "reduce_scatter":
         uniform = rng.random() < 0.6
         counts = [rng.choice([1, 2, 5, 300]) if big else rng.randint(1, 3)] * P if uniform else [rng.randint(0, 3) for _ in range(P)]
         shape = rand_shape()
         ax = rng.randrange(len(shape))
         shape[ax] = sum(counts)
-        absorb(kind, comm.Reduce_scatter(values(shape, dt, i), m4t.MPI_SUM, ax, counts[R]))
+        absorb(kind, comm.Reduce_scatter(leaf_values(shape, dt, i, True), m4t.MPI_SUM, ax, counts[R]))
     elif kind == "ring":
         n = rng.choice([1, 17, 50000])
         tag = rng.randint(0, 50)
