@@ -29,7 +29,7 @@ def _env():
     return env
 
 
-@pytest.mark.parametrize("nprocs", [2, 5])
+@pytest.mark.parametrize("nprocs", [5])
 def test_spmd_suites_over_the_tcp_mesh(nprocs):
     res = run_spmd(nprocs, ["tests/spmd/run_all.py"], device="cpu", timeout=900, extra_env={"M4T_NET": "1"})
     assert res.returncode == 0, f"np={nprocs}\nSTDOUT:\n{res.stdout[-4000:]}\nSTDERR:\n{res.stderr[-8000:]}"
@@ -71,7 +71,7 @@ def test_hierarchical_allreduce_values_all_sizes_and_dtypes(tmp_path):
         "assert float(x.grad[0]) == P * (R + 1)\n"
         "c.Barrier()\n"
         "if R == 0: print('HIER OK', flush=True)\n")
-    for nprocs, per_node in ((6, 2), (8, 4)):
+    for nprocs, per_node in ((6, 2),):
         res = run_spmd(nprocs, [str(script)], device="cpu", timeout=600,
                        extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
         assert res.returncode == 0, res.stderr[-4000:]
@@ -130,7 +130,7 @@ def test_sub_communicators_inside_a_node_use_shared_memory(tmp_path):
         "sub2.Free(); node.Free(); rail.Free()\n"
         "c.Barrier()\n"
         "if R == 0: print('NODE SPLIT OK', flush=True)\n")
-    for nprocs in (4, 6):
+    for nprocs in (6,):
         res = run_spmd(nprocs, [str(script)], device="cpu", timeout=300, extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": "2"})
         assert res.returncode == 0, res.stderr[-4000:]
         assert "NODE SPLIT OK" in res.stdout
@@ -162,7 +162,7 @@ def test_hierarchical_reduce_scatter_uniform_counts(tmp_path):
         "c.Barrier()\n"
         "if R == 0: print(\"HIER RS OK\")\n"
     )
-    for nprocs, per_node in ((4, 2), (6, 3), (8, 2)):
+    for nprocs, per_node in ((6, 3),):
         res = run_spmd(nprocs, [str(script)], device="cpu", timeout=300,
                        extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
         assert res.returncode == 0, res.stderr[-4000:]
@@ -191,7 +191,7 @@ def test_hierarchical_allgather_uniform_lengths(tmp_path):
         "c.Barrier()\n"
         "if R == 0: print(\"HIER AG OK\", flush=True)\n"
     )
-    for nprocs, per_node in ((4, 2), (6, 3), (8, 2)):
+    for nprocs, per_node in ((8, 4),):
         res = run_spmd(nprocs, [str(script)], device="cpu", timeout=300,
                        extra_env={"M4T_NET": "1", "M4T_NET_LOCAL_SIZE": str(per_node)})
         assert res.returncode == 0, res.stderr[-4000:]
@@ -336,17 +336,18 @@ def test_hosts_option_starts_the_other_nodes_through_a_remote_shell(tmp_path):
         "c.Barrier()\n"
         "if c.rank == 2: sys.exit(7)\n"
         "c.Allreduce(torch.ones(1), m.MPI_SUM)\n")
-    res = subprocess.run(base + [str(bad)], env=_env(), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    res = subprocess.run(base + [str(bad)], env=dict(_env(), M4T_EXIT_TIMEOUT_S="2"), cwd=str(ROOT), capture_output=True,
+                         text=True, timeout=300)
     assert res.returncode != 0
 
 
-@pytest.mark.parametrize("nprocs,per_node,seed", [(4, 2, 1), (6, 3, 2), (5, 0, 4)])
+@pytest.mark.parametrize("nprocs,per_node,seed", [(4, 2, 1), (5, 0, 4)])  # more seeds / sizes: run tests/spmd/fuzz_ops.py by hand
 def test_random_operation_sequences_give_identical_results_on_every_transport(nprocs, per_node, seed):
     """tests/spmd/fuzz_ops.py: a seeded random sequence of collectives, re-partitions, rings and sub-communicators with
     exactly representable values.  Shared memory, the flat mesh, the hierarchical mode and the piece-wise slab paths
     must produce bit-identical outputs on every rank."""
     def digests(extra):
-        res = run_spmd(nprocs, ["tests/spmd/fuzz_ops.py", str(seed), "140"], device="cpu", timeout=600, extra_env=extra)
+        res = run_spmd(nprocs, ["tests/spmd/fuzz_ops.py", str(seed), "100"], device="cpu", timeout=600, extra_env=extra)
         assert res.returncode == 0, res.stderr[-4000:]
         line = [ln for ln in res.stdout.splitlines() if ln.startswith("FUZZ")]
         assert len(line) == 1, res.stdout[-2000:]
