@@ -232,7 +232,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     ap.add_argument("--master-port", type=int, default=None, help="port of the rendezvous store on node 0")
     ap.add_argument("--hosts", default=None, help="comma-separated hosts, this one first: start the other nodes' launchers "
                                                   "through --rsh (like mpirun --host)")
-    ap.add_argument("--rsh", default="ssh", help="remote shell used with --hosts (default: ssh)")
+    ap.add_argument("--hostfile", default=None, help="file with one host per line (this one first; text after the host name, "
+                                                     "e.g. 'slots=8', and #-comments are ignored) - like mpirun --hostfile")
+    ap.add_argument("--rsh", default="ssh", help="remote shell used with --hosts / --hostfile (default: ssh)")
     ap.add_argument("-m", dest="module", default=None, help="run a module (python -m) instead of a script")
     ap.add_argument("rest", nargs=argparse.REMAINDER, help="script and its arguments")
     argv = list(sys.argv[1:] if argv is None else argv)
@@ -241,10 +243,10 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     while i < len(argv):  # walk the launcher's own options; a `-m` among the script's arguments is not ours
         a = argv[i]
         if a in ("-np", "-n", "--nproc", "--timeout", "--nnodes", "--node-rank", "--master-addr", "--master-port", "--hosts",
-                 "--rsh"):
+                 "--rsh", "--hostfile"):
             i += 2
         elif a == "--tag-output" or a.startswith(("--nproc=", "--timeout=", "--nnodes=", "--node-rank=", "--master-addr=",
-                                                   "--master-port=", "--hosts=", "--rsh=")):
+                                                   "--master-port=", "--hosts=", "--rsh=", "--hostfile=")):
             i += 1
         elif a == "-m" and i + 1 < len(argv):
             # like `python -m mod args...`: everything after the module name belongs to the module, options included
@@ -262,8 +264,12 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
         if not rest:
             ap.error("no script given")
         cmd = [sys.executable] + rest if rest[0].endswith(".py") else rest
-    if args.hosts:
-        return launch_on_hosts(args.hosts.split(","), args.np, cmd, rsh=args.rsh, timeout=args.timeout, tag_output=args.tag_output,
+    hosts = args.hosts.split(",") if args.hosts else []
+    if args.hostfile:
+        with open(args.hostfile) as f:
+            hosts += [ln.split("#", 1)[0].split()[0] for ln in f if ln.split("#", 1)[0].strip()]
+    if hosts:
+        return launch_on_hosts(hosts, args.np, cmd, rsh=args.rsh, timeout=args.timeout, tag_output=args.tag_output,
                                master_port=args.master_port, master_addr=args.master_addr)
     return launch(args.np, cmd, timeout=args.timeout, tag_output=args.tag_output, nnodes=args.nnodes,
                   node_rank=args.node_rank, master_addr=args.master_addr, master_port=args.master_port)

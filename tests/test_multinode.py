@@ -326,7 +326,11 @@ def test_hosts_option_starts_the_other_nodes_through_a_remote_shell(tmp_path):
         "if c.rank == 3: print('LAST RANK OK', flush=True)\n")
     base = [sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", "--hosts", "127.0.0.1,127.0.0.1", "--rsh", str(rsh),
             "--timeout", "240"]
-    res = subprocess.run(base + [str(ok)], env=_env(), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+    hostfile = tmp_path / "hosts"
+    hostfile.write_text("127.0.0.1 slots=2  # this node\n# a comment\n127.0.0.1 slots=2\n")
+    via_file = [sys.executable, "-m", "mpi4torch_b200.launch", "-np", "2", "--hostfile", str(hostfile), "--rsh", str(rsh),
+                "--timeout", "240"]
+    res = subprocess.run(via_file + [str(ok)], env=_env(), cwd=str(ROOT), capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-4000:]
     assert "LAST RANK OK" in res.stdout  # printed by a rank of the remotely started node
     bad = tmp_path / "bad.py"
