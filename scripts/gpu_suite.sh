@@ -6,6 +6,12 @@ STAGED=""; if [ "$NP" -gt 2 ]; then STAGED="--no-staged"; fi
 OUT=gpurun_out; mkdir -p $OUT
 export PYTHONPATH=$PWD M4T_TIMEOUT_S=90 M4T_DEVICE_TIMEOUT_S=10 M4T_DEBUG_SEGV=1
 echo "=== spmd suite np=$NP"; M4T_TEST_DEVICE=cuda timeout 900 python -m mpi4torch_b200.launch -np $NP tests/spmd/run_all.py > $OUT/spmd_np$NP.log 2>&1; echo "exit=$?"; grep -v "^W0" $OUT/spmd_np$NP.log | tail -8 | cut -c1-400
+echo "=== fuzz np=$NP: device digests must equal the host digests"
+for seed in 1 2 3; do
+  D=$(M4T_TEST_DEVICE=cuda timeout 300 python -m mpi4torch_b200.launch -np $NP tests/spmd/fuzz_ops.py $seed 150 2>&1 | grep "^FUZZ")
+  H=$(M4T_CUDA=0 timeout 300 python -m mpi4torch_b200.launch -np $NP tests/spmd/fuzz_ops.py $seed 150 2>&1 | grep "^FUZZ")
+  if [ -n "$D" ] && [ "$D" = "$H" ]; then echo "seed $seed: identical"; else echo "seed $seed: DIFFERENT"; echo " device: $D"; echo " host:   $H"; fi
+done
 echo "=== bench N=$NP fused"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NP --steps 20 --warmup 5 > $OUT/bench_n$NP.log 2>&1
 echo "exit=$?"; grep -v "^W0\|^\*\*\*\|OMP_NUM" $OUT/bench_n$NP.log | tail -2 | cut -c1-2000

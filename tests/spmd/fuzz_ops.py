@@ -5,8 +5,10 @@ memory, the flat TCP mesh and the hierarchical mode).  All values are small inte
 reduction is exact and independent of the order in which a transport combines the contributions.
 
     python -m mpi4torch_b200.launch -np 4 tests/spmd/fuzz_ops.py [seed] [nops]
+    M4T_TEST_DEVICE=cuda python -m mpi4torch_b200.launch -np 4 tests/spmd/fuzz_ops.py [seed] [nops]   # same digests expected
 """
 import hashlib
+import os
 import random
 import sys
 
@@ -16,6 +18,10 @@ import mpi4torch_b200 as m4t
 
 comm = m4t.COMM_WORLD
 R, P = comm.rank, comm.size
+# M4T_TEST_DEVICE=cuda runs the same sequence on device tensors (NVLink backend): the digests must equal the CPU ones
+DEVICE = torch.device(os.environ.get("M4T_TEST_DEVICE", "cpu"))
+if DEVICE.type == "cuda":
+    DEVICE = torch.device("cuda", torch.cuda.current_device())
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 nops = int(sys.argv[2]) if len(sys.argv) > 2 else 120
 rng = random.Random(seed)  # the same stream on every rank: all ranks draw the same op sequence
@@ -27,19 +33,19 @@ def values(shape, dtype, salt):
     n = 1
     for s in shape:
         n *= s
-    return ((torch.arange(n) * 7 + salt * 3 + R * 5) % 13).reshape(shape).to(dtype)
+    return ((torch.arange(n) * 7 + salt * 3 + R * 5) % 13).reshape(shape).to(dtype).to(DEVICE)
 
 
 def absorb(name, t):
     if t.requires_grad:  # on every rank, also where the result is empty: the adjoint is a collective
         # also push a gradient through the op: the adjoint communication must agree across transports too
-        w = ((torch.arange(t.numel()) * 3 + R) % 5).reshape(t.shape).to(t.dtype)
+        w = ((torch.arange(t.numel()) * 3 + R) % 5).reshape(t.shape).to(t.dtype).to(t.device)
         leaf = LEAVES.pop()
         (t * w).sum().backward()
         g = leaf.grad if leaf.grad is not None else torch.zeros(0)
         digest.update(b"grad")
-        digest.update(g.detach().to(torch.float64).contiguous().numpy().tobytes())
-    t = t.detach().to(torch.float64).contiguous()
+        digest.update(g.detach().to(torch.float64).cpu().contiguous().numpy().tobytes())
+    t = t.detach().to(torch.float64).cpu().contiguous()
     digest.update(name.encode())
     digest.update(str(tuple(t.shape)).encode())
     digest.update(t.numpy().tobytes())
@@ -92,7 +98,7 @@ for i in range(nops):
         if R == root:
             src = leaf_values(shape, dt, i, True)
         else:  # placeholder; it takes part in the adjoint Gather, so it is a leaf like root's tensor
-            src = torch.zeros(1, dtype=dt)
+            src = torch.zeros(1, dtype=dt, device=DEVICE)
             if dt == torch.float64:
                 src.requires_grad_()
                 LEAVES.append(src)
@@ -121,7 +127,7 @@ for i in range(nops):
         n = rng.choice([1, 17, 50000])
         tag = rng.randint(0, 50)
         h = comm.Isend(values([n], dt, i), (R + 1) % P, tag)
-        y = comm.Recv(torch.empty(n, dtype=dt), (R - 1) % P, tag)
+        y = comm.Recv(torch.empty(n, dtype=dt, device=DEVICE), (R - 1) % P, tag)
         comm.Wait(h)
         absorb(kind, y)
     elif kind == "split":
@@ -130,7 +136,7 @@ for i in range(nops):
         absorb(kind, sub.Allgather(values([R % 2 + 1, 2], dt, i), 0))
         sub.Free()
 
-mine = torch.tensor(list(digest.digest()[:8]), dtype=torch.int64)
+mine = torch.tensor(list(digest.digest()[:8]), dtype=torch.int64)  # host tensor on every transport
 every = comm.Allgather(mine, 0).reshape(P, 8)
 if R == 0:
     print("FUZZ seed", seed, "np", P, "digests", [bytes(row.tolist()).hex() for row in every], flush=True)
