@@ -60,29 +60,39 @@ class NodeRails:
         self.rail.Free()
 
 
-def hierarchical_allreduce(x: torch.Tensor, rails: NodeRails, op: int = m4t.MPI_SUM, scale: Optional[float] = None) -> torch.Tensor:
+def _rail_allreduce(part: torch.Tensor, rails: NodeRails, op: int, scale: Optional[float],
+                    rail_dtype: Optional[torch.dtype]) -> torch.Tensor:
+    wire = part if rail_dtype is None or rail_dtype == part.dtype else part.to(rail_dtype)
+    red = rails.rail.Allreduce(wire, op) if scale is None else rails.rail.AllreduceFused(wire, op, float(scale), None)
+    return red if red.dtype == part.dtype else red.to(part.dtype)
+
+
+def hierarchical_allreduce(x: torch.Tensor, rails: NodeRails, op: int = m4t.MPI_SUM, scale: Optional[float] = None,
+                           rail_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """``scale * Allreduce(x, op)`` over ``rails.comm`` as ``node.Reduce_scatter -> rail.Allreduce -> node.Allgather``.
 
     Differentiable for ``MPI_SUM`` (like ``Allreduce``).  The tensor is flattened and padded to a multiple of the node
-    size; the result has the shape of ``x``.
+    size; the result has the shape of ``x``.  ``rail_dtype`` (e.g. ``torch.bfloat16`` for fp32 gradients) is the dtype
+    the node-level partial sums cross the network in: half the bytes on the slow level, full precision inside the node;
+    the gradient takes the same route.
     """
     L = rails.per_node
     flat = x.reshape(-1)
     n = flat.numel()
     if L == 1:
-        red = rails.rail.Allreduce(flat, op) if scale is None else rails.rail.AllreduceFused(flat, op, float(scale), None)
-        return red.reshape(x.shape)
+        return _rail_allreduce(flat, rails, op, scale, rail_dtype).reshape(x.shape)
     per = (n + L - 1) // L
     if per * L != n:
         flat = torch.cat([flat, flat.new_zeros(per * L - n)])
     part = rails.node.Reduce_scatter(flat, op, 0, per)
-    part = rails.rail.Allreduce(part, op) if scale is None else rails.rail.AllreduceFused(part, op, float(scale), None)
+    part = _rail_allreduce(part, rails, op, scale, rail_dtype)
     full = rails.node.Allgather(part, 0)
     return full[:n].reshape(x.shape)
 
 
 @torch.no_grad()
-def hierarchical_sync_gradients_(params, rails: NodeRails, average: bool = True) -> None:
+def hierarchical_sync_gradients_(params, rails: NodeRails, average: bool = True,
+                                 rail_dtype: Optional[torch.dtype] = None) -> None:
     """DDP-style in-place gradient synchronisation through :func:`hierarchical_allreduce` (one bucket per dtype/device)."""
     by_key = {}
     for p in params:
@@ -90,7 +100,7 @@ def hierarchical_sync_gradients_(params, rails: NodeRails, average: bool = True)
             by_key.setdefault((p.grad.dtype, p.grad.device), []).append(p)
     for group in by_key.values():
         flat = torch.cat([p.grad.reshape(-1) for p in group])
-        red = hierarchical_allreduce(flat, rails, m4t.MPI_SUM, 1.0 / rails.comm.size if average else None)
+        red = hierarchical_allreduce(flat, rails, m4t.MPI_SUM, 1.0 / rails.comm.size if average else None, rail_dtype)
         off = 0
         for p in group:
             k = p.grad.numel()

@@ -393,6 +393,14 @@ class TestNodeRails(unittest.TestCase):
         self.assertEqual(z.tolist(), [P - 1.0] * 4)
         s = hierarchical_allreduce(torch.ones(6, dtype=DT, device=DEVICE), rails, m4t.MPI_SUM, scale=1.0 / P)
         self.assertTrue(torch.allclose(s, torch.ones(6, dtype=DT, device=DEVICE)))
+        # node-level partial sums cross the network in bf16: result and gradient keep the input dtype, values to bf16 accuracy
+        x32 = (torch.arange(10, dtype=torch.float32) + R).to(DEVICE).requires_grad_()
+        y32 = hierarchical_allreduce(x32, rails, rail_dtype=torch.bfloat16)
+        self.assertEqual(y32.dtype, torch.float32)
+        self.assertTrue(torch.allclose(y32, comm.Allreduce(x32.detach(), m4t.MPI_SUM), rtol=2 ** -6, atol=0))
+        y32.sum().backward()
+        self.assertEqual(x32.grad.dtype, torch.float32)
+        self.assertTrue(torch.allclose(x32.grad, torch.full_like(x32, float(P)), rtol=2 ** -6, atol=0))
         rails.free()
 
     def test_hierarchical_gradient_sync_matches_the_flat_one(self):
