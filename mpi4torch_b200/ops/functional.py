@@ -41,11 +41,13 @@ def allreduce_sgd_step_(param: torch.Tensor, local_grad: torch.Tensor, lr: float
     return param
 
 
-def average_parameters_flat(params: Iterable[torch.Tensor], comm=None) -> List[torch.Tensor]:
+def average_parameters_flat(params: Iterable[torch.Tensor], comm=None, rails=None) -> List[torch.Tensor]:
     """Average a parameter list across ranks with ONE bucketed allreduce per
     dtype (launch-latency bound otherwise); differentiable, so the gradient
-    synchronisation falls out of the adjoint."""
-    c = _comm(comm)
+    synchronisation falls out of the adjoint.  With ``rails``
+    (:class:`mpi4torch_b200.parallel.NodeRails`) the allreduce is the two-level
+    composition node.Reduce_scatter -> rail.Allreduce -> node.Allgather."""
+    c = _comm(comm) if rails is None else rails.comm
     params = list(params)
     out: List[Optional[torch.Tensor]] = [None] * len(params)
     by_key = {}
@@ -53,7 +55,12 @@ def average_parameters_flat(params: Iterable[torch.Tensor], comm=None) -> List[t
         by_key.setdefault((p.dtype, p.device), []).append(i)
     for idxs in by_key.values():
         flat = torch.cat([params[i].reshape(-1) for i in idxs])
-        avg = c.AllreduceFused(flat, m4t.MPI_SUM, 1.0 / c.size, None)
+        if rails is not None:
+            from mpi4torch_b200.parallel.hierarchical import hierarchical_allreduce
+
+            avg = hierarchical_allreduce(flat, rails, m4t.MPI_SUM, 1.0 / c.size)
+        else:
+            avg = c.AllreduceFused(flat, m4t.MPI_SUM, 1.0 / c.size, None)
         off = 0
         for i in idxs:
             n = params[i].numel()

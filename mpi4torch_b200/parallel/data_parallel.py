@@ -20,14 +20,17 @@ class DataParallel(torch.nn.Module):
     forward, one backward) with the ``1/size`` fused into the kernel epilogue.
     """
 
-    def __init__(self, module: torch.nn.Module, comm=None):
+    def __init__(self, module: torch.nn.Module, comm=None, rails=None):
         super().__init__()
         self.module = module
-        self.comm = m4t.COMM_WORLD if comm is None else comm
+        # rails (parallel.NodeRails): average through the two-level composition - NVLink / shared memory inside the node,
+        # 1/L of the parameters per rank across nodes - instead of one flat Allreduce over `comm`
+        self.rails = rails
+        self.comm = (m4t.COMM_WORLD if comm is None else comm) if rails is None else rails.comm
 
     def forward(self, *args, **kwargs):
         names, params = zip(*self.module.named_parameters()) if any(True for _ in self.module.parameters()) else ((), ())
-        averaged = average_parameters_flat(params, self.comm)
+        averaged = average_parameters_flat(params, self.comm, self.rails)
         return functional_call(self.module, dict(zip(names, averaged)), args, kwargs)
 
 

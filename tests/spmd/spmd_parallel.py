@@ -403,6 +403,25 @@ class TestNodeRails(unittest.TestCase):
         self.assertTrue(torch.allclose(x32.grad, torch.full_like(x32, float(P)), rtol=2 ** -6, atol=0))
         rails.free()
 
+    def test_data_parallel_wrapper_over_rails_matches_the_flat_wrapper(self):
+        from mpi4torch_b200.parallel import NodeRails
+
+        rails = NodeRails(comm, per_node=self._per_node())
+        torch.manual_seed(9)
+        flat_net = DataParallel(torch.nn.Linear(5, 3).to(DT).to(DEVICE), comm)
+        rail_net = DataParallel(torch.nn.Linear(5, 3).to(DT).to(DEVICE), rails=rails)
+        rail_net.module.load_state_dict(flat_net.module.state_dict())
+        g = torch.Generator().manual_seed(200 + R)
+        x = torch.randn(7, 5, generator=g, dtype=DT).to(DEVICE)
+        la = flat_net(x).square().sum()
+        lb = rail_net(x).square().sum()
+        self.assertTrue(torch.allclose(la, lb, rtol=1e-12, atol=1e-12))
+        la.backward()
+        lb.backward()
+        for pa, pb in zip(flat_net.module.parameters(), rail_net.module.parameters()):
+            self.assertTrue(torch.allclose(pa.grad, pb.grad, rtol=1e-11, atol=1e-12))
+        rails.free()
+
     def test_hierarchical_gradient_sync_matches_the_flat_one(self):
         from mpi4torch_b200.parallel import NodeRails, hierarchical_sync_gradients_
 
