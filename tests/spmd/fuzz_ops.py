@@ -4,7 +4,7 @@ Every transport must print the same lines for the same seed and world size (test
 memory, the flat TCP mesh and the hierarchical mode).  All values are small integers stored in the chosen dtype, so every
 reduction is exact and independent of the order in which a transport combines the contributions.
 
-    python -m mpi4torch_b200.launch -np 4 tests/spmd/fuzz_ops.py [seed] [nops]
+    python -m mpi4torch_b200.launch -np 4 tests/spmd/fuzz_ops.py [seed] [nops] [share of large ops]
     M4T_TEST_DEVICE=cuda python -m mpi4torch_b200.launch -np 4 tests/spmd/fuzz_ops.py [seed] [nops]   # same digests expected
 """
 import hashlib
@@ -24,6 +24,7 @@ if DEVICE.type == "cuda":
     DEVICE = torch.device("cuda", torch.cuda.current_device())
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 nops = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+big_share = float(sys.argv[3]) if len(sys.argv) > 3 else 0.15  # share of operations with a large dimension
 rng = random.Random(seed)  # the same stream on every rank: all ranks draw the same op sequence
 DTYPES = [torch.float64, torch.float32, torch.int64, torch.int32, torch.bfloat16]
 digest = hashlib.sha256()
@@ -66,7 +67,7 @@ def rand_shape(axis_len=None, big=False):
     nd = rng.randint(1, 3)
     shape = [rng.randint(1, 5) for _ in range(nd)]
     if big:
-        shape[rng.randrange(nd)] = rng.choice([1000, 4099, 30011])
+        shape[rng.randrange(nd)] = rng.choice([1000, 4099, 30011, 250007])
     return shape
 
 
@@ -74,7 +75,7 @@ for i in range(nops):
     kind = rng.choice(["allreduce", "allreduce", "bcast", "reduce", "gather", "allgather", "scatter", "alltoall", "repart",
                        "reduce_scatter", "ring", "split"])
     dt = rng.choice(DTYPES)
-    big = rng.random() < 0.15
+    big = rng.random() < big_share
     if kind == "allreduce":
         op = rng.choice([m4t.MPI_SUM, m4t.MPI_MAX, m4t.MPI_MIN])
         absorb(kind, comm.Allreduce(leaf_values(rand_shape(big=big), dt, i, op == m4t.MPI_SUM), op))
